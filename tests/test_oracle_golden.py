@@ -1,0 +1,91 @@
+"""Pin the CPU oracle (oracle/srgpt_oracle.py) against the committed golden fixtures, which were
+produced by the REFERENCE's own modules (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import srgpt_oracle as O
+from tests.golden.make_golden import CASES
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _close(a, b, rtol=2e-4, atol=2e-5):
+    a, b = a.float(), b.float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference_pipeline(golden_dir, name):
+    kw, n_regions, t_text, kind, n_new, depth_on = CASES[name]
+    g = _load(golden_dir, name)
+    cfg = O.OracleConfig(**kw)
+    weights = O.make_weights(cfg, seed=int(g["weight_seed"]))
+    input_ids, images, depths, masks = O.synth_request(cfg, n_regions, t_text, seed=1234, kind=kind)
+    # the synthetic request itself must be reproducible (it is regenerated on the GPU box)
+    assert torch.equal(input_ids, g["input_ids"])
+    _close(images, g["images"], 0, 0)
+    _close(masks[0], g["masks"], 0, 0)
+    if not depth_on:
+        depths = None
+    ids, enc = O.generate(cfg, weights, input_ids, images, depths, masks, n_new, return_all=True)
+    _close(enc["tower_features"], g["tower_features"])
+    _close(enc["hres"], g["hres"])
+    _close(enc["lres"], g["lres"])
+    _close(enc["mask_embeds"][0], g["mask_embeds"])
+    if depth_on:
+        _close(enc["depth_features"], g["depth_features"])
+        _close(enc["depth_embeds"][0], g["depth_embeds"])
+    _close(enc["image_features"], g["image_features"])
+    _close(enc["inputs_embeds"], g["inputs_embeds"][0])
+    _close(enc["logits"], g["logits"], rtol=1e-3, atol=1e-4)
+    assert ids.tolist() == g["new_ids"].tolist()
+
+
+@pytest.mark.parametrize("tag", ["rgb448", "depth448", "rgb384", "odd336"])
+def test_mask_pooling_kats(golden_dir, tag):
+    g = _load(golden_dir, "op_kats")
+    x = g[f"{tag}_x"]
+    masks = g[f"{tag}_masks"].float()
+    out32 = O.mask_pooling(x.float(), [masks])[0]
+    _close(out32, g[f"{tag}_out_f32"], rtol=1e-5, atol=1e-6)
+    out16 = O.mask_pooling(x.to(torch.bfloat16), [masks])[0]
+    assert out16.dtype == torch.bfloat16
+    assert torch.equal(out16.float(), g[f"{tag}_out_bf16"])  # bit-exact: same torch ops, same roundings
+    assert O.mask_pooling(x.float(), [None]) == [None]
+    assert O.mask_pooling(x.float(), None) == [None]
+
+
+def test_downsample_and_ln2d_kats(golden_dir):
+    g = _load(golden_dir, "op_kats")
+    assert torch.equal(O.downsample_block(g["downsample_x"]), g["downsample_out"])
+    _close(O.layernorm2d(g["ln2d_x"], g["ln2d_w"], g["ln2d_b"]), g["ln2d_out"], 1e-6, 1e-6)
+
+
+def test_bf16_mode_tracks_fp32():
+    """The rounding-faithful bf16 mode stays within bf16 noise of the fp32 ground truth."""
+    kw = CASES["tiny_boxes"][0]
+    cfg = O.OracleConfig(**kw)
+    w = O.make_weights(cfg, seed=3)
+    ids, im, de, ma = O.synth_request(cfg, 2, 24, kind="box")
+    a = O.encode_multimodal(cfg, w, im, de, ma, torch.float32)
+    b = O.encode_multimodal(cfg, w, im, de, ma, torch.bfloat16)
+    for k in ("tower_features", "image_features"):
+        ref = a[k].float()
+        err = (b[k].float() - ref).abs().max() / ref.abs().max()
+        assert err < 0.05, (k, err)
+
+
+def test_depth_to_u8x3():
+    d = torch.linspace(0, 1, 12).view(1, 3, 4)
+    out = O.depth_to_u8x3(d, 6, 8)
+    assert out.shape == (6, 8, 3) and out.dtype == torch.uint8
+    assert out.min() == 0 and out.max() == 255
+    assert torch.equal(out[..., 0], out[..., 2])
