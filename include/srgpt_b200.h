@@ -1,0 +1,150 @@
+/* srgpt_b200 — C-ABI of the B200 (sm_100a) kernels behind SpatialRGPT's multimodal generate() path.
+ *
+ * The reference (AnjieCheng/SpatialRGPT) has no FFI / plugin layer: every op below replaces a
+ * PyTorch library call on the path  LlavaLlamaModel.generate -> prepare_inputs_labels_for_multimodal
+ * -> llm.generate  (llava/model/language_model/llava_llama.py:194-213).  Each entry cites the
+ * reference call site it replaces (paths relative to the reference checkout;
+ * "modeling_llama.py" = llava/train/transformers_replace/models/llama/modeling_llama.py).
+ *
+ * Conventions
+ *   - plain C: device pointers as void*, sizes as int / long long, CUDA stream as void* (cudaStream_t).
+ *   - all tensors are row-major; "bf16" means __nv_bfloat16; strides (ld*) are in ELEMENTS.
+ *   - every function is asynchronous on `stream`, allocates nothing, and returns 0 on success or a
+ *     negative srgpt error code; the message is available from srgpt_last_error().  Nothing throws.
+ *   - callable from any host thread; no global state except the last-error string (thread-local).
+ */
+#ifndef SRGPT_B200_H_
+#define SRGPT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRGPT_ABI_VERSION 1
+
+/* ---- library -------------------------------------------------------------------------------- */
+int srgpt_abi_version(void);
+const char* srgpt_last_error(void);
+/* sm count + compute capability of the current device; fails (<0) unless it is sm_100. */
+int srgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense GEMM on tcgen05/TMEM (gemm_tcgen05.cu) --------------------------------------------
+ * C[M,N] = epilogue(A[M,K] · W[N,K]^T), bf16 in, fp32 accumulate.  W is the nn.Linear weight as
+ * stored ([out, in]).  Replaces every F.linear / Conv2d(k=s) / ConvTranspose2d(k=s) on the path:
+ * SigLIP q/k/v/out/fc1/fc2 (HF SiglipVisionModel, call site vision_encoder.py:119-130),
+ * deconv refinement (base_extractor.py:92-97), rgb/depth projectors (base_extractor.py:158),
+ * mm_projector (base_projector.py:76-79), Llama q/k/v/o/gate/up/down at prefill
+ * (modeling_llama.py:429-431,498,221). */
+enum {
+  SRGPT_EPI_NONE = 0,           /* C = acc                                                        */
+  SRGPT_EPI_BIAS = 1,           /* C = acc + bias[n]                                              */
+  SRGPT_EPI_BIAS_GELU_TANH = 2, /* C = gelu_tanh(bf16(acc + bias))   (SigLIP fc1)                 */
+  SRGPT_EPI_BIAS_GELU_ERF = 3,  /* C = gelu_erf(bf16(acc + bias))    (deconv #2, mm_projector)    */
+  SRGPT_EPI_BIAS_RESIDUAL = 4,  /* C = bf16(acc + bias) + residual[row (% res_row_mod), n]        */
+  SRGPT_EPI_SWIGLU = 5          /* W rows interleaved (gate_i, up_i): C[:, i] = silu(g) * u; C has N/2 cols */
+};
+int srgpt_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                    const void* bias /*bf16[N] or NULL*/, const void* residual /*bf16 or NULL*/, int ldr,
+                    int res_row_mod /*0 = none*/, int epilogue, int out_fp32, void* stream);
+
+/* ---- row-wise normalisation / elementwise (rowops.cu) ----------------------------------------
+ * LayerNorm over the last dim, fp32 statistics, bf16 in/out.  act: 0 none, 1 GELU(erf) applied to
+ * the bf16-rounded LN output.  Replaces nn.LayerNorm in SigLIP (eps 1e-6) and LayerNorm2d + GELU
+ * (base_extractor.py:12-24,93-95; our activations are pixel-major so LN2d is a row LayerNorm). */
+int srgpt_layernorm_bf16(const void* x, int ldx, const void* weight, const void* bias, void* y, int ldy, int rows,
+                         int cols, float eps, int act, void* stream);
+/* mm_projector front end (base_projector.py:32-52,75): DownSampleBlock (zero-pad side->even,
+ * 2x2 token merge, the reference's transposed output order) fused with LayerNorm(4C).
+ * x: [n_img, side*side, C] -> y: [n_img, ceil(side/2)^2, 4C]. */
+int srgpt_downsample_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int n_img, int side,
+                                    int C, float eps, void* stream);
+/* LlamaRMSNorm (modeling_llama.py:70-75): y = weight * bf16(x * rsqrt(mean(x^2) + eps)). */
+int srgpt_rmsnorm_bf16(const void* x, int ldx, const void* weight, void* y, int ldy, int rows, int cols, float eps,
+                       void* stream);
+/* SigLIP patch embedding front end: Conv2d(3, D, k=14, s=14) == GEMM over this im2col
+ * (HF SiglipVisionEmbeddings; call site siglip_encoder.py:11-16).  images: [n, 3, R, R] fp32 or
+ * bf16 (src_is_bf16) -> A: [n*(R/ps)^2, ldk] bf16, column = c*ps*ps + ky*ps + kx, zero padded to ldk. */
+int srgpt_patchify_bf16(const void* images, int src_is_bf16, void* A, int n, int R, int ps, int ldk, void* stream);
+/* Embedding splice (llava_arch.py:434-539): out[r,:] = src[src_id[r]][src_row[r],:] for the four
+ * sources (0 = token embedding table, 1 = image features, 2 = mask embeds, 3 = depth embeds).
+ * The (src_id,src_row) plan is built on the host from input_ids. */
+int srgpt_splice_rows_bf16(const void* src0, const void* src1, const void* src2, const void* src3, const int* src_id,
+                           const int* src_row, void* out, int rows, int cols, void* stream);
+
+/* ---- region extractor HBM kernels (region.cu) -------------------------------------------------
+ * MaskPooling weights (base_extractor.py:52-72): bilinear (align_corners=False, no antialias)
+ * resample of masks [n_img, M, IH, IW] to the feature grid (side x side), cast to bf16, divide by
+ * bf16(sum + 1e-8).  w: [n_img, M, side*side] bf16 in the feature tensor's row order:
+ * order = 0 row-major (y*side+x); order = 2 the 2-level 2x2-nested order the deconv GEMMs produce
+ * (see DESIGN.md "hres layout").  rscale = (float)(1.0 / scale_factor) exactly as ATen computes it. */
+int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, int n_img, int M, int IH, int IW, int side,
+                       float rscale, int order, void* stream);
+/* Mask pooling proper (base_extractor.py:74-78): out[i,m,:] = sum_l w[i,m,l] * x[i,l,:].
+ * x: [n_img, L, C] bf16 streamed once; partial: fp32 workspace of srgpt_mask_pool_workspace() bytes. */
+long long srgpt_mask_pool_workspace(int n_img, int M, int L, int C);
+int srgpt_mask_pool_bf16(const void* x, const void* w, void* out, void* workspace, int n_img, int M, int L, int C,
+                         void* stream);
+/* AdaptiveAvgPool2d(out_side) over the (side x side) feature map (base_extractor.py:123,145).
+ * x: [n_img, side*side, C] in `order` (as above) -> y: [n_img, out_side*out_side, C] row-major. */
+int srgpt_adaptive_avgpool_bf16(const void* x, void* y, int n_img, int side, int out_side, int C, int order,
+                                void* stream);
+/* Row permutation between the nested order and row-major (tests / API parity for `hres`). */
+int srgpt_reorder_rows_bf16(const void* x, void* y, int n_img, int side, int C, int from_order, int to_order,
+                            void* stream);
+/* Depth map preparation (llava/eval/eval_spatial.py:99-105): bilinear resize of depth [h, w] fp32 to
+ * (H, W), min-max normalise * 255, truncate to u8, replicate to 3 channels -> out [H, W, 3] u8.
+ * workspace: (H*W + 2) floats. */
+int srgpt_depth_to_u8x3(const void* depth, int h, int w, void* out, int H, int W, void* workspace, void* stream);
+
+/* ---- attention (attention.cu) ------------------------------------------------------------------
+ * Prefill attention, softmax in fp32, flash-style (no S x S matrix in HBM).
+ * Replaces SigLIP's eager attention (non-causal, head_dim 72) and flash_attn_func(causal=True) with
+ * GQA (modeling_llama.py:564-566).  q/k/v/out rows are tokens; head h of a row starts at h*head_dim.
+ * Sequences are `batch` equal-length segments of `seqlen` consecutive rows. */
+int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld,
+                                 int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
+                                 int causal, void* stream);
+/* RoPE + KV-cache append for `rows` new tokens of one sequence (modeling_llama.py:448-456):
+ * rotates q and k in place inside the fused qkv buffer [rows, (nh + 2*nkv)*hd] using the bf16
+ * cos/sin tables [max_pos, hd/2], and writes k, v into the paged cache.
+ * Cache layout: pages [n_pages, 2 (k,v), page_size, nkv, hd] bf16 for ONE layer; page_table[i] =
+ * physical page of logical page i of this sequence.  start_pos: device int (position of row 0). */
+int srgpt_rope_kv_append_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
+                              const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_table,
+                              int page_size, void* stream);
+/* Decode attention for ONE new token over the paged cache (replaces torch.cat of the cache +
+ * flash_attn_func with q_len 1, modeling_llama.py:451-456,564).  q: [nh*hd] bf16 (already rotated),
+ * kv_len_minus1: device int = position of the new token (its k/v are already in the cache). */
+int srgpt_attention_decode_bf16(const void* q, void* out, const void* kv_pages, const int* page_table, int page_size,
+                                const int* kv_len_minus1, int n_heads, int n_kv_heads, int head_dim, float scale,
+                                void* stream);
+
+/* ---- decode-time weight-streaming kernels (gemv.cu) -------------------------------------------
+ * One token: y = W · x with W [N, K] bf16 streamed once from HBM (the decode roofline).
+ *   norm_weight != NULL : x is first RMS-normalised (LlamaRMSNorm) inside the kernel.
+ *   mode SRGPT_GEMV_PLAIN    : y[n] = bf16(acc) (+ residual[n])            (o_proj, down_proj)
+ *   mode SRGPT_GEMV_SWIGLU   : W rows interleaved (gate_i, up_i); y[i] = silu(g)*u   (gate/up)
+ *   mode SRGPT_GEMV_QKV_ROPE : W = fused [q;k;v]; rotates q,k at *pos with the cos/sin tables, writes
+ *                              q to y [nh*hd] and appends k,v to the paged cache      (q/k/v_proj + RoPE)
+ * Replaces modeling_llama.py:429-431,448-456,498,221 at q_len == 1. */
+enum { SRGPT_GEMV_PLAIN = 0, SRGPT_GEMV_SWIGLU = 1, SRGPT_GEMV_QKV_ROPE = 2 };
+int srgpt_gemv_bf16(const void* x, const void* W, int ldw, void* y, int N, int K, const void* norm_weight, float eps,
+                    const void* residual, int mode,
+                    /* QKV_ROPE only: */ int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
+                    const void* sin_tab, const int* pos, void* kv_pages, const int* page_table, int page_size,
+                    void* stream);
+/* Final norm + lm_head + greedy argmax (modeling_llama.py:922,1044-1045 + HF greedy search):
+ * logits = float(bf16(W · rmsnorm(x))); writes argmax (lowest index on ties) to out_ids[*step],
+ * copies the chosen token's embedding row to next_x, then ++*step and ++*pos.
+ * logits_out (fp32 [V]) may be NULL.  workspace: srgpt_lm_head_workspace(V) bytes. */
+long long srgpt_lm_head_workspace(int V);
+int srgpt_lm_head_argmax_bf16(const void* x, const void* W, int ldw, int V, int K, const void* norm_weight, float eps,
+                              float* logits_out, void* workspace, const void* embed_table, void* next_x,
+                              long long* out_ids, int* step, int* pos, void* stream);
+/* Plain argmax over fp32 rows (first index on ties), e.g. first token after prefill. */
+int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGPT_B200_H_ */

@@ -1,0 +1,101 @@
+"""ctypes binding of libsrgpt_b200.so (the C-ABI declared in include/srgpt_b200.h).
+
+There is deliberately NO fallback: if the shared library cannot be built/loaded, or a kernel
+returns an error, a ``SrgptError`` is raised.  Nothing in this package computes on the CPU or
+through torch operators on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SrgptError(RuntimeError):
+    pass
+
+
+vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes); mirrors include/srgpt_b200.h one to one
+SIGNATURES = {
+    "srgpt_abi_version": (ci, []),
+    "srgpt_last_error": (C.c_char_p, []),
+    "srgpt_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
+    "srgpt_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
+    "srgpt_layernorm_bf16": (ci, [vp, ci, vp, vp, vp, ci, ci, ci, cf, ci, vp]),
+    "srgpt_downsample_layernorm_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, vp]),
+    "srgpt_rmsnorm_bf16": (ci, [vp, ci, vp, vp, ci, ci, ci, cf, vp]),
+    "srgpt_patchify_bf16": (ci, [vp, ci, vp, ci, ci, ci, ci, vp]),
+    "srgpt_splice_rows_bf16": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
+    "srgpt_mask_weights": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, cf, ci, vp]),
+    "srgpt_mask_pool_workspace": (cll, [ci, ci, ci, ci]),
+    "srgpt_mask_pool_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "srgpt_adaptive_avgpool_bf16": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),
+    "srgpt_reorder_rows_bf16": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),
+    "srgpt_depth_to_u8x3": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
+    "srgpt_attention_prefill_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp]),
+    "srgpt_rope_kv_append_bf16": (ci, [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci, vp]),
+    "srgpt_attention_decode_bf16": (ci, [vp, vp, vp, vp, ci, vp, ci, ci, ci, cf, vp]),
+    "srgpt_gemv_bf16": (ci, [vp, vp, ci, vp, ci, ci, vp, cf, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci, vp]),
+    "srgpt_lm_head_workspace": (cll, [ci]),
+    "srgpt_lm_head_argmax_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
+}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the .so is missing/stale and nvcc is present) and type the library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if build_if_missing and _build.is_stale():
+            try:
+                _build.build(verbose=False)
+            except Exception as e:  # stale-but-present is still loadable; missing is fatal
+                if not os.path.exists(path):
+                    raise SrgptError(f"libsrgpt_b200.so is missing and could not be built: {e}") from e
+        if not os.path.exists(path):
+            raise SrgptError(f"{path} not found; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        try:
+            import torch  # noqa: F401  (loads libcudart.so.12 that the library links against)
+        except Exception:
+            pass
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise SrgptError(f"{path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.srgpt_abi_version() != 1:
+            raise SrgptError("ABI version mismatch between _lib.py and libsrgpt_b200.so")
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    return (load().srgpt_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SrgptError(f"{what} failed with code {rc}: {last_error()}")
+
+
+def device_info():
+    sm, maj, mnr = ci(0), ci(0), ci(0)
+    check(load().srgpt_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "srgpt_device_info")
+    return sm.value, maj.value, mnr.value

@@ -1,0 +1,54 @@
+// Library-level entry points of the srgpt C-ABI: version, last error, device info.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "srgpt_b200.h"
+
+namespace srgpt {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;  // B200
+  }
+  return cached;
+}
+
+}  // namespace srgpt
+
+using namespace srgpt;
+
+extern "C" __attribute__((visibility("default"))) int srgpt_abi_version(void) { return SRGPT_ABI_VERSION; }
+
+extern "C" __attribute__((visibility("default"))) const char* srgpt_last_error(void) { return g_last_error; }
+
+extern "C" __attribute__((visibility("default"))) int srgpt_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {
+  int dev = 0, n = 0, maj = 0, mnr = 0;
+  SRGPT_CHECK_CUDA(cudaGetDevice(&dev));
+  SRGPT_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  SRGPT_CHECK_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  SRGPT_CHECK_CUDA(cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count_out) *sm_count_out = n;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = mnr;
+  if (maj != 10) {
+    set_last_error("srgpt_b200 kernels are built for sm_100a only; device is sm_%d%d", maj, mnr);
+    return SRGPT_ERR_UNSUPPORTED;
+  }
+  return SRGPT_OK;
+}

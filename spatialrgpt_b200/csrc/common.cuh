@@ -1,0 +1,112 @@
+// Shared device/host helpers for the sm_100a kernels behind the srgpt C-ABI (include/srgpt_b200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace srgpt {
+
+// ---- host-side error plumbing: every extern "C" entry returns 0 or a negative code, never throws
+enum : int {
+  SRGPT_OK = 0,
+  SRGPT_ERR_INVALID = -1,   // bad argument (shape / alignment / null)
+  SRGPT_ERR_CUDA = -2,      // CUDA runtime / driver error (see srgpt_last_error)
+  SRGPT_ERR_UNSUPPORTED = -3,
+};
+
+void set_last_error(const char* fmt, ...);
+
+#define SRGPT_CHECK_ARG(cond)                                                              \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      ::srgpt::set_last_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond);   \
+      return ::srgpt::SRGPT_ERR_INVALID;                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define SRGPT_CHECK_CUDA(expr)                                                             \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::srgpt::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                \
+                              cudaGetErrorString(_e));                                     \
+      return ::srgpt::SRGPT_ERR_CUDA;                                                      \
+    }                                                                                      \
+  } while (0)
+
+#define SRGPT_CHECK_LAUNCH() SRGPT_CHECK_CUDA(cudaGetLastError())
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int sm_count();  // cached multiProcessorCount of the current device
+
+// ---- device helpers
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 8 bf16 (one 16-byte vector) -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]);
+  v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]);
+  v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// streaming 16-byte load that does not allocate in L1 (weights / features read exactly once)
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; `red` is >= 32 floats of shared memory; every thread gets the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+}  // namespace srgpt

@@ -1,0 +1,460 @@
+// Dense bf16 GEMM for sm_100a: C[M,N] = epilogue(A[M,K] · W[N,K]^T), fp32 accumulation in TMEM.
+//
+// This is the tensor-core core of the prefill path (SURVEY.md §2c K1,K3,K5,K6,K8,K9,K12,K13,K16,
+// K20,K21): every nn.Linear / Conv2d(k=s) / ConvTranspose2d(k=s) the reference runs through
+// cuBLAS/cuDNN (e.g. modeling_llama.py:429-431,498,221; base_extractor.py:92-97,158;
+// base_projector.py:76-79) is one instantiation of this kernel with a fused epilogue.
+//
+// Design (Blackwell-native, no library code):
+//   * persistent kernel, one CTA per SM, static round-robin over 128x128 output tiles;
+//   * warp 0  : TMA producer  (cp.async.bulk.tensor 2D, 128B-swizzled K-major boxes, 6-stage ring);
+//   * warp 1  : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM;
+//   * warps 2-5: epilogue (tcgen05.ld 32x32b -> registers -> fused bias/activation/residual ->
+//                 16-byte global stores); overlaps the next tile's main loop.
+//   * mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// Out-of-bounds rows/cols/K are zero-filled by TMA, so M, N need no padding and K only has to
+// be a multiple of 8 elements (16-byte global strides).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "srgpt_b200.h"
+
+namespace srgpt {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 6;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_BUFS = 2;
+constexpr int TMEM_COLS = ACC_BUFS * BN;  // 256 (power of two >= 32)
+constexpr int NUM_THREADS = 192;           // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();  // deadlock breaker: turns a hang into a launch error
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; single-CTA, kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (ignored for swizzled K-major; 1) | [32,46) SBO>>4 (8 rows * 128 B)
+//   [46,48) version=1 | [61,64) layout_type=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__device__ __forceinline__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Params {
+  int M, N, K;
+  int ldc;                 // elements
+  const bf16* bias;        // [N] or null
+  const bf16* residual;    // [*, ldr] or null
+  int ldr;
+  int res_row_mod;         // >0: residual row = row % res_row_mod (broadcast position embeddings)
+  void* C;
+  int epilogue;
+  int out_fp32;
+};
+
+template <int EPI>
+__device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, const Params& p, int row, int col0) {
+  // v[j] is the fp32 accumulator of column col0 + j.  Rounding points mirror the reference's
+  // sequence of bf16 torch ops (linear -> activation -> residual add), see DESIGN.md.
+  if (EPI == SRGPT_EPI_NONE) return;
+  if (EPI == SRGPT_EPI_SWIGLU) return;  // handled by the caller (pairs of columns)
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (col0 + j + 8 <= p.N) {
+        uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
+        float f[8];
+        unpack8(b, f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[j + t] += f[t];
+      } else {
+        for (int t = 0; t < 8; ++t)
+          if (col0 + j + t < p.N) v[j + t] += __bfloat162float(p.bias[col0 + j + t]);
+      }
+    }
+  }
+  if (EPI == SRGPT_EPI_BIAS_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(bf16_round(v[j]));
+  } else if (EPI == SRGPT_EPI_BIAS_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(bf16_round(v[j]));
+  } else if (EPI == SRGPT_EPI_BIAS_RESIDUAL) {
+    if (p.residual != nullptr) {
+      const int rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+      const bf16* rp = p.residual + (size_t)rrow * p.ldr + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (col0 + j + 8 <= p.N) {
+          uint4 b = *reinterpret_cast<const uint4*>(rp + j);
+          float f[8];
+          unpack8(b, f);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[j + t] = bf16_round(v[j + t]) + f[t];
+        } else {
+          for (int t = 0; t < 8; ++t)
+            if (col0 + j + t < p.N) v[j + t] = bf16_round(v[j + t]) + __bfloat162float(rp[j + t]);
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned stage buffers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [ACC_BUFS]
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_BUFS;  // [ACC_BUFS]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_BUFS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < ACC_BUFS; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM;
+        const int n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d(smem_u32(sa), &tmap_a, fb, kb * BK, m0);
+          tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &tmap_b, fb, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (>>4) address field
+            umma_f16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator complete -> epilogue
+        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BM;
+      const int n0 = (tile / tiles_m) * BN;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + lg * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (EPI == SRGPT_EPI_SWIGLU) {
+            // interleaved weight rows: column 2i = gate_i, 2i+1 = up_i -> out[:, i]
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = bf16_round(v[2 * j]), u = bf16_round(v[2 * j + 1]);
+              o[j] = bf16_round(silu(g)) * u;
+            }
+            bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + (col0 >> 1);
+            const int ncols_out = p.N >> 1;
+            if ((col0 >> 1) + 16 <= ncols_out) {
+              *reinterpret_cast<uint4*>(cp) = pack8(o);
+              *reinterpret_cast<uint4*>(cp + 8) = pack8(o + 8);
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if ((col0 >> 1) + j < ncols_out) cp[j] = __float2bfloat16_rn(o[j]);
+            }
+          } else {
+            apply_epilogue<EPI>(v, p, row, col0);
+            if (p.out_fp32) {
+              float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+              if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = v[j];
+              }
+            } else {
+              bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
+              if (col0 + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(v + j);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// [rows, k] row-major bf16 matrix with `ld` elements between rows -> box {BK, box_rows}, 128B swizzle
+static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SRGPT_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%d k=%d ld=%d ptr=%p)", (int)r, rows, k, ld, ptr);
+    return SRGPT_ERR_CUDA;
+  }
+  return SRGPT_OK;
+}
+
+template <int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+}  // namespace gemm
+}  // namespace srgpt
+
+using namespace srgpt;
+
+extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
+                               const void* bias, const void* residual, int ldr, int res_row_mod, int epilogue,
+                               int out_fp32, void* stream) {
+  SRGPT_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr);
+  SRGPT_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  SRGPT_CHECK_ARG(lda >= K && ldw >= K);
+  SRGPT_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0);  // 16-byte global strides for TMA
+  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  SRGPT_CHECK_ARG(epilogue >= SRGPT_EPI_NONE && epilogue <= SRGPT_EPI_SWIGLU);
+  if (epilogue == SRGPT_EPI_SWIGLU) {
+    SRGPT_CHECK_ARG((N % 2) == 0 && !out_fp32 && ldc >= N / 2 && (ldc % 8) == 0);
+  } else {
+    SRGPT_CHECK_ARG(ldc >= N);
+    SRGPT_CHECK_ARG(out_fp32 || (ldc % 8) == 0);
+  }
+  if (residual != nullptr) {
+    SRGPT_CHECK_ARG(epilogue == SRGPT_EPI_BIAS_RESIDUAL && ldr >= N && (ldr % 8) == 0);
+    SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
+  }
+  if (bias != nullptr) SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+
+  CUtensorMap ta, tb;
+  int rc = gemm::make_tmap(&ta, A, M, K, lda, gemm::BM);
+  if (rc != SRGPT_OK) return rc;
+  rc = gemm::make_tmap(&tb, W, N, K, ldw, gemm::BN);
+  if (rc != SRGPT_OK) return rc;
+
+  gemm::Params p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.bias = reinterpret_cast<const bf16*>(bias);
+  p.residual = reinterpret_cast<const bf16*>(residual);
+  p.ldr = ldr; p.res_row_mod = res_row_mod;
+  p.C = C; p.epilogue = epilogue; p.out_fp32 = out_fp32;
+
+  const int tiles = ceil_div(M, gemm::BM) * ceil_div(N, gemm::BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case SRGPT_EPI_NONE: return gemm::launch<SRGPT_EPI_NONE>(ta, tb, p, grid, st);
+    case SRGPT_EPI_BIAS: return gemm::launch<SRGPT_EPI_BIAS>(ta, tb, p, grid, st);
+    case SRGPT_EPI_BIAS_GELU_TANH: return gemm::launch<SRGPT_EPI_BIAS_GELU_TANH>(ta, tb, p, grid, st);
+    case SRGPT_EPI_BIAS_GELU_ERF: return gemm::launch<SRGPT_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, st);
+    case SRGPT_EPI_BIAS_RESIDUAL: return gemm::launch<SRGPT_EPI_BIAS_RESIDUAL>(ta, tb, p, grid, st);
+    case SRGPT_EPI_SWIGLU: return gemm::launch<SRGPT_EPI_SWIGLU>(ta, tb, p, grid, st);
+  }
+  return SRGPT_ERR_INVALID;
+}

@@ -1,0 +1,362 @@
+// Region-extractor HBM kernels: mask-weight resampling, mask-guided pooling, adaptive average
+// pooling, row re-ordering and depth-map preparation.
+//
+// Reference semantics: llava/model/region_extractor/base_extractor.py:27-84 (MaskPooling),
+// :123,145 (AdaptiveAvgPool2d(27)), llava/eval/eval_spatial.py:99-105 (depth map).
+//
+// Feature-row orders (`order` argument):
+//   0 : row-major, row = y*side + x                       (tower features, reference `hres`)
+//   2 : 2-level nested 2x2, side = 4P: row = ((y>>2)*P + (x>>2))*16 + (((y>>1)&1)*2 + ((x>>1)&1))*4
+//       + ((y&1)*2 + (x&1)).  This is the order in which the two ConvTranspose2d(k=2,s=2) GEMMs emit
+//       pixels, so the refinement never needs a pixel-shuffle pass over the 37.7 MB/image tensor.
+#include "common.cuh"
+#include "srgpt_b200.h"
+
+namespace srgpt {
+
+__device__ __forceinline__ int feat_row(int y, int x, int side, int order) {
+  if (order == 0) return y * side + x;
+  const int P = side >> 2;
+  return ((((y >> 2) * P + (x >> 2)) << 4) | (((((y >> 1) & 1) << 1) | ((x >> 1) & 1)) << 2) | (((y & 1) << 1) | (x & 1)));
+}
+
+// ATen area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=false)
+__device__ __forceinline__ float src_index(float rscale, int dst) {
+  const float s = rscale * ((float)dst + 0.5f) - 0.5f;
+  return s < 0.f ? 0.f : s;
+}
+
+template <typename T>
+__device__ __forceinline__ float bilinear_tap(const T* __restrict__ img, int IH, int IW, float rs_y, float rs_x, int oy, int ox) {
+  const float sy = src_index(rs_y, oy), sx = src_index(rs_x, ox);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < IH - 1 ? 1 : 0), x1 = x0 + (x0 < IW - 1 ? 1 : 0);
+  const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float v00 = (float)img[(size_t)y0 * IW + x0], v01 = (float)img[(size_t)y0 * IW + x1];
+  const float v10 = (float)img[(size_t)y1 * IW + x0], v11 = (float)img[(size_t)y1 * IW + x1];
+  // same association as ATen's upsample_bilinear2d kernels
+  return __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01))),
+                   __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11))));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask weights: one CTA per (mask, image).  pass 1: resample -> bf16, sum; pass 2: divide.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_weights_kernel(const T* __restrict__ masks, bf16* __restrict__ w, int M, int IH, int IW, int side, float rscale, int order) {
+  __shared__ float red[32];
+  const int m = blockIdx.x, img = blockIdx.y;
+  const T* src = masks + ((size_t)img * M + m) * IH * IW;
+  const int L = side * side;
+  bf16* dst = w + ((size_t)img * M + m) * L;
+  float sum = 0.f;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const int oy = l / side, ox = l % side;
+    const bf16 v = __float2bfloat16_rn(bilinear_tap(src, IH, IW, rscale, rscale, oy, ox));
+    dst[feat_row(oy, ox, side, order)] = v;
+    sum += __bfloat162float(v);
+  }
+  const float total = block_sum(sum, red);
+  // denorm = mask.sum() + 1e-8 with both results rounded to bf16 (base_extractor.py:61)
+  const float denorm = bf16_round(bf16_round(total) + 1e-8f);
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const int oy = l / side, ox = l % side;
+    const int r = feat_row(oy, ox, side, order);
+    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(dst[r]), denorm));  // same thread wrote dst[r]
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask pooling: out[img,m,c] = sum_l w[img,m,l] * x[img,l,c]
+// CTA = 16 channel-threads (8 channels each = 128 channels, one 256-byte row segment) x 16 row lanes.
+// grid = (row chunks R, channel chunks Q, images).  fp32 partials [img][R][M][C], then a tiny reduce.
+// ---------------------------------------------------------------------------------------------
+constexpr int MP_THREADS = 256;
+constexpr int MP_CH = 128;   // channels per CTA
+constexpr int MP_RL = 16;    // row lanes
+constexpr int MP_MT = 8;     // masks per pass
+constexpr int MP_MAX_ROWS = 512;  // rows per CTA (weights staged in smem: 8 * 512 * 4 = 16 KB)
+
+__global__ void __launch_bounds__(MP_THREADS)
+mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
+                 int rows_per_cta, int R) {
+  // one buffer, two views (never live at the same time; 36 KB keeps us under the 48 KB static limit):
+  //   sw  [MP_MT][MP_MAX_ROWS]            staged mask weights for this CTA's rows
+  //   sred[warps][MP_MT][MP_CH/8][9]      cross-warp reduction of the accumulators (+1 pad)
+  constexpr int SRED_FLOATS = (MP_THREADS / 32) * MP_MT * (MP_CH / 8) * 9;
+  constexpr int SW_FLOATS = MP_MT * MP_MAX_ROWS;
+  __shared__ float sbuf[SRED_FLOATS > SW_FLOATS ? SRED_FLOATS : SW_FLOATS];
+  float (*sw)[MP_MAX_ROWS] = reinterpret_cast<float (*)[MP_MAX_ROWS]>(sbuf);
+  float (*sred)[MP_MT][MP_CH / 8][9] = reinterpret_cast<float (*)[MP_MT][MP_CH / 8][9]>(sbuf);
+  const int img = blockIdx.z;
+  const int cthr = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * MP_CH + cthr * 8;
+  const bool c_ok = c0 < C;
+  const int l0 = blockIdx.x * rows_per_cta;
+  const int nrows = min(rows_per_cta, L - l0);
+  const bf16* xb = x + ((size_t)img * L + l0) * C + c0;
+
+  for (int m0 = 0; m0 < M; m0 += MP_MT) {
+    const int mt = min(MP_MT, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < MP_MT * rows_per_cta; i += MP_THREADS) {
+      const int mm = i / rows_per_cta, r = i % rows_per_cta;
+      sw[mm][r] = (mm < mt && r < nrows) ? __bfloat162float(w[((size_t)img * M + m0 + mm) * L + l0 + r]) : 0.f;
+    }
+    __syncthreads();
+    float acc[MP_MT][8];
+#pragma unroll
+    for (int mm = 0; mm < MP_MT; ++mm)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[mm][t] = 0.f;
+
+    if (c_ok) {
+      int r = rl;
+      // 4 independent 16-byte loads in flight per thread
+      for (; r + 3 * MP_RL < nrows; r += 4 * MP_RL) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int mm = 0; mm < MP_MT; ++mm) {
+            const float wm = sw[mm][r + k * MP_RL];
+            if (wm != 0.f) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) acc[mm][t] = fmaf(wm, f[t], acc[mm][t]);
+            }
+          }
+        }
+      }
+      for (; r < nrows; r += MP_RL) {
+        float f[8];
+        unpack8(ld_stream16(xb + (size_t)r * C), f);
+#pragma unroll
+        for (int mm = 0; mm < MP_MT; ++mm) {
+          const float wm = sw[mm][r];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[mm][t] = fmaf(wm, f[t], acc[mm][t]);
+        }
+      }
+    }
+    // reduce over the 16 row lanes: 2 lanes inside each warp (xor 16), then 8 warps via smem
+#pragma unroll
+    for (int mm = 0; mm < MP_MT; ++mm)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[mm][t] += __shfl_xor_sync(0xffffffffu, acc[mm][t], 16);
+    __syncthreads();  // everyone is done reading sw before sred (same storage) is written
+    if (lane < 16) {
+#pragma unroll
+      for (int mm = 0; mm < MP_MT; ++mm)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sred[warp][mm][cthr][t] = acc[mm][t];
+    }
+    __syncthreads();
+    // 8 masks x 128 channels = 1024 outputs, 256 threads -> 4 each
+    for (int i = threadIdx.x; i < MP_MT * MP_CH; i += MP_THREADS) {
+      const int mm = i / MP_CH, ch = i % MP_CH;
+      const int c = blockIdx.y * MP_CH + ch;
+      if (mm < mt && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < MP_THREADS / 32; ++wv) s += sred[wv][mm][ch >> 3][ch & 7];
+        partial[(((size_t)img * R + blockIdx.x) * M + m0 + mm) * C + c] = s;
+      }
+    }
+  }
+}
+
+__global__ void mask_pool_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int M, int C, int R) {
+  const int m = blockIdx.x, img = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += partial[(((size_t)img * R + r) * M + m) * C + c];
+    out[((size_t)img * M + m) * C + c] = __float2bfloat16_rn(s);
+  }
+}
+
+static void mask_pool_plan(int n_img, int L, int C, int* R, int* rows_per_cta, int* Q) {
+  *Q = ceil_div(C, MP_CH);
+  int want = ceil_div(2 * sm_count(), (*Q) * n_img);  // ~2 CTAs per SM
+  if (want < 1) want = 1;
+  int rpc = ceil_div(L, want);
+  if (rpc > MP_MAX_ROWS) rpc = MP_MAX_ROWS;
+  if (rpc < MP_RL) rpc = MP_RL;
+  rpc = ceil_div(rpc, MP_RL) * MP_RL;
+  if (rpc > MP_MAX_ROWS) rpc = MP_MAX_ROWS;
+  *rows_per_cta = rpc;
+  *R = ceil_div(L, rpc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive average pool: one CTA per output pixel, threads along channels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160)
+adaptive_avgpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int side, int out_side, int C, int order) {
+  const int img = blockIdx.y;
+  const int oy = blockIdx.x / out_side, ox = blockIdx.x % out_side;
+  // ATen start_index / end_index: floor(o*in/out), ceil((o+1)*in/out)
+  const int ys = (oy * side) / out_side, ye = ((oy + 1) * side + out_side - 1) / out_side;
+  const int xs = (ox * side) / out_side, xe = ((ox + 1) * side + out_side - 1) / out_side;
+  const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
+  const bf16* xb = x + (size_t)img * side * side * C;
+  for (int c = threadIdx.x; c < (C >> 3); c += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(xb + (size_t)feat_row(yy, xx, side, order) * C + (c << 3)), f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] += f[t];
+      }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] *= inv;
+    *reinterpret_cast<uint4*>(y + ((size_t)img * out_side * out_side + blockIdx.x) * C + (c << 3)) = pack8(acc);
+  }
+}
+
+__global__ void reorder_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int side, int C, int from_order, int to_order) {
+  const int img = blockIdx.y;
+  const int yy = blockIdx.x / side, xx = blockIdx.x % side;
+  const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)img * side * side + feat_row(yy, xx, side, from_order)) * C);
+  uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)img * side * side + feat_row(yy, xx, side, to_order)) * C);
+  for (int c = threadIdx.x; c < (C >> 3); c += blockDim.x) dst[c] = src[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth map: resize + min/max (pass 1), normalise to u8 x3 (pass 2)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void depth_init_kernel(int* mm) {
+  mm[0] = float_to_ordered(INFINITY);
+  mm[1] = float_to_ordered(-INFINITY);
+}
+__global__ void __launch_bounds__(256)
+depth_resize_kernel(const float* __restrict__ d, int h, int w, float* __restrict__ tmp, int H, int W, float rs_y, float rs_x, int* mm) {
+  __shared__ float smin[8], smax[8];
+  float lo = INFINITY, hi = -INFINITY;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+    const float v = bilinear_tap(d, h, w, rs_y, rs_x, p / W, p % W);
+    tmp[p] = v;
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
+    atomicMin(&mm[0], float_to_ordered(lo));
+    atomicMax(&mm[1], float_to_ordered(hi));
+  }
+}
+__global__ void depth_norm_kernel(const float* __restrict__ tmp, const int* __restrict__ mm, unsigned char* __restrict__ out, int n) {
+  const float lo = ordered_to_float(mm[0]), hi = ordered_to_float(mm[1]);
+  const float range = __fsub_rn(hi, lo);
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const float t = __fmul_rn(__fdiv_rn(__fsub_rn(tmp[p], lo), range), 255.0f);
+    const unsigned char u = (unsigned char)t;  // numpy astype(uint8): truncation
+    out[3 * p] = u;
+    out[3 * p + 1] = u;
+    out[3 * p + 2] = u;
+  }
+}
+
+}  // namespace srgpt
+
+using namespace srgpt;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, int n_img, int M, int IH, int IW, int side,
+                                  float rscale, int order, void* stream) {
+  SRGPT_CHECK_ARG(masks && w && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
+  SRGPT_CHECK_ARG(order == 0 || (order == 2 && (side % 4) == 0));
+  dim3 grid(M, n_img);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mask_is_bf16)
+    mask_weights_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), reinterpret_cast<bf16*>(w), M, IH, IW, side, rscale, order);
+  else
+    mask_weights_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), reinterpret_cast<bf16*>(w), M, IH, IW, side, rscale, order);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long long srgpt_mask_pool_workspace(int n_img, int M, int L, int C) {
+  if (n_img <= 0 || M <= 0 || L <= 0 || C <= 0) return -1;
+  int R, rpc, Q;
+  mask_pool_plan(n_img, L, C, &R, &rpc, &Q);
+  return (long long)n_img * R * M * C * (long long)sizeof(float);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const void* x, const void* w, void* out, void* workspace, int n_img, int M, int L, int C,
+                                    void* stream) {
+  SRGPT_CHECK_ARG(x && w && out && workspace && n_img > 0 && M > 0 && L > 0 && C > 0);
+  SRGPT_CHECK_ARG((C % 8) == 0 && aligned16(x));
+  int R, rpc, Q;
+  mask_pool_plan(n_img, L, C, &R, &rpc, &Q);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(R, Q, n_img);
+  mask_pool_kernel<<<grid, MP_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
+                                                reinterpret_cast<float*>(workspace), M, L, C, rpc, R);
+  SRGPT_CHECK_LAUNCH();
+  mask_pool_reduce_kernel<<<dim3(M, n_img), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), reinterpret_cast<bf16*>(out), M, C, R);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_adaptive_avgpool_bf16(const void* x, void* y, int n_img, int side, int out_side, int C, int order,
+                                           void* stream) {
+  SRGPT_CHECK_ARG(x && y && n_img > 0 && side > 0 && out_side > 0 && C > 0 && (C % 8) == 0);
+  SRGPT_CHECK_ARG(order == 0 || (order == 2 && (side % 4) == 0));
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(y));
+  adaptive_avgpool_kernel<<<dim3(out_side * out_side, n_img), 160, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), side, out_side, C, order);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_reorder_rows_bf16(const void* x, void* y, int n_img, int side, int C, int from_order, int to_order,
+                                       void* stream) {
+  SRGPT_CHECK_ARG(x && y && x != y && n_img > 0 && side > 0 && C > 0 && (C % 8) == 0);
+  SRGPT_CHECK_ARG((from_order == 0 || from_order == 2) && (to_order == 0 || to_order == 2));
+  SRGPT_CHECK_ARG(((from_order | to_order) & 2) == 0 || (side % 4) == 0);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(y));
+  reorder_rows_kernel<<<dim3(side * side, n_img), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), side, C, from_order, to_order);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_depth_to_u8x3(const void* depth, int h, int w, void* out, int H, int W, void* workspace, void* stream) {
+  SRGPT_CHECK_ARG(depth && out && workspace && h > 0 && w > 0 && H > 0 && W > 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* tmp = reinterpret_cast<float*>(workspace);
+  int* mm = reinterpret_cast<int*>(tmp + (size_t)H * W);
+  // ATen area_pixel_compute_scale with size= given: (float)in / out
+  const float rs_y = (float)h / (float)H, rs_x = (float)w / (float)W;
+  depth_init_kernel<<<1, 1, 0, st>>>(mm);
+  SRGPT_CHECK_LAUNCH();
+  int blocks = ceil_div(H * W, 256);
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  depth_resize_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(depth), h, w, tmp, H, W, rs_y, rs_x, mm);
+  SRGPT_CHECK_LAUNCH();
+  depth_norm_kernel<<<blocks, 256, 0, st>>>(tmp, mm, reinterpret_cast<unsigned char*>(out), H * W);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}

@@ -1,0 +1,266 @@
+// Row-wise HBM-bound kernels: LayerNorm (+GELU), DownSample+LayerNorm, RMSNorm, patchify, splice,
+// argmax.  All use 16-byte vector accesses with threads mapped along the contiguous (channel) dim.
+#include "common.cuh"
+#include "srgpt_b200.h"
+
+namespace srgpt {
+
+void set_last_error(const char* fmt, ...);
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one CTA per row, each thread keeps up to MAXV 16-byte chunks of the row in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 128;
+constexpr int LN_MAXV = 5;  // cols <= 128 * 5 * 8 = 5120
+
+struct DownsampleGather {  // optional: build the input row from 4 source rows (DownSampleBlock)
+  int enabled;
+  int side;      // source side (27)
+  int half;      // ceil(side/2) (14)
+  int C;         // source channels
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ weight, const bf16* __restrict__ bias,
+                 bf16* __restrict__ y, int ldy, int cols, float eps, int act, DownsampleGather g) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nchunk = cols >> 3;
+  float v[LN_MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < nchunk) {
+      uint4 u;
+      if (GATHER) {
+        // output token (a, b) of image n gathers x[2b+dy? ...]: see base_projector.py:44-52.
+        // out[n, a*half + b, q*C + ch] with q = 2*qa + qb  <-  x[n, (2b + qa)*side + (2a + qb), ch]
+        const int per_img = g.half * g.half;
+        const int n = row / per_img, t = row % per_img;
+        const int a = t / g.half, b = t % g.half;
+        const int col = c << 3;
+        const int q = col / g.C, ch = col % g.C;
+        const int sy = 2 * b + (q >> 1), sx = 2 * a + (q & 1);
+        if (sy < g.side && sx < g.side) {
+          u = *reinterpret_cast<const uint4*>(x + ((size_t)n * g.side * g.side + (size_t)sy * g.side + sx) * g.C + ch);
+        } else {
+          u = make_uint4(0, 0, 0, 0);
+        }
+      } else {
+        u = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + (c << 3));
+      }
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sum += v[i][t];
+    }
+  }
+  const float mean = block_sum(sum, red) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < nchunk) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = v[i][t] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float var = block_sum(sq, red) / (float)cols;
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < nchunk) {
+      float w[8], b[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(weight + (c << 3)), w);
+      unpack8(*reinterpret_cast<const uint4*>(bias + (c << 3)), b);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float r = (v[i][t] - mean) * rstd * w[t] + b[t];
+        if (act == 1) r = gelu_erf(bf16_round(r));
+        o[t] = r;
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)row * ldy + (c << 3)) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm (Llama): y = weight * bf16(x * rsqrt(mean(x^2) + eps))
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LN_THREADS)
+rmsnorm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ weight, bf16* __restrict__ y, int ldy,
+               int cols, float eps) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nchunk = cols >> 3;
+  float v[LN_MAXV][8];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < nchunk) {
+      unpack8(*reinterpret_cast<const uint4*>(x + (size_t)row * ldx + (c << 3)), v[i]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sq += v[i][t] * v[i][t];
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < nchunk) {
+      float w[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(weight + (c << 3)), w);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = w[t] * bf16_round(v[i][t] * rstd);
+      *reinterpret_cast<uint4*>(y + (size_t)row * ldy + (c << 3)) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patchify: images [n,3,R,R] -> A [n*P*P, ldk], col = c*ps*ps + ky*ps + kx (Conv2d weight flatten order)
+// ---------------------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void patchify_kernel(const SrcT* __restrict__ img, bf16* __restrict__ A, int R, int ps, int ldk) {
+  const int P = R / ps;
+  const int row = blockIdx.x;  // n*P*P + py*P + px
+  const int n = row / (P * P), t = row % (P * P);
+  const int py = t / P, px = t % P;
+  const int kk = 3 * ps * ps;
+  for (int col = threadIdx.x; col < ldk; col += blockDim.x) {
+    float val = 0.f;
+    if (col < kk) {
+      const int c = col / (ps * ps), r = col % (ps * ps);
+      const int ky = r / ps, kx = r % ps;
+      val = (float)img[(((size_t)n * 3 + c) * R + (py * ps + ky)) * R + (px * ps + kx)];
+    }
+    A[(size_t)row * ldk + col] = __float2bfloat16_rn(val);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// splice: out[r,:] = src[src_id[r]][src_row[r],:]
+// ---------------------------------------------------------------------------------------------
+__global__ void splice_kernel(const bf16* s0, const bf16* s1, const bf16* s2, const bf16* s3, const int* __restrict__ src_id,
+                              const int* __restrict__ src_row, bf16* __restrict__ out, int cols) {
+  const int r = blockIdx.x;
+  const int id = src_id[r];
+  const bf16* base = id == 0 ? s0 : (id == 1 ? s1 : (id == 2 ? s2 : s3));
+  const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)src_row[r] * cols);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r * cols);
+  for (int c = threadIdx.x; c < (cols >> 3); c += blockDim.x) dst[c] = src[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// argmax over fp32 rows, first index on ties
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) argmax_f32_kernel(const float* __restrict__ x, int cols, long long* __restrict__ out) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* row = x + (size_t)blockIdx.x * cols;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = row[c];
+    if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    out[blockIdx.x] = bi;
+  }
+}
+
+}  // namespace srgpt
+
+using namespace srgpt;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" __attribute__((visibility("default"))) int srgpt_layernorm_bf16(const void* x, int ldx, const void* weight, const void* bias, void* y, int ldy, int rows,
+                                    int cols, float eps, int act, void* stream) {
+  SRGPT_CHECK_ARG(x && weight && bias && y && rows > 0 && cols > 0);
+  SRGPT_CHECK_ARG((cols % 8) == 0 && cols <= LN_THREADS * LN_MAXV * 8);
+  SRGPT_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0 && ldx >= cols && ldy >= cols);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(bias) && aligned16(y));
+  SRGPT_CHECK_ARG(act == 0 || act == 1);
+  DownsampleGather g{0, 0, 0, 0};
+  layernorm_kernel<false><<<rows, LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
+      reinterpret_cast<bf16*>(y), ldy, cols, eps, act, g);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_downsample_layernorm_bf16(const void* x, const void* weight, const void* bias, void* y, int n_img,
+                                               int side, int C, float eps, void* stream) {
+  SRGPT_CHECK_ARG(x && weight && bias && y && n_img > 0 && side > 0 && C > 0);
+  SRGPT_CHECK_ARG((C % 8) == 0 && 4 * C <= LN_THREADS * LN_MAXV * 8);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(bias) && aligned16(y));
+  const int half = (side + 1) / 2;
+  DownsampleGather g{1, side, half, C};
+  const int rows = n_img * half * half;
+  layernorm_kernel<true><<<rows, LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), 0, reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
+      reinterpret_cast<bf16*>(y), 4 * C, 4 * C, eps, 0, g);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_rmsnorm_bf16(const void* x, int ldx, const void* weight, void* y, int ldy, int rows, int cols, float eps,
+                                  void* stream) {
+  SRGPT_CHECK_ARG(x && weight && y && rows > 0 && cols > 0);
+  SRGPT_CHECK_ARG((cols % 8) == 0 && cols <= LN_THREADS * LN_MAXV * 8);
+  SRGPT_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0 && ldx >= cols && ldy >= cols);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(y));
+  rmsnorm_kernel<<<rows, LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), reinterpret_cast<bf16*>(y), ldy, cols, eps);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_patchify_bf16(const void* images, int src_is_bf16, void* A, int n, int R, int ps, int ldk, void* stream) {
+  SRGPT_CHECK_ARG(images && A && n > 0 && R > 0 && ps > 0 && (R % ps) == 0);
+  SRGPT_CHECK_ARG(ldk >= 3 * ps * ps && (ldk % 8) == 0);
+  const int P = R / ps;
+  const int rows = n * P * P;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_is_bf16)
+    patchify_kernel<bf16><<<rows, 128, 0, st>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<bf16*>(A), R, ps, ldk);
+  else
+    patchify_kernel<float><<<rows, 128, 0, st>>>(reinterpret_cast<const float*>(images), reinterpret_cast<bf16*>(A), R, ps, ldk);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_splice_rows_bf16(const void* src0, const void* src1, const void* src2, const void* src3,
+                                      const int* src_id, const int* src_row, void* out, int rows, int cols, void* stream) {
+  SRGPT_CHECK_ARG(src0 && src_id && src_row && out && rows > 0 && cols > 0 && (cols % 8) == 0);
+  SRGPT_CHECK_ARG(aligned16(src0) && aligned16(src1) && aligned16(src2) && aligned16(src3) && aligned16(out));
+  splice_kernel<<<rows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src0), reinterpret_cast<const bf16*>(src1), reinterpret_cast<const bf16*>(src2),
+      reinterpret_cast<const bf16*>(src3), src_id, src_row, reinterpret_cast<bf16*>(out), cols);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream) {
+  SRGPT_CHECK_ARG(x && out && rows > 0 && cols > 0);
+  argmax_f32_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, out);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}

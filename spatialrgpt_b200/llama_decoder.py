@@ -1,0 +1,212 @@
+"""Llama decoder on the sm_100a kernels: prefill (tcgen05 GEMMs + flash attention), paged KV cache,
+and a CUDA-graph-captured decode step made of weight-streaming GEMV kernels.
+
+Reference: llava/train/transformers_replace/models/llama/modeling_llama.py — LlamaModel.forward
+(824-936), LlamaDecoderLayer (611-684), LlamaFlashAttention2 (405-566), LlamaMLP (194-223),
+LlamaRMSNorm (61-75), rotary embedding (81-130, 160-191), lm_head + float() (1044-1045),
+prepare_inputs_for_generation (1112-1149); greedy loop = HF GenerationMixin (llava_llama.py:212).
+The reference re-allocates the KV cache with torch.cat every step (451-456) and launches ~25
+torch kernels per layer per token; here one token is 5 kernels per layer replayed from a CUDA graph
+with the position / step counters living in device memory.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .config import LlamaDims
+from .weights import LlamaW
+
+PAGE_SIZE = 16
+
+
+def build_rope_tables(dims: LlamaDims, max_pos: int, device) -> (torch.Tensor, torch.Tensor):
+    """cos/sin exactly as LlamaRotaryEmbedding.forward computes them (modeling_llama.py:86,117-130):
+    fp32 inv_freq, fp32 outer product, cos/sin in fp32, cast to bf16.  Host-side table build (once)."""
+    hd = dims.head_dim
+    inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    t = torch.arange(max_pos, dtype=torch.int64).float()
+    freqs = t[:, None] * inv_freq[None, :]
+    return freqs.cos().to(torch.bfloat16).to(device).contiguous(), freqs.sin().to(torch.bfloat16).to(device).contiguous()
+
+
+class PagedKVCache:
+    """KV pages for all layers: [layers, n_pages, 2 (k,v), PAGE_SIZE, n_kv_heads, head_dim] bf16, a free list
+    and per-sequence page tables (int32, device) of fixed capacity so decode graphs stay valid."""
+
+    def __init__(self, dims: LlamaDims, n_pages: int, max_seqs: int, max_pages_per_seq: int, device):
+        self.dims = dims
+        self.n_pages = n_pages
+        self.max_pages_per_seq = max_pages_per_seq
+        self.pages = torch.zeros((dims.num_hidden_layers, n_pages, 2, PAGE_SIZE, dims.num_key_value_heads, dims.head_dim),
+                                 dtype=torch.bfloat16, device=device)
+        self.page_tables = torch.zeros((max_seqs, max_pages_per_seq), dtype=torch.int32, device=device)
+        self.free: List[int] = list(range(n_pages - 1, -1, -1))
+        self.owned: List[List[int]] = [[] for _ in range(max_seqs)]
+
+    def reserve(self, seq: int, n_tokens: int) -> None:
+        """Make sure sequence `seq` owns pages for positions [0, n_tokens)."""
+        need = (n_tokens + PAGE_SIZE - 1) // PAGE_SIZE
+        if need > self.max_pages_per_seq:
+            raise RuntimeError(f"sequence needs {need} KV pages > capacity {self.max_pages_per_seq}")
+        own = self.owned[seq]
+        if need > len(own):
+            add = need - len(own)
+            if add > len(self.free):
+                raise RuntimeError("KV cache exhausted")
+            new = [self.free.pop() for _ in range(add)]
+            start = len(own)
+            own.extend(new)
+            self.page_tables[seq, start:start + add] = torch.tensor(new, dtype=torch.int32)
+
+    def release(self, seq: int) -> None:
+        self.free.extend(reversed(self.owned[seq]))
+        self.owned[seq] = []
+
+    def layer(self, l: int) -> torch.Tensor:
+        return self.pages[l]
+
+
+class LlamaDecoder:
+    def __init__(self, dims: LlamaDims, w: LlamaW, max_seq_len: int = 4096, max_new_tokens_cap: int = 4096, max_seqs: int = 1,
+                 kv_pages: Optional[int] = None):
+        self.dims = dims
+        self.w = w
+        dev = w.embed.device
+        self.device = dev
+        self.max_seq_len = max_seq_len
+        self.cos, self.sin = build_rope_tables(dims, max_seq_len, dev)
+        ppseq = (max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE
+        self.cache = PagedKVCache(dims, kv_pages if kv_pages is not None else ppseq * max_seqs, max_seqs, ppseq, dev)
+        H, nh, hd, I = dims.hidden_size, dims.num_attention_heads, dims.head_dim, dims.intermediate_size
+        # decode-step state (static addresses -> graph-capturable)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)       # position of the token being processed
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)      # number of generated tokens so far
+        self.out_ids = torch.zeros(max_new_tokens_cap, dtype=torch.int64, device=dev)
+        self.h = torch.zeros(H, dtype=torch.bfloat16, device=dev)      # residual stream of the current token
+        self.q_buf = torch.zeros(nh * hd, dtype=torch.bfloat16, device=dev)
+        self.attn_buf = torch.zeros(nh * hd, dtype=torch.bfloat16, device=dev)
+        self.act_buf = torch.zeros(I, dtype=torch.bfloat16, device=dev)
+        self.lm_ws = ops.lm_head_workspace(dims.vocab_size, dev)
+        self.scale = hd ** -0.5
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernels_per_decode_step = 5 * dims.num_hidden_layers + 2
+
+    # ---------------------------------------------------------------------------------------------
+    def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
+        """Embedding gather through the splice kernel (source 0 only)."""
+        flat = ids.reshape(-1).to(device=self.device, dtype=torch.int32)
+        return ops.splice_rows(self.w.embed, None, None, None, torch.zeros_like(flat), flat)
+
+    def prefill_hidden(self, inputs_embeds: torch.Tensor, seq: int = 0, start_pos: int = 0) -> torch.Tensor:
+        """Run all layers over one sequence's prompt rows [S, H]; fills the KV cache; returns the
+        final-layer residual stream [S, H] (before the final norm)."""
+        d, w = self.dims, self.w
+        S = inputs_embeds.shape[0]
+        if start_pos + S > self.max_seq_len:
+            raise RuntimeError(f"prompt of {S} tokens at {start_pos} exceeds max_seq_len {self.max_seq_len}")
+        self.cache.reserve(seq, start_pos + S)
+        nh, nkv, hd = d.num_attention_heads, d.num_key_value_heads, d.head_dim
+        qd, kd = nh * hd, nkv * hd
+        sp = torch.tensor([start_pos], dtype=torch.int32, device=self.device)
+        pt = self.cache.page_tables[seq]
+        x = inputs_embeds.to(torch.bfloat16).contiguous().clone()
+        if start_pos != 0:
+            raise NotImplementedError("chunked prefill (prompt attention over cached pages) is a next-round item")
+        for l, lw in enumerate(w.layers):
+            h = ops.rmsnorm(x, lw.in_norm, d.rms_norm_eps)
+            qkv = ops.gemm(h, lw.qkv_w)
+            ops.rope_kv_append(qkv, nh, nkv, hd, self.cos, self.sin, sp, self.cache.layer(l), pt, PAGE_SIZE)
+            o = ops.attention_prefill(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], 1, S, nh, nkv, hd, self.scale, causal=True)
+            x = ops.gemm(o, lw.o_w, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+            h = ops.rmsnorm(x, lw.post_norm, d.rms_norm_eps, out=h)
+            a = ops.gemm(h, lw.gateup_w, epilogue=ops.EPI_SWIGLU)
+            x = ops.gemm(a, lw.down_w, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+        return x
+
+    def logits_all(self, hidden: torch.Tensor) -> torch.Tensor:
+        """lm_head over every row -> fp32 logits [S, V] (LlamaForCausalLM.forward semantics, 1044-1045)."""
+        hn = ops.rmsnorm(hidden, self.w.norm, self.dims.rms_norm_eps)
+        lg = ops.gemm(hn, self.w.lm_head, out_fp32=False)  # bf16 rounding first, then .float()
+        return lg.float()
+
+    # ---------------------------------------------------------------------------------------------
+    def _decode_step_launch(self, seq: int, logits_out: Optional[torch.Tensor] = None) -> None:
+        d, w = self.dims, self.w
+        nh, nkv, hd = d.num_attention_heads, d.num_key_value_heads, d.head_dim
+        pt = self.cache.page_tables[seq]
+        for l, lw in enumerate(w.layers):
+            pages = self.cache.layer(l)
+            ops.gemv(self.h, lw.qkv_w, self.q_buf, norm_weight=lw.in_norm, eps=d.rms_norm_eps, mode=ops.GEMV_QKV_ROPE,
+                     n_heads=nh, n_kv_heads=nkv, head_dim=hd, cos_tab=self.cos, sin_tab=self.sin, pos=self.pos, kv_pages=pages,
+                     page_table=pt, page_size=PAGE_SIZE)
+            ops.attention_decode(self.q_buf, self.attn_buf, pages, pt, PAGE_SIZE, self.pos, nh, nkv, hd, self.scale)
+            ops.gemv(self.attn_buf, lw.o_w, self.h, residual=self.h, mode=ops.GEMV_PLAIN)
+            ops.gemv(self.h, lw.gateup_w, self.act_buf, norm_weight=lw.post_norm, eps=d.rms_norm_eps, mode=ops.GEMV_SWIGLU)
+            ops.gemv(self.act_buf, lw.down_w, self.h, residual=self.h, mode=ops.GEMV_PLAIN)
+        ops.lm_head_argmax(self.h, w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
+                           embed_table=w.embed, next_x=self.h, logits_out=logits_out)
+
+    def _ensure_graph(self, seq: int) -> None:
+        if self._graph is not None:
+            return
+        # warm up once outside capture (lazy cudaFuncSetAttribute calls etc.), on a side stream
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        saved = (self.pos.clone(), self.step.clone(), self.h.clone(), self.out_ids.clone())
+        with torch.cuda.stream(s):
+            self._decode_step_launch(seq)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.pos.copy_(saved[0]); self.step.copy_(saved[1]); self.h.copy_(saved[2]); self.out_ids.copy_(saved[3])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._decode_step_launch(seq)
+        self._graph = g
+
+    @torch.no_grad()
+    def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, eos_token_ids=None, stopping_fn=None,
+                             use_graph: bool = True, return_logits: bool = False, seq: int = 0):
+        """Greedy decoding started from prompt embeddings [S, H].  Returns LongTensor [n_new]
+        (and fp32 logits [n_new, V] when return_logits).  ``stopping_fn(ids_so_far: LongTensor) -> bool``."""
+        d, w = self.dims, self.w
+        S = inputs_embeds.shape[0]
+        if max_new_tokens < 1:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        if max_new_tokens > self.out_ids.numel():
+            raise RuntimeError(f"max_new_tokens {max_new_tokens} exceeds the decoder's cap {self.out_ids.numel()}")
+        if S + max_new_tokens > self.max_seq_len:
+            raise RuntimeError(f"{S} prompt + {max_new_tokens} new tokens exceed max_seq_len {self.max_seq_len}")
+        eos = set()
+        if eos_token_ids is not None:
+            eos = set(int(e) for e in (eos_token_ids if isinstance(eos_token_ids, (list, tuple, set)) else [eos_token_ids]))
+        self.cache.release(seq)
+        self.cache.reserve(seq, S + max_new_tokens)
+        hidden = self.prefill_hidden(inputs_embeds, seq, 0)
+        logits = torch.empty((max_new_tokens, d.vocab_size), dtype=torch.float32, device=self.device) if return_logits else None
+        # first token: final norm + lm_head + argmax on the last prompt row; afterwards pos == S
+        self.pos.fill_(S - 1)
+        self.step.zero_()
+        ops.lm_head_argmax(hidden[S - 1], w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
+                           embed_table=w.embed, next_x=self.h, logits_out=None if logits is None else logits[0])
+        need_host_check = bool(eos) or stopping_fn is not None
+        n = 1
+        if use_graph and not return_logits:
+            self._ensure_graph(seq)
+        while n < max_new_tokens:
+            if need_host_check:
+                ids = self.out_ids[:n]
+                last = int(ids[-1])  # device->host sync, like HF's per-token eos check
+                if last in eos or (stopping_fn is not None and stopping_fn(ids)):
+                    break
+            if use_graph and not return_logits:
+                self._graph.replay()
+            else:
+                self._decode_step_launch(seq, None if logits is None else logits[n])
+            n += 1
+        out = self.out_ids[:n].clone()
+        if return_logits:
+            return out, logits[:n]
+        return out

@@ -1,0 +1,315 @@
+"""``LlavaLlamaModel`` — the reference's VLM class (llava/model/language_model/llava_llama.py:48-213
++ llava/model/llava_arch.py:252-650) re-built over the sm_100a kernels, keeping its public surface:
+``generate(input_ids, images=, depths=, masks=, attention_mask=, **generation_kwargs)``, ``forward``,
+``prepare_inputs_labels_for_multimodal``, ``encode_images``, the ``get_*`` accessors, ``config``,
+``tokenizer``, ``device`` / ``dtype``.  ``LlavaLlamaForCausalLM`` is an alias (the name the north
+star and llava/model/builder.py:138 use; the reference never defines it)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import ops
+from .config import LlavaConfig
+from .constants import IGNORE_INDEX, IMAGE_TOKEN_INDEX
+from .llama_decoder import LlamaDecoder
+from .multimodal_encoder import VisionTower
+from .multimodal_projector import MultimodalProjector
+from .region_extractor import RegionExtractor
+from .weights import ModelWeights
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    logits: torch.Tensor
+    loss: Optional[torch.Tensor] = None
+    past_key_values: Any = None
+    hidden_states: Any = None
+    attentions: Any = None
+
+
+class LlavaLlamaModel:
+    config_class = LlavaConfig
+    main_input_name = "input_embeds"
+
+    def __init__(self, config: LlavaConfig, weights: ModelWeights, tokenizer=None, image_processor=None,
+                 max_seq_len: int = 4096):
+        # fail loudly when the CUDA extension or a B200 is missing: there is no CPU path
+        from . import _lib
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SrgptError("spatialrgpt_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        _lib.device_info()
+        self.config = config
+        self.weights = weights
+        self.tokenizer = tokenizer
+        self.vision_tower = VisionTower(config, weights.vision, image_processor)
+        self.mm_projector = MultimodalProjector(config, weights.projector)
+        self.region_extractor = RegionExtractor(config, weights.region) if (config.enable_region and weights.region is not None) else None
+        self.llm = LlamaDecoder(config.llama, weights.llama, max_seq_len=max_seq_len)
+        self.training = False
+
+    # ---- accessors (llava_arch.py:252-278) -----------------------------------------------------------
+    def get_llm(self):
+        return self.llm
+
+    def get_lm_head(self):
+        return self.weights.llama.lm_head
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+    def get_mm_projector(self):
+        return self.mm_projector
+
+    def get_region_extractor(self):
+        return self.region_extractor
+
+    def get_input_embeddings(self):
+        return self.llm.embed_tokens
+
+    @property
+    def device(self):
+        return self.weights.llama.embed.device
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def eval(self):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        dt = k.get("dtype", None)
+        for x in a:
+            if isinstance(x, torch.dtype):
+                dt = x
+        if dt is not None and dt not in (torch.bfloat16,):
+            raise NotImplementedError("the sm_100a path computes in bf16 (eval_spatial.py:221); fp16 is a next-round item")
+        return self
+
+    # ---- encoders ---------------------------------------------------------------------------------
+    def encode_images(self, images: torch.Tensor) -> torch.Tensor:
+        """llava_arch.py:307-310 (tower -> projector, no regions)."""
+        return self.mm_projector(self.vision_tower(images))
+
+    def _encode_multimodal(self, images, masks, depths):
+        """llava_arch.py:387-411.  Returns (image_features [N,196,H], mask_embeds, depth_embeds)."""
+        cfg = self.config
+        if isinstance(images, (list, tuple)):
+            images = torch.cat([im if im.dim() == 4 else im[None] for im in images], dim=0)
+        elif images.dim() == 5:
+            images = images.flatten(0, 1)
+        if depths is not None:
+            if isinstance(depths, (list, tuple)):
+                depths = torch.cat([d if d.dim() == 4 else d[None] for d in depths], dim=0)
+            elif depths.dim() == 5:
+                depths = depths.flatten(0, 1)
+        N = images.shape[0]
+        mask_embeds = depth_embeds = None
+        use_depth = cfg.enable_region and cfg.enable_depth and depths is not None
+        if use_depth and depths.shape == images.shape:
+            # one tower pass over [images; depths] (same weights, llava_arch.py:398,404): twice the GEMM M
+            both = self.vision_tower(torch.cat([images.to(self.device), depths.to(self.device).to(images.dtype)], dim=0))
+            tower_features, depth_features = both[:N], both[N:]
+        else:
+            tower_features = self.vision_tower(images)
+            depth_features = self.vision_tower(depths) if use_depth else None
+        if cfg.enable_region and self.region_extractor is not None:
+            hres, lres = self.region_extractor.feature_refinement_nested(tower_features.contiguous())
+            mask_embeds, depth_embeds = self.region_extractor(hres, None if depth_features is None else depth_features.contiguous(),
+                                                              masks, hres_order=ops.ORDER_NESTED)
+        else:
+            lres = tower_features
+        image_features = self.mm_projector(lres)
+        return image_features, mask_embeds, depth_embeds
+
+    # ---- embedding splice (llava_arch.py:333-650) -----------------------------------------------------
+    def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                                             masks=None, depths=None):
+        if images is None or (input_ids is not None and input_ids.shape[1] == 1):
+            return input_ids, position_ids, attention_mask, past_key_values, None, labels  # llava_arch.py:355-385
+        cfg = self.config
+        image_features, mask_embeds, depth_embeds = self._encode_multimodal(images, masks, depths)
+        n_img, n_tok, H = image_features.shape
+        dev = self.device
+
+        ids_cpu = input_ids.detach().to("cpu", torch.int64)
+        B, T = ids_cpu.shape
+        am_cpu = torch.ones((B, T), dtype=torch.bool) if attention_mask is None else attention_mask.detach().to("cpu").bool()
+        lab_cpu = torch.full((B, T), IGNORE_INDEX, dtype=torch.int64) if labels is None else labels.detach().to("cpu", torch.int64)
+
+        def cat_rows(embeds):
+            """list of per-image [M_i, H] or None -> (flat tensor or None, row offsets)"""
+            if embeds is None:
+                return None, [0] * (n_img + 1)
+            offs, parts, o = [], [], 0
+            for e in embeds:
+                offs.append(o)
+                if e is not None:
+                    parts.append(e)
+                    o += e.shape[0]
+            offs.append(o)
+            return (torch.cat(parts, 0).contiguous() if parts else None), offs
+
+        mflat, moff = cat_rows(mask_embeds)
+        dflat, doff = cat_rows(depth_embeds)
+        img_flat = image_features.reshape(n_img * n_tok, H)
+
+        new_embeds: List[torch.Tensor] = []
+        new_labels: List[torch.Tensor] = []
+        cur_image_idx = 0
+        for b in range(B):
+            ids = ids_cpu[b][am_cpu[b]]
+            lab = lab_cpu[b][am_cpu[b]]
+            n = ids.shape[0]
+            src_id = torch.zeros(n, dtype=torch.int32)
+            src_row = ids.clamp(min=0).to(torch.int32)  # image slots -> token 0 (llava_arch.py:436), replaced below
+            img_pos = torch.where(ids == IMAGE_TOKEN_INDEX)[0].tolist()
+            if img_pos:
+                first_img = cur_image_idx
+                if cfg.enable_region and mask_embeds is not None and mask_embeds[first_img] is not None:
+                    pos = torch.where(ids == cfg.llm_mask_token_id)[0]
+                    k = min(pos.numel(), moff[first_img + 1] - moff[first_img])
+                    if pos.numel() > k:
+                        print("Error: fewer mask embeds than <mask> tokens")  # llava_arch.py:476-477 (prints, no raise)
+                    src_id[pos[:k]] = 2
+                    src_row[pos[:k]] = torch.arange(moff[first_img], moff[first_img] + k, dtype=torch.int32)
+                elif cfg.enable_region and int((ids == cfg.llm_mask_token_id).sum()) > 0:
+                    print("Error: mask embed is None, but the num of <mask> is not 0!!!")
+                if cfg.enable_region and cfg.enable_depth and depths is not None and depth_embeds is not None and depth_embeds[first_img] is not None:
+                    pos = torch.where(ids == cfg.llm_depth_token_id)[0]
+                    k = min(pos.numel(), doff[first_img + 1] - doff[first_img])
+                    src_id[pos[:k]] = 3
+                    src_row[pos[:k]] = torch.arange(doff[first_img], doff[first_img] + k, dtype=torch.int32)
+            # expand every <image> slot into that image's n_tok feature rows
+            sid_parts, srow_parts, lab_parts = [], [], []
+            start = 0
+            for p in img_pos:
+                sid_parts.append(src_id[start:p]); srow_parts.append(src_row[start:p]); lab_parts.append(lab[start:p])
+                sid_parts.append(torch.full((n_tok,), 1, dtype=torch.int32))
+                srow_parts.append(torch.arange(cur_image_idx * n_tok, (cur_image_idx + 1) * n_tok, dtype=torch.int32))
+                lab_parts.append(torch.full((n_tok,), IGNORE_INDEX, dtype=torch.int64))
+                cur_image_idx += 1
+                start = p + 1
+            sid_parts.append(src_id[start:]); srow_parts.append(src_row[start:]); lab_parts.append(lab[start:])
+            sid, srow = torch.cat(sid_parts), torch.cat(srow_parts)
+            new_embeds.append(ops.splice_rows(self.weights.llama.embed, img_flat, mflat if mflat is not None else img_flat,
+                                              dflat if dflat is not None else img_flat, sid.to(dev), srow.to(dev)))
+            new_labels.append(torch.cat(lab_parts))
+
+        max_model_len = getattr(cfg.llama, "tokenizer_model_max_length", None)
+        if max_model_len is not None:
+            new_embeds = [x[:max_model_len] for x in new_embeds]
+            new_labels = [x[:max_model_len] for x in new_labels]
+        max_len = max(x.shape[0] for x in new_embeds)
+        left = getattr(cfg.llama, "tokenizer_padding_side", "right") == "left"
+        out = torch.zeros((B, max_len, H), dtype=torch.bfloat16, device=dev)
+        lab_out = torch.full((B, max_len), IGNORE_INDEX, dtype=torch.int64)
+        am_out = torch.zeros((B, max_len), dtype=torch.bool)
+        pos_out = torch.zeros((B, max_len), dtype=torch.int64)
+        for b, (e, l) in enumerate(zip(new_embeds, new_labels)):
+            n = e.shape[0]
+            sl = slice(max_len - n, max_len) if left else slice(0, n)
+            out[b, sl] = e
+            lab_out[b, sl] = l
+            am_out[b, sl] = True
+            pos_out[b, sl] = torch.arange(n)
+        ret_labels = None if labels is None else lab_out.to(dev)
+        ret_am = None if attention_mask is None else am_out.to(device=dev, dtype=attention_mask.dtype)
+        ret_pos = None if position_ids is None else pos_out.to(dev)
+        self._last_seq_lens = [x.shape[0] for x in new_embeds]
+        return None, ret_pos, ret_am, past_key_values, out, ret_labels
+
+    # ---- forward: logits for every position (llava_llama.py:100-192) ----------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids=None, images=None, masks=None, depths=None, attention_mask=None, position_ids=None,
+                past_key_values=None, seqlens_in_batch=None, inputs_embeds=None, labels=None, use_cache=None, **kwargs):
+        if past_key_values is not None:
+            raise NotImplementedError("external past_key_values are not supported; the KV cache is paged and internal")
+        if inputs_embeds is None:
+            if images is None:
+                inputs_embeds = self.llm.embed_tokens(input_ids).view(*input_ids.shape, -1)
+            else:
+                (_, position_ids, attention_mask, _, inputs_embeds, labels) = self.prepare_inputs_labels_for_multimodal(
+                    input_ids, position_ids, attention_mask, None, labels, images, masks, depths)
+        B, S, H = inputs_embeds.shape
+        lens = [S] * B if attention_mask is None else attention_mask.bool().sum(-1).tolist()
+        logits = torch.zeros((B, S, self.config.llama.vocab_size), dtype=torch.float32, device=self.device)
+        for b in range(B):
+            n = int(lens[b])
+            if attention_mask is not None and not bool(attention_mask[b, :n].all()):
+                raise NotImplementedError("left-padded batches in forward() are a next-round item")
+            self.llm.cache.release(0)
+            hid = self.llm.prefill_hidden(inputs_embeds[b, :n], 0, 0)
+            logits[b, :n] = self.llm.logits_all(hid)
+        return CausalLMOutputWithPast(logits=logits)
+
+    __call__ = forward
+
+    # ---- generate (llava_llama.py:194-213) --------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
+                 depths: Optional[torch.Tensor] = None, masks: Optional[List[torch.Tensor]] = None,
+                 attention_mask: Optional[torch.Tensor] = None, **generation_kwargs):
+        do_sample = bool(generation_kwargs.pop("do_sample", False))
+        temperature = generation_kwargs.pop("temperature", None)
+        generation_kwargs.pop("top_p", None)
+        num_beams = int(generation_kwargs.pop("num_beams", 1) or 1)
+        max_new_tokens = generation_kwargs.pop("max_new_tokens", None)
+        max_length = generation_kwargs.pop("max_length", None)
+        generation_kwargs.pop("use_cache", None)
+        stopping_criteria = generation_kwargs.pop("stopping_criteria", None)
+        pad_token_id = generation_kwargs.pop("pad_token_id", None)
+        eos_token_id = generation_kwargs.pop("eos_token_id", self.config.llama.eos_token_id)
+        return_logits = bool(generation_kwargs.pop("output_logits", False))
+        use_graph = bool(generation_kwargs.pop("use_cuda_graph", True))
+        if do_sample and temperature not in (None, 0, 0.0):
+            raise NotImplementedError("sampling is a next-round item (SURVEY.md §8f.4); the graded mode is greedy")
+        if num_beams != 1:
+            raise NotImplementedError("beam search is a next-round item (SURVEY.md §8f.4)")
+        if generation_kwargs:
+            raise TypeError(f"unsupported generation kwargs: {sorted(generation_kwargs)}")
+
+        if images is not None:
+            (_, _, attention_mask, _, inputs_embeds, _) = self.prepare_inputs_labels_for_multimodal(
+                input_ids, None, attention_mask, None, None, images, masks, depths)
+            lens = self._last_seq_lens
+        else:
+            inputs_embeds = self.llm.embed_tokens(input_ids).view(*input_ids.shape, -1)
+            lens = [input_ids.shape[1]] * input_ids.shape[0] if attention_mask is None else attention_mask.sum(-1).tolist()
+        B = inputs_embeds.shape[0]
+        if max_new_tokens is None:
+            max_new_tokens = 20 if max_length is None else max(int(max_length) - max(lens), 1)  # HF default max_length=20
+        pad = pad_token_id if pad_token_id is not None else (self.config.llama.pad_token_id or 0)
+
+        outs, all_logits = [], []
+        for b in range(B):
+            n = int(lens[b])
+            left = getattr(self.config.llama, "tokenizer_padding_side", "right") == "left"
+            emb = inputs_embeds[b, inputs_embeds.shape[1] - n:] if left else inputs_embeds[b, :n]
+            stop_fn = None
+            if stopping_criteria:
+                def stop_fn(ids, _sc=stopping_criteria):
+                    return any(bool(c(ids[None], None)) for c in _sc)
+            r = self.llm.generate_from_embeds(emb, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
+                                              use_graph=use_graph, return_logits=return_logits)
+            if return_logits:
+                r, lg = r
+                all_logits.append(lg)
+            outs.append(r)
+        n_max = max(o.numel() for o in outs)
+        seqs = torch.full((B, n_max), int(pad), dtype=torch.int64, device=self.device)
+        for b, o in enumerate(outs):
+            seqs[b, : o.numel()] = o
+        if return_logits:
+            return seqs, all_logits
+        return seqs
+
+
+LlavaLlamaForCausalLM = LlavaLlamaModel

@@ -1,0 +1,94 @@
+"""Vision tower: SigLIP forward on the sm_100a kernels.
+
+Mirrors ``VisionTower.forward`` + ``feature_select`` (llava/model/multimodal_encoder/
+vision_encoder.py:26-34,115-132) and ``SiglipVisionTower`` (siglip_encoder.py:7-17): returns
+``hidden_states[select_layer]`` with all T patch tokens ("cls_patch"; SigLIP has no CLS token).
+Only the layers that output depends on are executed (select_layer=-2 -> L-1 layers; the reference
+runs all L layers, the post-layernorm and the pooling head and throws them away).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+from .config import LlavaConfig
+from .weights import VisionW, patch_ldk
+
+
+def tower_layers_needed(num_hidden_layers: int, select_layer: int) -> int:
+    # hidden_states = (embeddings, layer_1, ..., layer_L)
+    idx = select_layer if select_layer >= 0 else num_hidden_layers + 1 + select_layer
+    if not 0 <= idx <= num_hidden_layers:
+        raise ValueError(f"select_layer {select_layer} out of range for {num_hidden_layers} layers")
+    return idx
+
+
+class VisionTower:
+    def __init__(self, cfg: LlavaConfig, w: VisionW, image_processor=None):
+        self.cfg = cfg
+        self.vc = cfg.vision
+        self.w = w
+        self.select_layer = cfg.mm_vision_select_layer
+        self.select_feature = cfg.mm_vision_select_feature
+        if self.select_feature not in ("cls_patch", "patch"):
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")  # vision_encoder.py:33
+        if self.select_feature == "patch":
+            raise NotImplementedError("'patch' drops a CLS token; SigLIP has none (CLIP tower is a next-round item)")
+        self.n_layers = tower_layers_needed(self.vc.num_hidden_layers, self.select_layer)
+        if len(w.layers) < self.n_layers:
+            raise ValueError(f"need {self.n_layers} vision layers, weights hold {len(w.layers)}")
+        self.is_loaded = True
+        self.image_processor = image_processor
+        # builder.py:190-192 records the special token ids here
+        self.config = SimpleNamespace(llm_mask_token_id=cfg.llm_mask_token_id, llm_depth_token_id=cfg.llm_depth_token_id,
+                                      hidden_size=self.vc.hidden_size, image_size=self.vc.image_size,
+                                      patch_size=self.vc.patch_size)
+
+    @property
+    def device(self):
+        return self.w.patch_w.device
+
+    @property
+    def dtype(self):
+        return self.w.patch_w.dtype
+
+    @property
+    def hidden_size(self):
+        return self.vc.hidden_size
+
+    @property
+    def num_patches(self):
+        return self.vc.grid ** 2
+
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """images [N, 3, R, R] (fp32 or bf16, on the device) -> [N, T, D] bf16."""
+        if isinstance(images, (list, tuple)):  # vision_encoder.py:116-125
+            return [self.forward(im.unsqueeze(0) if im.dim() == 3 else im) for im in images]
+        vc, w = self.vc, self.w
+        if images.dim() != 4 or images.shape[-1] != vc.image_size or images.shape[-2] != vc.image_size:
+            raise ValueError(f"expected images [N, 3, {vc.image_size}, {vc.image_size}], got {tuple(images.shape)}")
+        images = images.to(device=self.device)
+        if images.dtype not in (torch.float32, torch.bfloat16):
+            images = images.float()
+        images = images.contiguous()
+        N, T, D, nh, hd = images.shape[0], vc.grid ** 2, vc.hidden_size, vc.num_attention_heads, vc.head_dim
+        a = ops.patchify(images, vc.patch_size, patch_ldk(vc.patch_size))
+        x = ops.gemm(a, w.patch_w, bias=w.patch_b, residual=w.pos_emb, epilogue=ops.EPI_BIAS_RESIDUAL, res_row_mod=T)
+        scale = hd ** -0.5
+        for i in range(self.n_layers):
+            lw = w.layers[i]
+            h = ops.layernorm(x, lw.ln1_w, lw.ln1_b, vc.layer_norm_eps)
+            qkv = ops.gemm(h, lw.qkv_w, bias=lw.qkv_b, epilogue=ops.EPI_BIAS)
+            o = ops.attention_prefill(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], N, T, nh, nh, hd, scale, causal=False)
+            x = ops.gemm(o, lw.out_w, bias=lw.out_b, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+            h = ops.layernorm(x, lw.ln2_w, lw.ln2_b, vc.layer_norm_eps, out=h)
+            h1 = ops.gemm(h, lw.fc1_w, bias=lw.fc1_b, epilogue=ops.EPI_BIAS_GELU_TANH)
+            x = ops.gemm(h1, lw.fc2_w, bias=lw.fc2_b, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+        return x.view(N, T, D)
+
+    __call__ = forward
+
+
+SiglipVisionTower = VisionTower

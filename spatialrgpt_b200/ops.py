@@ -1,0 +1,275 @@
+"""torch.Tensor-facing wrappers over the C-ABI (one function per exported kernel group).
+
+torch is used for device memory and streams only; every computation below is a hand-written
+sm_100a kernel in ``csrc/``.  All wrappers raise ``SrgptError`` on any failure (no fallbacks).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import SrgptError, check
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GELU_ERF, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(6)
+GEMV_PLAIN, GEMV_SWIGLU, GEMV_QKV_ROPE = range(3)
+ORDER_ROWMAJOR, ORDER_NESTED = 0, 2
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise SrgptError(f"{name}: expected a CUDA tensor (the sm_100a kernels have no CPU fallback)")
+    if t.dtype != dtype:
+        raise SrgptError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def _rowmajor2d(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise SrgptError(f"{name}: expected a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None, out_fp32: bool = False,
+         res_row_mod: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores."""
+    _need(a, BF16, "gemm.a"); _need(w, BF16, "gemm.w")
+    lda, ldw = _rowmajor2d(a, "gemm.a"), _rowmajor2d(w, "gemm.w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise SrgptError(f"gemm: K mismatch {K} vs {K2}")
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    else:
+        _need(out, torch.float32 if out_fp32 else BF16, "gemm.out")
+        if out.shape != (M, n_out):
+            raise SrgptError(f"gemm.out: expected {(M, n_out)}, got {tuple(out.shape)}")
+    ldc = _rowmajor2d(out, "gemm.out")
+    ldr = 0
+    if residual is not None:
+        _need(residual, BF16, "gemm.residual")
+        ldr = _rowmajor2d(residual, "gemm.residual")
+    if bias is not None:
+        _need(bias, BF16, "gemm.bias")
+    check(_lib.load().srgpt_gemm_bf16(_p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(residual), ldr,
+                                      res_row_mod, epilogue, 1 if out_fp32 else 0, _stream()), "srgpt_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, act: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, BF16, "layernorm.x")
+    ldx = _rowmajor2d(x, "layernorm.x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    check(_lib.load().srgpt_layernorm_bf16(_p(x), ldx, _p(weight), _p(bias), _p(out), _rowmajor2d(out, "layernorm.out"),
+                                           rows, cols, eps, act, _stream()), "srgpt_layernorm_bf16")
+    return out
+
+
+def downsample_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """x [n, side*side, C] -> [n, ceil(side/2)^2, 4C] (DownSampleBlock + LayerNorm)."""
+    _need(x, BF16, "downsample_layernorm.x")
+    if x.dim() != 3 or not x.is_contiguous():
+        raise SrgptError("downsample_layernorm: expected contiguous [n, side*side, C]")
+    n, hw, c = x.shape
+    side = int(round(hw ** 0.5))
+    if side * side != hw:
+        raise SrgptError(f"downsample_layernorm: {hw} tokens is not a square grid")
+    half = (side + 1) // 2
+    out = torch.empty((n, half * half, 4 * c), dtype=BF16, device=x.device)
+    check(_lib.load().srgpt_downsample_layernorm_bf16(_p(x), _p(weight), _p(bias), _p(out), n, side, c, eps, _stream()),
+          "srgpt_downsample_layernorm_bf16")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, BF16, "rmsnorm.x")
+    ldx = _rowmajor2d(x, "rmsnorm.x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+    check(_lib.load().srgpt_rmsnorm_bf16(_p(x), ldx, _p(weight), _p(out), _rowmajor2d(out, "rmsnorm.out"), rows, cols, eps,
+                                         _stream()), "srgpt_rmsnorm_bf16")
+    return out
+
+
+def patchify(images: torch.Tensor, patch: int, ldk: int) -> torch.Tensor:
+    if not images.is_cuda or images.dim() != 4 or images.shape[1] != 3 or not images.is_contiguous():
+        raise SrgptError("patchify: expected a contiguous CUDA tensor [n, 3, R, R]")
+    if images.dtype not in (torch.float32, BF16):
+        raise SrgptError(f"patchify: unsupported dtype {images.dtype}")
+    n, _, R, R2 = images.shape
+    if R != R2:
+        raise SrgptError("patchify: square images only")
+    P = R // patch
+    out = torch.empty((n * P * P, ldk), dtype=BF16, device=images.device)
+    check(_lib.load().srgpt_patchify_bf16(_p(images), 1 if images.dtype == BF16 else 0, _p(out), n, R, patch, ldk, _stream()),
+          "srgpt_patchify_bf16")
+    return out
+
+
+def splice_rows(src0: torch.Tensor, src1, src2, src3, src_id: torch.Tensor, src_row: torch.Tensor) -> torch.Tensor:
+    _need(src0, BF16, "splice.src0"); _need(src_id, torch.int32, "splice.src_id"); _need(src_row, torch.int32, "splice.src_row")
+    cols = src0.shape[-1]
+    rows = src_id.numel()
+    for s in (src1, src2, src3):
+        if s is not None:
+            _need(s, BF16, "splice.src")
+            if s.shape[-1] != cols or not s.is_contiguous():
+                raise SrgptError("splice: all sources must be contiguous with the same width")
+    out = torch.empty((rows, cols), dtype=BF16, device=src0.device)
+    check(_lib.load().srgpt_splice_rows_bf16(_p(src0), _p(src1), _p(src2), _p(src3), _p(src_id), _p(src_row), _p(out), rows,
+                                             cols, _stream()), "srgpt_splice_rows_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
+    """masks [n_img, M, IH, IW] (fp32 or bf16) -> normalised bf16 pooling weights [n_img, M, side*side]."""
+    if not masks.is_cuda or masks.dim() != 4 or not masks.is_contiguous():
+        raise SrgptError("mask_weights: expected a contiguous CUDA tensor [n_img, M, IH, IW]")
+    if masks.dtype not in (torch.float32, BF16):
+        raise SrgptError(f"mask_weights: unsupported dtype {masks.dtype}")
+    n, M, IH, IW = masks.shape
+    # base_extractor.py:53-57: scale_factor = (L / (IH*IW)) ** 0.5 in Python doubles; ATen then uses
+    # static_cast<float>(1.0 / scale_factor) as the source-index scale.
+    scale_factor = ((side * side) / (IH * IW)) ** 0.5
+    if int(IH * scale_factor) != side or int(IW * scale_factor) != side:
+        raise SrgptError(f"mask_weights: floor({IH}x{IW} * {scale_factor}) != {side} (non-square masks are unsupported)")
+    rscale = float(torch.tensor(1.0 / scale_factor, dtype=torch.float64).to(torch.float32))
+    w = torch.empty((n, M, side * side), dtype=BF16, device=masks.device)
+    check(_lib.load().srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), n, M, IH, IW, side, rscale, order,
+                                         _stream()), "srgpt_mask_weights")
+    return w
+
+
+def mask_pool(x: torch.Tensor, w: torch.Tensor, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [n_img, L, C] bf16, w [n_img, M, L] bf16 -> [n_img, M, C] bf16."""
+    _need(x, BF16, "mask_pool.x"); _need(w, BF16, "mask_pool.w")
+    if x.dim() != 3 or w.dim() != 3 or not x.is_contiguous() or not w.is_contiguous():
+        raise SrgptError("mask_pool: expected contiguous x [n, L, C] and w [n, M, L]")
+    n, L, Cc = x.shape
+    n2, M, L2 = w.shape
+    if n != n2 or L != L2:
+        raise SrgptError("mask_pool: shape mismatch between x and w")
+    need = _lib.load().srgpt_mask_pool_workspace(n, M, L, Cc)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
+    out = torch.empty((n, M, Cc), dtype=BF16, device=x.device)
+    check(_lib.load().srgpt_mask_pool_bf16(_p(x), _p(w), _p(out), _p(workspace), n, M, L, Cc, _stream()), "srgpt_mask_pool_bf16")
+    return out
+
+
+def adaptive_avgpool(x: torch.Tensor, side: int, out_side: int, order: int) -> torch.Tensor:
+    _need(x, BF16, "adaptive_avgpool.x")
+    n, L, Cc = x.shape
+    if L != side * side or not x.is_contiguous():
+        raise SrgptError("adaptive_avgpool: expected contiguous [n, side*side, C]")
+    y = torch.empty((n, out_side * out_side, Cc), dtype=BF16, device=x.device)
+    check(_lib.load().srgpt_adaptive_avgpool_bf16(_p(x), _p(y), n, side, out_side, Cc, order, _stream()),
+          "srgpt_adaptive_avgpool_bf16")
+    return y
+
+
+def reorder_rows(x: torch.Tensor, side: int, from_order: int, to_order: int) -> torch.Tensor:
+    _need(x, BF16, "reorder_rows.x")
+    n, L, Cc = x.shape
+    if L != side * side or not x.is_contiguous():
+        raise SrgptError("reorder_rows: expected contiguous [n, side*side, C]")
+    y = torch.empty_like(x)
+    check(_lib.load().srgpt_reorder_rows_bf16(_p(x), _p(y), n, side, Cc, from_order, to_order, _stream()), "srgpt_reorder_rows_bf16")
+    return y
+
+
+def depth_to_u8x3(depth: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """depth [h, w] or [1, h, w] fp32 -> [H, W, 3] uint8 (eval_spatial.py:99-105)."""
+    _need(depth, torch.float32, "depth_to_u8x3.depth")
+    d = depth.reshape(depth.shape[-2], depth.shape[-1]).contiguous()
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=depth.device)
+    ws = torch.empty(H * W + 2, dtype=torch.float32, device=depth.device)
+    check(_lib.load().srgpt_depth_to_u8x3(_p(d), d.shape[0], d.shape[1], _p(out), H, W, _p(ws), _stream()), "srgpt_depth_to_u8x3")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def attention_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, seqlen: int, n_heads: int,
+                      n_kv_heads: int, head_dim: int, scale: float, causal: bool,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: 2-D row-major views [batch*seqlen, heads*head_dim] (may be column slices of a fused qkv buffer)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, BF16, f"attention_prefill.{nm}")
+    q_ld, k_ld, v_ld = _rowmajor2d(q, "q"), _rowmajor2d(k, "k"), _rowmajor2d(v, "v")
+    if k_ld != v_ld:
+        raise SrgptError("attention_prefill: k and v must share a row stride")
+    if out is None:
+        out = torch.empty((batch * seqlen, n_heads * head_dim), dtype=BF16, device=q.device)
+    check(_lib.load().srgpt_attention_prefill_bf16(_p(q), _p(k), _p(v), _p(out), q_ld, k_ld, _rowmajor2d(out, "out"), batch,
+                                                   seqlen, n_heads, n_kv_heads, head_dim, scale, 1 if causal else 0, _stream()),
+          "srgpt_attention_prefill_bf16")
+    return out
+
+
+def rope_kv_append(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, cos_tab: torch.Tensor,
+                   sin_tab: torch.Tensor, start_pos: torch.Tensor, kv_pages: torch.Tensor, page_table: torch.Tensor,
+                   page_size: int) -> None:
+    _need(qkv, BF16, "rope_kv_append.qkv")
+    if not qkv.is_contiguous() or qkv.shape[1] != (n_heads + 2 * n_kv_heads) * head_dim:
+        raise SrgptError("rope_kv_append: qkv must be contiguous [rows, (nh + 2 nkv) * hd]")
+    _need(start_pos, torch.int32, "rope_kv_append.start_pos"); _need(page_table, torch.int32, "rope_kv_append.page_table")
+    check(_lib.load().srgpt_rope_kv_append_bf16(_p(qkv), qkv.shape[0], n_heads, n_kv_heads, head_dim, _p(cos_tab), _p(sin_tab),
+                                                _p(start_pos), _p(kv_pages), _p(page_table), page_size, _stream()),
+          "srgpt_rope_kv_append_bf16")
+
+
+def attention_decode(q: torch.Tensor, out: torch.Tensor, kv_pages: torch.Tensor, page_table: torch.Tensor, page_size: int,
+                     pos: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, scale: float) -> torch.Tensor:
+    check(_lib.load().srgpt_attention_decode_bf16(_p(q), _p(out), _p(kv_pages), _p(page_table), page_size, _p(pos), n_heads,
+                                                  n_kv_heads, head_dim, scale, _stream()), "srgpt_attention_decode_bf16")
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, norm_weight: Optional[torch.Tensor] = None, eps: float = 0.0,
+         residual: Optional[torch.Tensor] = None, mode: int = GEMV_PLAIN, n_heads: int = 0, n_kv_heads: int = 0,
+         head_dim: int = 0, cos_tab=None, sin_tab=None, pos=None, kv_pages=None, page_table=None, page_size: int = 0) -> torch.Tensor:
+    N, K = w.shape
+    check(_lib.load().srgpt_gemv_bf16(_p(x), _p(w), w.stride(0), _p(y), N, K, _p(norm_weight), eps, _p(residual), mode, n_heads,
+                                      n_kv_heads, head_dim, _p(cos_tab), _p(sin_tab), _p(pos), _p(kv_pages), _p(page_table),
+                                      page_size, _stream()), "srgpt_gemv_bf16")
+    return y
+
+
+def lm_head_workspace(V: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().srgpt_lm_head_workspace(V), dtype=torch.uint8, device=device)
+
+
+def lm_head_argmax(x: torch.Tensor, w: torch.Tensor, norm_weight: Optional[torch.Tensor], eps: float, workspace: torch.Tensor,
+                   out_ids: torch.Tensor, step: torch.Tensor, pos: torch.Tensor, embed_table: Optional[torch.Tensor] = None,
+                   next_x: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None) -> None:
+    V, K = w.shape
+    check(_lib.load().srgpt_lm_head_argmax_bf16(_p(x), _p(w), w.stride(0), V, K, _p(norm_weight), eps, _p(logits_out),
+                                                _p(workspace), _p(embed_table), _p(next_x), _p(out_ids), _p(step), _p(pos),
+                                                _stream()), "srgpt_lm_head_argmax_bf16")
+
+
+def argmax_f32(x: torch.Tensor) -> torch.Tensor:
+    _need(x, torch.float32, "argmax_f32.x")
+    rows, cols = x.shape
+    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    check(_lib.load().srgpt_argmax_f32(_p(x), rows, cols, _p(out), _stream()), "srgpt_argmax_f32")
+    return out

@@ -1,0 +1,100 @@
+"""Region extractor on the sm_100a kernels (reference: llava/model/region_extractor/
+base_extractor.py:112-173, type "regiongpt").
+
+feature_refinement: ConvT(k2,s2) -> LayerNorm2d -> GELU -> ConvT(k2,s2) -> GELU as two tcgen05
+GEMMs + one row LayerNorm kernel.  The up-sampled feature map stays in the *nested* pixel order the
+GEMMs emit (DESIGN.md "hres layout"); mask pooling and AdaptiveAvgPool2d(27) index it directly, so the
+37.7 MB/image tensor is written once and read once per consumer with no pixel-shuffle pass.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .config import LlavaConfig
+from .weights import RegionW
+
+ADA_POOL = 27  # base_extractor.py:123 ("hardcoded pooling size")
+
+
+class MaskPooling:
+    """base_extractor.py:27-84.  ``x`` [B, L, C]; ``order`` is the row order of x."""
+
+    def forward(self, x: torch.Tensor, mask_list: Optional[Sequence[Optional[torch.Tensor]]], order: int = ops.ORDER_ROWMAJOR,
+                return_list: bool = True) -> List[Optional[torch.Tensor]]:
+        B, L, _ = x.shape
+        side = int(round(L ** 0.5))
+        if mask_list is None:
+            mask_list = [None] * B
+        out: List[Optional[torch.Tensor]] = [None] * B
+        idx = [i for i in range(B) if mask_list[i] is not None]
+        if not idx:
+            return out
+        same = all(mask_list[i].shape == mask_list[idx[0]].shape and mask_list[i].dtype == mask_list[idx[0]].dtype for i in idx)
+        if same and len(idx) == B and B > 1:
+            masks = torch.stack([self._prep(mask_list[i], x.device) for i in idx], 0)
+            pooled = ops.mask_pool(x, ops.mask_weights(masks, side, order))
+            for j, i in enumerate(idx):
+                out[i] = pooled[j]
+        else:
+            for i in idx:
+                m = self._prep(mask_list[i], x.device)[None]
+                out[i] = ops.mask_pool(x[i:i + 1], ops.mask_weights(m, side, order))[0]
+        if not return_list:
+            return torch.cat([o for o in out if o is not None])
+        return out
+
+    @staticmethod
+    def _prep(mask: torch.Tensor, device) -> torch.Tensor:
+        m = mask.detach().to(device=device)
+        if m.dtype not in (torch.float32, torch.bfloat16):
+            m = m.float()  # base_extractor.py:55
+        return m.contiguous()
+
+    __call__ = forward
+
+
+class RegionExtractor:
+    def __init__(self, cfg: LlavaConfig, w: RegionW):
+        if cfg.region_extractor_type != "regiongpt":
+            raise NotImplementedError(f"{cfg.region_extractor_type} not implemented")  # base_extractor.py:161
+        self.cfg = cfg
+        self.w = w
+        self.mask_pooling = MaskPooling()
+        self.C = cfg.vision.hidden_size
+
+    def feature_refinement_nested(self, tower_features: torch.Tensor):
+        """[N, T, C] -> (hres in nested order [N, 16T, C], lres [N, 729, C] row-major)."""
+        N, T, C = tower_features.shape
+        P = int(round(T ** 0.5))
+        w = self.w
+        x = tower_features.reshape(N * T, C)
+        y1 = ops.gemm(x, w.deconv1_w, bias=w.deconv1_b, epilogue=ops.EPI_BIAS)  # [N*T, 4C] == [N*4T, C]
+        y1 = ops.layernorm(y1.view(N * T * 4, C), w.ln_w, w.ln_b, 1e-6, act=1)  # LayerNorm2d + GELU
+        y2 = ops.gemm(y1, w.deconv2_w, bias=w.deconv2_b, epilogue=ops.EPI_BIAS_GELU_ERF)  # [N*4T, 4C] == [N*16T, C]
+        hres = y2.view(N, 16 * T, C)
+        lres = ops.adaptive_avgpool(hres, 4 * P, ADA_POOL, ops.ORDER_NESTED)
+        return hres, lres
+
+    def feature_refinement(self, tower_features: torch.Tensor):
+        """Reference signature/layout (base_extractor.py:137-147): hres flattened row-major (H W)."""
+        hres, lres = self.feature_refinement_nested(tower_features)
+        side = 4 * int(round(tower_features.shape[1] ** 0.5))
+        return ops.reorder_rows(hres, side, ops.ORDER_NESTED, ops.ORDER_ROWMAJOR), lres
+
+    def extract_region_features(self, features: torch.Tensor, masks, proj_w, proj_b, order: int):
+        pooled = self.mask_pooling(features, masks, order=order, return_list=True)
+        return [None if p is None else ops.gemm(p.contiguous(), proj_w, bias=proj_b, epilogue=ops.EPI_BIAS) for p in pooled]
+
+    def forward(self, image_features: torch.Tensor, depth_features: Optional[torch.Tensor], masks, hres_order: int = ops.ORDER_ROWMAJOR):
+        """base_extractor.py:167-173.  ``image_features`` = hres (row-major by default, like the reference)."""
+        w = self.w
+        mask_embeds = self.extract_region_features(image_features, masks, w.rgb_w, w.rgb_b, hres_order)
+        depth_embeds = None
+        if depth_features is not None:
+            depth_embeds = self.extract_region_features(depth_features, masks, w.depth_w, w.depth_b, ops.ORDER_ROWMAJOR)
+        return mask_embeds, depth_embeds
+
+    __call__ = forward

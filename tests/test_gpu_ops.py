@@ -1,0 +1,382 @@
+"""Op-level parity of every C-ABI kernel against plain fp32 torch / the CPU oracle.  Needs a B200."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import srgpt_oracle as O
+from tests.util import BF16_1ROUND, BF16_CHAIN, assert_close, load_npz
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from spatialrgpt_b200 import _lib, ops as _ops
+    _lib.load()
+    sm, maj, mnr = _lib.device_info()
+    assert maj == 10, f"these tests need an sm_100 device, got sm_{maj}{mnr}"
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=BF):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 128, 128), (256, 256, 512), (259, 384, 512), (1, 128, 64), (3, 8, 8), (77, 200, 72),
+    (300, 4304, 1152), (300, 1152, 4304), (1024, 1152, 592), (259, 6144, 4096), (130, 272, 4096),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(ops, M, N, K):
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    ref = a.float() @ w.float().t()
+    out = ops.gemm(a.to(DEV), w.to(DEV))
+    assert_close(out, ref, **BF16_1ROUND, what=f"gemm {M}x{N}x{K}")
+    out32 = ops.gemm(a.to(DEV), w.to(DEV), out_fp32=True)
+    assert_close(out32, ref, rel_rms=1e-4, rel_max=1e-3, what=f"gemm fp32-out {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(259, 384, 512), (200, 296, 144), (1024, 1152, 1152)])
+def test_gemm_epilogues(ops, M, N, K):
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
+    acc = a.float() @ w.float().t()
+    ad, wd, bd, rd = a.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV)
+    assert_close(ops.gemm(ad, wd, bias=bd, epilogue=ops.EPI_BIAS), acc + bias.float(), **BF16_1ROUND, what="bias")
+    assert_close(ops.gemm(ad, wd, bias=bd, epilogue=ops.EPI_BIAS_GELU_TANH), F.gelu(acc + bias.float(), approximate="tanh"),
+                 **BF16_CHAIN, what="gelu_tanh")
+    assert_close(ops.gemm(ad, wd, bias=bd, epilogue=ops.EPI_BIAS_GELU_ERF), F.gelu(acc + bias.float()), **BF16_CHAIN, what="gelu_erf")
+    assert_close(ops.gemm(ad, wd, bias=bd, residual=rd, epilogue=ops.EPI_BIAS_RESIDUAL), acc + bias.float() + res.float(),
+                 **BF16_CHAIN, what="bias_residual")
+    assert_close(ops.gemm(ad, wd, residual=rd, epilogue=ops.EPI_BIAS_RESIDUAL), acc + res.float(), **BF16_CHAIN, what="residual")
+    # in-place residual (out aliases residual), as the decoder layers use it
+    x = rd.clone()
+    ops.gemm(ad, wd, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+    assert_close(x, acc + res.float(), **BF16_CHAIN, what="residual in place")
+    # broadcast residual rows (position embeddings): row % mod
+    mod = 37
+    pos = rnd(mod, N, seed=5)
+    ref = acc + bias.float() + pos.float()[torch.arange(M) % mod]
+    assert_close(ops.gemm(ad, wd, bias=bd, residual=pos.to(DEV), epilogue=ops.EPI_BIAS_RESIDUAL, res_row_mod=mod), ref,
+                 **BF16_CHAIN, what="pos-emb residual")
+    # SwiGLU over interleaved (gate, up) rows
+    g, u = acc[:, 0::2], acc[:, 1::2]
+    assert_close(ops.gemm(ad, wd, epilogue=ops.EPI_SWIGLU), F.silu(g) * u, **BF16_CHAIN, what="swiglu")
+
+
+def test_gemm_strided_views(ops):
+    """A and the output may be column slices of wider buffers (fused qkv)."""
+    M, K, N = 200, 144, 136
+    big = rnd(M, 3 * K, seed=7).to(DEV)
+    w = rnd(N, K, seed=8, scale=K ** -0.5)
+    a = big[:, K:2 * K]
+    outbuf = torch.zeros(M, 2 * N, dtype=BF, device=DEV)
+    ops.gemm(a, w.to(DEV), out=outbuf[:, N:])
+    assert_close(outbuf[:, N:], a.float().cpu() @ w.float().t(), **BF16_1ROUND, what="strided")
+    assert float(outbuf[:, :N].abs().max()) == 0.0
+
+
+def test_gemm_rejects_bad_args(ops):
+    from spatialrgpt_b200 import SrgptError
+    a, w = rnd(16, 12).to(DEV), rnd(8, 12).to(DEV)  # K=12 -> 24-byte rows, not TMA-able
+    with pytest.raises(SrgptError):
+        ops.gemm(a, w)
+    with pytest.raises(SrgptError):
+        ops.gemm(rnd(16, 16), rnd(8, 16))  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------ row ops
+@pytest.mark.parametrize("rows,cols", [(7, 144), (300, 1152), (50, 4608), (3, 8)])
+def test_layernorm(ops, rows, cols):
+    x, w, b = rnd(rows, cols, seed=1, scale=2.0), 1 + 0.1 * rnd(cols, seed=2).float(), 0.1 * rnd(cols, seed=3).float()
+    w, b = w.to(BF), b.to(BF)
+    ref = F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-6)
+    assert_close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-6), ref, **BF16_1ROUND, what="layernorm")
+    assert_close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-6, act=1), F.gelu(ref), **BF16_CHAIN, what="layernorm+gelu")
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 256), (259, 4096), (2, 2560)])
+def test_rmsnorm(ops, rows, cols):
+    x, w = rnd(rows, cols, seed=1, scale=3.0), (1 + 0.1 * rnd(cols, seed=2).float()).to(BF)
+    ref = O.rms_norm(x.float(), w.float(), 1e-5)
+    assert_close(ops.rmsnorm(x.to(DEV), w.to(DEV), 1e-5), ref, **BF16_CHAIN, what="rmsnorm")
+    # bit-exact against the rounding-faithful bf16 restatement
+    ref16 = O.rms_norm(x, w, 1e-5)
+    got = ops.rmsnorm(x.to(DEV), w.to(DEV), 1e-5).cpu()
+    mism = (got.float() != ref16.float()).float().mean().item()
+    assert mism < 2e-3, f"{mism:.2e} of elements differ from the bf16 restatement"  # rsqrt ulp differences only
+
+
+@pytest.mark.parametrize("side,C", [(27, 144), (27, 1152), (4, 8), (5, 16)])
+def test_downsample_layernorm(ops, side, C):
+    x = rnd(2, side * side, C, seed=4)
+    w, b = (1 + 0.1 * rnd(4 * C, seed=5).float()).to(BF), (0.1 * rnd(4 * C, seed=6).float()).to(BF)
+    ds = O.downsample_block(x.float())
+    ref = F.layer_norm(ds, (4 * C,), w.float(), b.float(), 1e-5)
+    out = ops.downsample_layernorm(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5)
+    assert out.shape == ref.shape
+    assert_close(out, ref, **BF16_1ROUND, what="downsample+LN")
+
+
+@pytest.mark.parametrize("R,dtype", [(56, torch.float32), (112, BF), (448, torch.float32)])
+def test_patchify_matches_conv(ops, R, dtype):
+    n, ps, D = 2, 14, 32
+    img = rnd(n, 3, R, R, seed=9, dtype=dtype)
+    wconv = rnd(D, 3, ps, ps, seed=10, scale=0.05)
+    ldk = 592
+    A = ops.patchify(img.to(DEV), ps, ldk).cpu()
+    assert A.shape == (n * (R // ps) ** 2, ldk)
+    assert float(A[:, 588:].abs().max()) == 0.0
+    ref = F.conv2d(img.to(BF).float(), wconv.float(), stride=ps).flatten(2).transpose(1, 2).reshape(-1, D)
+    got = A[:, :588].float() @ wconv.float().reshape(D, -1).t()
+    assert_close(got, ref, rel_rms=1e-5, rel_max=1e-4, what="patchify")
+
+
+def test_splice_rows(ops):
+    H = 64
+    srcs = [rnd(10 + i, H, seed=20 + i).to(DEV) for i in range(4)]
+    g = torch.Generator().manual_seed(1)
+    sid = torch.randint(0, 4, (50,), generator=g).to(torch.int32)
+    srow = torch.tensor([int(torch.randint(0, 10 + int(s), (1,), generator=g)) for s in sid], dtype=torch.int32)
+    out = ops.splice_rows(*srcs, sid.to(DEV), srow.to(DEV)).cpu()
+    ref = torch.stack([srcs[int(s)][int(r)].cpu() for s, r in zip(sid, srow)])
+    assert torch.equal(out, ref)
+
+
+def test_argmax_first_index_on_ties(ops):
+    x = torch.zeros(3, 1000)
+    x[0, 17] = x[0, 900] = 5.0
+    x[1, 999] = 1.0
+    x[2] = -1.0
+    assert ops.argmax_f32(x.to(DEV)).tolist() == [17, 999, 0]
+
+
+# ------------------------------------------------------------------------------------------ region kernels
+@pytest.mark.parametrize("tag", ["rgb448", "depth448", "rgb384", "odd336"])
+def test_mask_pooling_golden(ops, golden_dir, tag):
+    """Reference MaskPooling known answers (tests/golden/op_kats.npz), row-major features."""
+    g = load_npz(os.path.join(golden_dir, "op_kats.npz"))
+    x, masks = g[f"{tag}_x"].to(BF), g[f"{tag}_masks"].float()
+    side = int(round(x.shape[1] ** 0.5))
+    w = ops.mask_weights(masks[None].to(DEV), side, ops.ORDER_ROWMAJOR)
+    # the resampled + normalised weights are bit-exact vs torch (same fp32 taps, same bf16 roundings)
+    m = F.interpolate(masks[None], scale_factor=(x.shape[1] / masks.shape[-1] ** 2) ** 0.5, mode="bilinear")[0].to(BF)
+    wref = (m.flatten(1) / (m.sum(dim=(-1, -2)) + 1e-8).unsqueeze(-1))
+    frac = (w[0].cpu().float() != wref.float()).float().mean().item()
+    assert frac < 1e-3, f"{frac:.2e} of the mask weights differ from torch"
+    out = ops.mask_pool(x.to(DEV), w)[0]
+    assert_close(out, g[f"{tag}_out_f32"], **BF16_CHAIN, what=f"mask_pool {tag} vs fp32 reference")
+    assert_close(out, g[f"{tag}_out_bf16"], **BF16_CHAIN, what=f"mask_pool {tag} vs bf16 reference")
+
+
+def _nested_perm(side):
+    P = side // 4
+    idx = torch.empty(side * side, dtype=torch.long)
+    for y in range(side):
+        for x in range(side):
+            idx[y * side + x] = (((y >> 2) * P + (x >> 2)) << 4) | ((((y >> 1) & 1) * 2 + ((x >> 1) & 1)) << 2) | ((y & 1) * 2 + (x & 1))
+    return idx  # idx[rowmajor] = nested row
+
+
+@pytest.mark.parametrize("side,C,M", [(16, 144, 3), (128, 1152, 8), (128, 1152, 11), (32, 256, 16)])
+def test_mask_pool_nested_order_and_multi_pass(ops, side, C, M):
+    R = side * 7 // 2
+    x = rnd(2, side * side, C, seed=3)
+    masks = (torch.rand(2, M, R, R, generator=torch.Generator().manual_seed(4)) > 0.7).float()
+    masks[:, 0] = 1.0  # all-ones mask -> plain mean
+    ref = torch.stack(O.mask_pooling(x.float(), [masks[0], masks[1]]))
+    perm = _nested_perm(side)
+    xn = torch.empty_like(x)
+    xn[:, perm] = x
+    w = ops.mask_weights(masks.to(DEV), side, ops.ORDER_NESTED)
+    out = ops.mask_pool(xn.to(DEV), w)
+    assert_close(out, ref, **BF16_CHAIN, what="nested mask_pool")
+    assert_close(out[:, 0], x.float().mean(1), **BF16_CHAIN, what="all-ones mask == mean")
+    # reorder kernel round trip
+    back = ops.reorder_rows(xn.to(DEV), side, ops.ORDER_NESTED, ops.ORDER_ROWMAJOR).cpu()
+    assert torch.equal(back, x)
+    # bf16 masks are accepted as well
+    w2 = ops.mask_weights(masks.to(BF).to(DEV), side, ops.ORDER_NESTED)
+    assert torch.equal(w2, w)
+
+
+@pytest.mark.parametrize("side,C", [(16, 144), (128, 64), (96, 32), (108, 16)])
+def test_adaptive_avgpool(ops, side, C):
+    x = rnd(2, side * side, C, seed=5)
+    ref = F.adaptive_avg_pool2d(x.float().view(2, side, side, C).permute(0, 3, 1, 2), 27).flatten(2).transpose(1, 2)
+    out = ops.adaptive_avgpool(x.to(DEV), side, 27, ops.ORDER_ROWMAJOR)
+    assert_close(out, ref, **BF16_1ROUND, what="adaptive_avgpool row-major")
+    if side % 4 == 0:
+        xn = torch.empty_like(x)
+        xn[:, _nested_perm(side)] = x
+        out2 = ops.adaptive_avgpool(xn.to(DEV), side, 27, ops.ORDER_NESTED)
+        assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("h,w,H,W", [(37, 53, 448, 448), (518, 518, 480, 640), (8, 8, 8, 8)])
+def test_depth_to_u8x3(ops, h, w, H, W):
+    d = torch.rand(1, h, w, generator=torch.Generator().manual_seed(6)) * 10 + 1
+    ref = O.depth_to_u8x3(d, H, W)
+    out = ops.depth_to_u8x3(d.to(DEV), H, W).cpu()
+    assert out.shape == ref.shape and out.dtype == torch.uint8
+    diff = (out.int() - ref.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3  # fp32 association at a truncation boundary
+    assert int(out.min()) == 0 and int(out.max()) == 255
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _sdpa_ref(q, k, v, nh, nkv, hd, scale, causal):
+    B, S = q.shape[0], q.shape[1]
+    qh = q.float().view(B, S, nh, hd).transpose(1, 2)
+    kh = k.float().view(B, S, nkv, hd).transpose(1, 2).repeat_interleave(nh // nkv, 1)
+    vh = v.float().view(B, S, nkv, hd).transpose(1, 2).repeat_interleave(nh // nkv, 1)
+    att = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        att = att.masked_fill(~torch.ones(S, S, dtype=torch.bool).tril(), float("-inf"))
+    return (att.softmax(-1) @ vh).transpose(1, 2).reshape(B, S, nh * hd)
+
+
+@pytest.mark.parametrize("B,S,nh,nkv,hd,causal", [
+    (2, 16, 2, 2, 72, False), (2, 64, 2, 2, 72, False), (1, 1024, 4, 4, 72, False), (3, 100, 2, 2, 72, False),
+    (1, 259, 8, 2, 128, True), (2, 65, 4, 1, 128, True), (1, 1, 2, 2, 128, True), (1, 300, 4, 4, 128, True),
+    (1, 130, 2, 2, 128, False), (1, 97, 2, 1, 64, True),
+])
+def test_attention_prefill(ops, B, S, nh, nkv, hd, causal):
+    qkv = rnd(B * S, (nh + 2 * nkv) * hd, seed=11)
+    qd, kd = nh * hd, nkv * hd
+    q, k, v = qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:]
+    scale = hd ** -0.5
+    ref = _sdpa_ref(q.reshape(B, S, -1), k.reshape(B, S, -1), v.reshape(B, S, -1), nh, nkv, hd, scale, causal).reshape(B * S, -1)
+    d = qkv.to(DEV)
+    out = ops.attention_prefill(d[:, :qd], d[:, qd:qd + kd], d[:, qd + kd:], B, S, nh, nkv, hd, scale, causal)
+    assert_close(out, ref, rel_rms=1e-2, rel_max=8e-2, what=f"attention B{B} S{S} hd{hd} causal={causal}")
+
+
+def _rope_tables(hd, theta, max_pos):
+    from spatialrgpt_b200.config import LlamaDims
+    from spatialrgpt_b200.llama_decoder import build_rope_tables
+    return build_rope_tables(LlamaDims(head_dim=hd, rope_theta=theta), max_pos, DEV)
+
+
+@pytest.mark.parametrize("S,nh,nkv,theta", [(37, 4, 2, 10000.0), (259, 8, 2, 500000.0), (16, 2, 2, 10000.0)])
+def test_rope_kv_append_and_decode_attention(ops, S, nh, nkv, theta):
+    hd, page = 128, 16
+    cfg = O.OracleConfig(head_dim=hd, rope_theta=theta)
+    qkv = rnd(S, (nh + 2 * nkv) * hd, seed=12)
+    cos, sin = _rope_tables(hd, theta, 512)
+    cr, sr = O.rope_cos_sin(cfg, torch.arange(512), BF)
+    assert torch.equal(cos.cpu(), cr[:, : hd // 2]) and torch.equal(sin.cpu(), sr[:, : hd // 2])
+    n_pages = (S + 1 + page - 1) // page + 2
+    pages = torch.zeros(n_pages, 2, page, nkv, hd, dtype=BF, device=DEV)
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(3)).to(torch.int32)  # scattered physical pages
+    pt = perm.to(DEV)
+    d = qkv.to(DEV).clone()
+    ops.rope_kv_append(d, nh, nkv, hd, cos, sin, torch.zeros(1, dtype=torch.int32, device=DEV), pages, pt, page)
+    # reference: bf16 rope exactly as modeling_llama.py:186-191
+    q = qkv[:, : nh * hd].view(S, nh, hd).transpose(0, 1)
+    k = qkv[:, nh * hd:(nh + nkv) * hd].view(S, nkv, hd).transpose(0, 1)
+    v = qkv[:, (nh + nkv) * hd:].view(S, nkv, hd)
+    c, s = cr[:S], sr[:S]
+    qr = (q * c[None]) + (O.rotate_half(q) * s[None])
+    kr = (k * c[None]) + (O.rotate_half(k) * s[None])
+    got = d.cpu()
+    assert torch.equal(got[:, : nh * hd].view(S, nh, hd).transpose(0, 1), qr)
+    assert torch.equal(got[:, nh * hd:(nh + nkv) * hd].view(S, nkv, hd).transpose(0, 1), kr)
+    pc = pages.cpu()
+    for pos in (0, S // 2, S - 1):
+        pg, sl = int(perm[pos // page]), pos % page
+        assert torch.equal(pc[pg, 0, sl], kr[:, pos]) and torch.equal(pc[pg, 1, sl], v[pos])
+    # decode attention for a new query at position S-1 over the S cached tokens
+    qn = rnd(nh * hd, seed=13)
+    out = torch.empty(nh * hd, dtype=BF, device=DEV)
+    ops.attention_decode(qn.to(DEV), out, pages, pt, page, torch.tensor([S - 1], dtype=torch.int32, device=DEV), nh, nkv, hd, hd ** -0.5)
+    kk = kr.float().repeat_interleave(nh // nkv, 0)
+    vv = v.float().transpose(0, 1).repeat_interleave(nh // nkv, 0)
+    att = torch.einsum("hd,hsd->hs", qn.float().view(nh, hd), kk) * hd ** -0.5
+    ref = torch.einsum("hs,hsd->hd", att.softmax(-1), vv).reshape(-1)
+    assert_close(out, ref, rel_rms=6e-3, rel_max=5e-2, what="decode attention")
+
+
+# ------------------------------------------------------------------------------------------ GEMV (decode)
+@pytest.mark.parametrize("N,K", [(512, 256), (4096, 4096), (6144, 4096), (4096, 14336), (1000, 1032), (2, 8)])
+def test_gemv_plain_and_residual(ops, N, K):
+    x, w, r = rnd(K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    ref = w.float() @ x.float()
+    y = torch.empty(N, dtype=BF, device=DEV)
+    ops.gemv(x.to(DEV), w.to(DEV), y)
+    assert_close(y, ref, **BF16_1ROUND, what="gemv")
+    h = r.to(DEV).clone()
+    ops.gemv(x.to(DEV), w.to(DEV), h, residual=h)
+    assert_close(h, ref + r.float(), **BF16_CHAIN, what="gemv + residual in place")
+
+
+@pytest.mark.parametrize("I,K", [(384, 256), (14336, 4096), (100, 64)])
+def test_gemv_rmsnorm_swiglu(ops, I, K):
+    x, nw = rnd(K, seed=1, scale=2.0), (1 + 0.1 * rnd(K, seed=4).float()).to(BF)
+    gate, up = rnd(I, K, seed=2, scale=K ** -0.5), rnd(I, K, seed=3, scale=K ** -0.5)
+    from spatialrgpt_b200.weights import interleave_rows
+    w = interleave_rows(gate, up)
+    xn = O.rms_norm(x.float(), nw.float(), 1e-5)
+    ref = F.silu(gate.float() @ xn) * (up.float() @ xn)
+    y = torch.empty(I, dtype=BF, device=DEV)
+    ops.gemv(x.to(DEV), w.to(DEV), y, norm_weight=nw.to(DEV), eps=1e-5, mode=ops.GEMV_SWIGLU)
+    assert_close(y, ref, **BF16_CHAIN, what="gemv rmsnorm+swiglu")
+
+
+@pytest.mark.parametrize("nh,nkv,K,pos", [(2, 1, 256, 5), (32, 8, 4096, 300), (4, 4, 512, 0)])
+def test_gemv_qkv_rope_cache(ops, nh, nkv, K, pos):
+    hd, page = 128, 16
+    N = (nh + 2 * nkv) * hd
+    x, nw, w = rnd(K, seed=1, scale=2.0), (1 + 0.1 * rnd(K, seed=4).float()).to(BF), rnd(N, K, seed=2, scale=K ** -0.5)
+    cos, sin = _rope_tables(hd, 10000.0, 512)
+    n_pages = pos // page + 2
+    pages = torch.zeros(n_pages, 2, page, nkv, hd, dtype=BF, device=DEV)
+    pt = torch.arange(n_pages - 1, -1, -1, dtype=torch.int32, device=DEV)
+    q = torch.empty(nh * hd, dtype=BF, device=DEV)
+    ops.gemv(x.to(DEV), w.to(DEV), q, norm_weight=nw.to(DEV), eps=1e-5, mode=ops.GEMV_QKV_ROPE, n_heads=nh, n_kv_heads=nkv,
+             head_dim=hd, cos_tab=cos, sin_tab=sin, pos=torch.tensor([pos], dtype=torch.int32, device=DEV), kv_pages=pages,
+             page_table=pt, page_size=page)
+    xn = O.rms_norm(x.float(), nw.float(), 1e-5)
+    full = (w.float() @ xn)
+    c, s = cos[pos].cpu().float().repeat(2), sin[pos].cpu().float().repeat(2)
+    qr = full[: nh * hd].view(nh, hd)
+    kr = full[nh * hd:(nh + nkv) * hd].view(nkv, hd)
+    vr = full[(nh + nkv) * hd:].view(nkv, hd)
+    qref = qr * c + O.rotate_half(qr) * s
+    kref = kr * c + O.rotate_half(kr) * s
+    assert_close(q.view(nh, hd), qref, **BF16_CHAIN, what="q rope")
+    pg = int(pt[pos // page])
+    assert_close(pages[pg, 0, pos % page], kref, **BF16_CHAIN, what="k cache")
+    assert_close(pages[pg, 1, pos % page], vr, **BF16_CHAIN, what="v cache")
+
+
+@pytest.mark.parametrize("V,K", [(512, 256), (32003, 512), (128259, 4096)])
+def test_lm_head_argmax(ops, V, K):
+    x, nw, w = rnd(K, seed=1), (1 + 0.1 * rnd(K, seed=4).float()).to(BF), rnd(V, K, seed=2, scale=4 * K ** -0.5)
+    emb = rnd(V, K, seed=5)
+    xn = O.rms_norm(x.float(), nw.float(), 1e-5)
+    ref = (w.float() @ xn)
+    ws = ops.lm_head_workspace(V, DEV)
+    out_ids = torch.full((8,), -1, dtype=torch.int64, device=DEV)
+    step = torch.tensor([3], dtype=torch.int32, device=DEV)
+    pos = torch.tensor([41], dtype=torch.int32, device=DEV)
+    nxt = torch.zeros(K, dtype=BF, device=DEV)
+    logits = torch.empty(V, dtype=torch.float32, device=DEV)
+    ops.lm_head_argmax(x.to(DEV), w.to(DEV), nw.to(DEV), 1e-5, ws, out_ids, step, pos, embed_table=emb.to(DEV), next_x=nxt, logits_out=logits)
+    assert_close(logits, ref, **BF16_1ROUND, what="logits")
+    tok = int(out_ids[3])
+    assert tok == int(torch.argmax(logits.cpu())), "argmax must agree with its own logits (first index on ties)"
+    assert float(ref[tok]) >= float(ref.max()) - 0.02 * float(ref.std())
+    assert int(step) == 4 and int(pos) == 42
+    assert torch.equal(nxt.cpu(), emb[tok])
+    assert out_ids.tolist()[:3] == [-1, -1, -1]
