@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on its config c2:
+
+    generated tokens/sec, SpatialRGPT-VILA1.5-8B shape (SigLIP-so400m @448 px + Llama-3-8B), one image,
+    8 mask regions, depth branch ON, 64-token prompt, 128 greedy tokens, batch 1 per GPU.
+
+A "step" is one complete request through the hot path (2 tower passes, deconv refinement, mask
+pooling, projector, splice, Llama prefill, 128 greedy tokens).  Synthetic inputs / random-init weights
+of the named architecture (no checkpoints offline).
+
+  python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of value / e2e / roofline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_REGIONS, T_TEXT, NEW_TOKENS = 8, 64, 128
+METRIC = "generated_tokens_per_sec"
+UNIT = "tokens/s"
+WORKLOAD = ("c2: SigLIP-so400m@448px + Llama-3-8B, 1 image, 8 mask regions, depth ON, 64-token prompt "
+            "(S=259 after splice), 128 greedy tokens, batch 1 per GPU")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic request, generated once on the host
+# --------------------------------------------------------------------------------------------------
+def make_request(cfg, seed):
+    from spatialrgpt_b200.synth import synth_request
+    return synth_request(cfg, N_REGIONS, T_TEXT, seed)
+
+
+def algorithmic_numbers(cfg):
+    """Per-request FLOPs / bytes (SURVEY.md §8d formulas)."""
+    v, l = cfg.vision, cfg.llama
+    T, Dv, Iv, Lv = v.grid ** 2, v.hidden_size, v.intermediate_size, v.num_hidden_layers - 1
+    f_vit = Lv * (2 * T * (4 * Dv * Dv + 2 * Dv * Iv) + 4 * T * T * Dv) + 2 * T * 3 * v.patch_size ** 2 * Dv
+    f_ref = 2 * T * Dv * 4 * Dv + 2 * 4 * T * Dv * 4 * Dv
+    H, I, nh, nkv, hd, V = l.hidden_size, l.intermediate_size, l.num_attention_heads, l.num_key_value_heads, l.head_dim, l.vocab_size
+    f_proj = 196 * 2 * (4 * Dv * H + H * H)
+    f_tok = l.num_hidden_layers * 2 * (H * nh * hd + 2 * H * nkv * hd + nh * hd * H + 3 * H * I)
+    S = T_TEXT - 1 + 196
+    f_prefill = S * f_tok + l.num_hidden_layers * 2 * S * S * nh * hd + 2 * H * V
+    w_stream = (l.num_hidden_layers * (H * (nh + 2 * nkv) * hd + nh * hd * H + 3 * H * I + 2 * H) + H + V * H) * 2
+    kv_per_tok = l.num_hidden_layers * 2 * nkv * hd * 2
+    return dict(S=S, flops_ttft=2 * f_vit + f_ref + f_proj + f_prefill, w_stream=w_stream, kv_per_tok=kv_per_tok,
+                gateup_bytes=2 * I * H * 2)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from spatialrgpt_b200 import baseline_config, ops
+    from spatialrgpt_b200.llava_llama import LlavaLlamaModel
+    from spatialrgpt_b200.weights import random_init
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = baseline_config("c2")
+    model = LlavaLlamaModel(cfg, random_init(cfg, dev, seed=0, n_tower_layers=cfg.vision.num_hidden_layers - 1), max_seq_len=1024)
+    nums = algorithmic_numbers(cfg)
+    hbm_peak, tensor_peak, peak_src = load_peaks()
+
+    input_ids, images, depths, masks = make_request(cfg, 1234 + rank)
+    pin = lambda t: t.pin_memory()  # noqa: E731
+    h_ids, h_img, h_dep, h_msk = pin(input_ids), pin(images), pin(depths), pin(masks[0])
+    d_ids, d_img, d_dep, d_msk = (t.to(dev) for t in (h_ids, h_img, h_dep, h_msk))
+    gen_kw = dict(do_sample=False, max_new_tokens=NEW_TOKENS, use_cache=True)
+
+    def step_device():
+        return model.generate(d_ids, images=d_img, depths=d_dep, masks=[d_msk], **gen_kw)
+
+    def step_e2e():
+        ids = h_ids.to(dev, non_blocking=True)
+        im = h_img.to(dev, non_blocking=True)
+        de = h_dep.to(dev, non_blocking=True)
+        mk = h_msk.to(dev, non_blocking=True)
+        out = model.generate(ids, images=im, depths=de, masks=[mk], **gen_kw)
+        return out.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_tok = 0
+        for _ in range(steps):
+            n_tok += int(fn().numel())
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:  # max over ranks (device time), total tokens via allgather
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            cnt = torch.tensor([n_tok], device=dev, dtype=torch.int64)
+            allc = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(allc, cnt)
+            n_tok = int(sum(int(c) for c in allc))
+        return ms, n_tok
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES = 0
+    ms, n_tok = timed(step_device, args.steps)
+    launches = ops.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, n_tok_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-kernel roofline of the dominant kernel, timed live with CUDA events: the gate/up GEMV
+    roof = None
+    if rank == 0:
+        llm = model.llm
+        evs = []
+        n_steps = 4
+        for _ in range(n_steps):
+            d, w = llm.dims, llm.w
+            for l, lw in enumerate(w.layers):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.gemv(llm.h, lw.gateup_w, llm.act_buf, norm_weight=lw.post_norm, eps=d.rms_norm_eps, mode=ops.GEMV_SWIGLU)
+                b.record()
+                evs.append((a, b))
+        torch.cuda.synchronize()
+        dur = [a.elapsed_time(b) for a, b in evs][len(w.layers):]  # drop the first (warm) pass
+        avg_ms = sum(dur) / len(dur)
+        achieved = nums["gateup_bytes"] / avg_ms / 1e6
+        # whole decode step, for context (graph replay timed with events)
+        llm._ensure_graph(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        llm.step.zero_(); llm.pos.fill_(nums["S"])
+        a.record()
+        for _ in range(32):
+            llm._graph.replay()
+        b.record(); torch.cuda.synchronize()
+        step_ms = a.elapsed_time(b) / 32
+        step_bytes = nums["w_stream"] + nums["kv_per_tok"] * (nums["S"] + 16)
+        roof = {"kernel": "gemv_kernel<SWIGLU> (rmsnorm + gate/up_proj 4096->2x14336 + SwiGLU), decode", "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                "traffic": None, "peak_source": peak_src, "bytes_per_launch": nums["gateup_bytes"], "avg_launch_ms": round(avg_ms, 5),
+                "decode_step": {"ms": round(step_ms, 4), "algorithmic_GBps": round(step_bytes / step_ms / 1e6, 1),
+                                "frac_hbm": round(step_bytes / step_ms / 1e6 / hbm_peak, 4), "kernels": llm.kernels_per_decode_step}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_reference_sample(budget_s=20.0)
+    line = {
+        "metric": METRIC, "value": round(n_tok / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "requests_per_step_per_gpu": 1, "new_tokens": NEW_TOKENS, "parallelism": f"replicas x{world}",
+                   "l2": "working set per step (16 GB of weights) exceeds the 126 MB L2; no flush needed",
+                   "ttft_flops": nums["flops_ttft"]},
+        "clocks": clocks,
+        "e2e": {"value": round(n_tok_e2e / (ms_e2e / 1e3), 2), "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_ids, h_img, h_dep, h_msk))),
+                "d2h_bytes_per_step": NEW_TOKENS * 8, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference (oracle port), bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def cpu_reference_sample(budget_s: float = 20.0, decode_tokens: int = 4):
+    """Times the reference algorithm (oracle/srgpt_oracle.py, the pinned CPU restatement of the
+    reference's PyTorch path) on the host cores for config c2 on a bounded sample:
+    ONE SigLIP layer (of 26 executed x 2 images), the full refinement / pooling / projector stage, ONE
+    Llama layer of prefill at S=259 (of 32) and `decode_tokens` decode steps of ONE layer (+ lm_head),
+    fp32 compute; per-stage times are scaled by the layer / token counts to one full request."""
+    from oracle import srgpt_oracle as O
+    import torch.nn.functional as F
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    if "w" not in _CPU_STATE:
+        oc = O.OracleConfig(v_layers=2, layers=1)  # widths of c2; tower runs v_layers-1 = 1 layer
+        _CPU_STATE["oc"] = oc
+        _CPU_STATE["w"] = O.make_weights(oc, seed=0, dtype=torch.float32)
+        _CPU_STATE["req"] = O.synth_request(oc, N_REGIONS, T_TEXT, seed=1234)
+    oc, w, (input_ids, images, depths, masks) = _CPU_STATE["oc"], _CPU_STATE["w"], _CPU_STATE["req"]
+    full_v, full_l = 26, 32
+    lm = w["llm"]["lm_head.weight"]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        tf = O.vision_tower_forward(oc, w["vision_tower"], images)  # patch embed + 1 layer
+        t_vit1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        hres, lres = O.feature_refinement(oc, w["region_extractor"], tf)
+        me, de = O.region_extractor_forward(oc, w["region_extractor"], hres, tf, masks)  # tf stands in for the depth pass output
+        feats = O.mm_projector_forward(oc, w["mm_projector"], lres)
+        emb = O.splice_embeddings(oc, w["llm"]["model.embed_tokens.weight"], input_ids, feats, me, de)[0]
+        t_region = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        logits, cache = O.llama_forward(oc, w["llm"], emb, None)  # 1 layer + final norm + lm_head over all S rows (modeling_llama.py:1044)
+        t_prefill1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        F.linear(emb, lm)
+        t_lm_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        nxt = int(torch.argmax(logits[-1]))
+        for _ in range(decode_tokens):
+            logits, cache = O.llama_forward(oc, w["llm"], w["llm"]["model.embed_tokens.weight"][nxt][None], cache)
+            nxt = int(torch.argmax(logits[-1]))
+        t_dec = (time.perf_counter() - t0) / decode_tokens
+        t0 = time.perf_counter()
+        for _ in range(decode_tokens):
+            F.linear(emb[:1], lm)
+        t_lm_1 = (time.perf_counter() - t0) / decode_tokens
+    lay_p = max(t_prefill1 - t_lm_s, 0.0)
+    lay_d = max(t_dec - t_lm_1, 0.0)
+    t_request = 2 * t_vit1 * full_v + t_region + lay_p * full_l + t_lm_s + (NEW_TOKENS - 1) * (lay_d * full_l + t_lm_1)
+    return {"value": round(NEW_TOKENS / t_request, 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle port, fp32, {threads} threads: 1 of 26 SigLIP layers (x2 images), full refinement/pooling/projector/"
+                       f"splice, 1 of 32 Llama layers at S=259 and {decode_tokens} decode tokens of 1 layer; stage times scaled by "
+                       f"layer/token counts to one 128-token request ({t_request:.1f} s est.)"),
+            "stage_s": {"vit_1layer_1img": round(t_vit1, 3), "region_projector_splice": round(t_region, 3),
+                        "llama_prefill_1layer": round(lay_p, 3), "lm_head_all_rows": round(t_lm_s, 3),
+                        "llama_decode_1layer_per_token": round(lay_d, 4), "lm_head_per_token": round(t_lm_1, 4)},
+            "sample_cpu_seconds": round(t_vit1 + t_region + t_prefill1 + t_dec * decode_tokens, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    res = None
+    for _ in range(warm):
+        res = cpu_reference_sample(decode_tokens=2)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(steps):
+        res = cpu_reference_sample(decode_tokens=2)
+        vals.append(res["value"])
+    wall = time.perf_counter() - t0
+    v = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": round(wall / max(steps, 1) * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (CPU)", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {**res, "value": v},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", 1))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
+                   "--steps", str(args.steps), "--warmup", str(args.warmup)]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

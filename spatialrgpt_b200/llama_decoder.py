@@ -203,6 +203,7 @@ class LlamaDecoder:
                     break
             if use_graph and not return_logits:
                 self._graph.replay()
+                ops.LAUNCHES += self.kernels_per_decode_step
             else:
                 self._decode_step_launch(seq, None if logits is None else logits[n])
             n += 1

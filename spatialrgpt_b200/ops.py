@@ -10,13 +10,26 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import SrgptError, check
+from ._lib import SrgptError
+from ._lib import check as _check_rc
+
+_KERNELS_PER_CALL = {"srgpt_mask_pool_bf16": 2, "srgpt_lm_head_argmax_bf16": 2, "srgpt_depth_to_u8x3": 3}
+
+
+def check(rc: int, what: str) -> None:
+    global LAUNCHES
+    _check_rc(rc, what)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GELU_ERF, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(6)
 GEMV_PLAIN, GEMV_SWIGLU, GEMV_QKV_ROPE = range(3)
 ORDER_ROWMAJOR, ORDER_NESTED = 0, 2
 
 BF16 = torch.bfloat16
+
+# number of OUR kernels launched through this module (bench.py's `gpu_launches`); CUDA-graph replays
+# are added by the decoder (kernels_per_decode_step per replay)
+LAUNCHES = 0
 
 
 def _stream() -> int:
