@@ -263,11 +263,15 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, int n_heads, int n_kv_heads, int h
 }
 
 // ---------------------------------------------------------------------------------------------
-// decode attention: one CTA per query head, 16 half-warps each own kv positions j = hw, hw+16, ...
-// every lane holds 8 of the 128 head dims (one 16-byte load per K/V row).
+// decode attention: one CTA per query head, 32 half-warps; half-warp hw owns kv positions
+// j = hw, hw+32, ...; every lane holds 8 of the 128 head dims (one 16-byte load per K/V row).
+// The kernel is latency-bound (a few hundred KB per head), so the page table is staged in shared
+// memory and four positions' K/V rows are requested before any of them is consumed.
 // ---------------------------------------------------------------------------------------------
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 512;
 constexpr int DEC_HW = DEC_THREADS / 16;
+constexpr int DEC_UNROLL = 4;
+constexpr int DEC_MAX_PAGES = 1024;
 
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf16* __restrict__ kv_pages,
@@ -276,40 +280,68 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
   constexpr int HD = 128;
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
+  __shared__ int s_pages[DEC_MAX_PAGES];
   const int head = blockIdx.x, kvh = head / group;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  // programmatic dependent launch: let the next kernel (o_proj GEMV) start priming its weight ring now;
+  // wait for the QKV kernel's q / KV-cache writes before reading them
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int kv_len = *kv_len_minus1 + 1;
+  const int n_pages = (kv_len + page_size - 1) / page_size;
+  const bool pages_in_smem = n_pages <= DEC_MAX_PAGES;
+  if (pages_in_smem)
+    for (int i = threadIdx.x; i < n_pages; i += DEC_THREADS) s_pages[i] = page_table[i];
   float qf[8];
   unpack8(*reinterpret_cast<const uint4*>(q + head * HD + hl * 8), qf);
+  __syncthreads();
   float m = -INFINITY, l = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t row_stride = (size_t)n_kv_heads * HD;
-  for (int j0 = 0; j0 < kv_len; j0 += DEC_HW) {  // warp-uniform trip count (both half-warps shuffle together)
-    const int j = j0 + hw;
-    const bool valid = j < kv_len;
-    float kf[8], vf[8];
-    if (valid) {
-      const int page = page_table[j / page_size], slot = j % page_size;
-      const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + slot) * row_stride + kvh * HD + hl * 8;
-      const bf16* vp = kv_pages + (((size_t)page * 2 + 1) * page_size + slot) * row_stride + kvh * HD + hl * 8;
-      unpack8(*reinterpret_cast<const uint4*>(kp), kf);
-      unpack8(*reinterpret_cast<const uint4*>(vp), vf);
-    } else {
+  for (int j0 = 0; j0 < kv_len; j0 += DEC_HW * DEC_UNROLL) {  // warp-uniform trip count
+    uint4 ku[DEC_UNROLL], vu[DEC_UNROLL];
+    bool valid[DEC_UNROLL];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) kf[t] = vf[t] = 0.f;
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int j = j0 + u * DEC_HW + hw;
+      valid[u] = j < kv_len;
+      ku[u] = make_uint4(0, 0, 0, 0);
+      vu[u] = make_uint4(0, 0, 0, 0);
+      if (valid[u]) {
+        const int pg = j / page_size;
+        const int page = pages_in_smem ? s_pages[pg] : page_table[pg];
+        const int slot = j - pg * page_size;
+        const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + slot) * row_stride + kvh * HD + hl * 8;
+        ku[u] = *reinterpret_cast<const uint4*>(kp);
+        vu[u] = *reinterpret_cast<const uint4*>(kp + (size_t)page_size * row_stride);
+      }
     }
-    float d = 0.f;
+    float d[DEC_UNROLL];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) d = fmaf(qf[t], kf[t], d);
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      float kf[8];
+      unpack8(ku[u], kf);
+      d[u] = 0.f;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);  // stays inside the half-warp
-    if (valid) {
-      d *= scale_log2;
-      const float m_new = fmaxf(m, d);
-      const float a = exp2f(m - m_new), p = exp2f(d - m_new);
-      l = l * a + p;
+      for (int t = 0; t < 8; ++t) d[u] = fmaf(qf[t], kf[t], d[u]);
+    }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] = acc[t] * a + p * vf[t];
-      m = m_new;
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < DEC_UNROLL; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);  // stays inside the half-warp
+    }
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      if (valid[u]) {
+        float vf[8];
+        unpack8(vu[u], vf);
+        const float dd = d[u] * scale_log2;
+        const float m_new = fmaxf(m, dd);
+        const float a = exp2f(m - m_new), p = exp2f(dd - m_new);
+        l = l * a + p;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = acc[t] * a + p * vf[t];
+        m = m_new;
+      }
     }
   }
   if (hl == 0) { s_m[hw] = m; s_l[hw] = l; }
@@ -401,9 +433,17 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf1
     set_last_error("srgpt_attention_decode_bf16: head_dim %d unsupported (128 only)", head_dim);
     return SRGPT_ERR_UNSUPPORTED;
   }
-  attn::attn_decode_kernel<<<n_heads, attn::DEC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(kv_pages), page_table,
-      page_size, kv_len_minus1, n_kv_heads, n_heads / n_kv_heads, scale * 1.4426950408889634f);
-  SRGPT_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_heads);
+  cfg.blockDim = dim3(attn::DEC_THREADS);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn::attn_decode_kernel, reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out),
+                                      reinterpret_cast<const bf16*>(kv_pages), page_table, page_size, kv_len_minus1, n_kv_heads,
+                                      n_heads / n_kv_heads, scale * 1.4426950408889634f));
   return SRGPT_OK;
 }
