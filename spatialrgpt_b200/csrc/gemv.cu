@@ -1,22 +1,21 @@
 // Decode-time weight-streaming kernels (one new token): y = W · x with W [N, K] bf16 read exactly
 // once from HBM.  At batch 1 the whole Llama decode step is bound by these reads (15 GB / token for
-// Llama-3-8B), so this kernel is written against the HBM roofline:
+// Llama-3-8B), so this kernel is written against the HBM roofline.
 //
-//   * one persistent CTA per SM; the 8 warps of a CTA split K (each warp owns a contiguous K slice),
-//     the CTA walks over row PAIRS, so work is balanced to within one pair per CTA;
-//   * weights arrive through per-warp rings of 1-D bulk-async copies (cp.async.bulk -> UBLKCP,
-//     completion on an mbarrier): ~100 KB per SM is in flight at all times, independent of registers,
-//     and the ring is primed BEFORE anything that depends on the previous kernel;
-//   * programmatic dependent launch: every kernel of the decode step issues
-//     griddepcontrol.launch_dependents right after priming its ring and griddepcontrol.wait before it
-//     touches an activation, so launch latency, ring priming and the RMSNorm prologue of kernel n+1
-//     overlap the tail of kernel n (the per-kernel fixed cost was ~12 us of a ~20 us kernel before);
-//   * x (RMS-normalised in the prologue when requested) lives in registers of the lane that needs it;
-//   * the pair is chosen so the fused epilogue is local: (gate_i, up_i) for SwiGLU, (d, d + hd/2) of a
-//     head for RoPE + KV-cache append, two vocabulary rows for lm_head + argmax.
+// Design (measured history in profiles/: v1 persistent warps 0.70, v2 bulk-copy rings + CTA-level K split
+// 0.48, this version — see DESIGN.md "decode GEMV"):
+//   * one warp = one PAIR of weight rows, read with 8 independent 16-byte streaming loads in flight per
+//     lane (ld.global.nc.L1::no_allocate).  A warp is latency-bound by design (4 KB in flight), the chip
+//     is saturated by having >= 2000 warps resident; CTAs are NOT persistent, so the hardware scheduler
+//     balances the row pairs dynamically and no warp ever owns 2 pairs while another owns 1;
+//   * the first 8 loads of every warp are issued BEFORE anything that depends on the previous kernel;
+//     programmatic dependent launch (griddepcontrol.launch_dependents / .wait) lets the next kernel's
+//     CTAs take the SM slots the current kernel frees in its tail, so launch latency, the first HBM
+//     round trip and the RMSNorm prologue overlap the previous kernel instead of adding ~6 us each;
+//   * x (RMS-normalised in the prologue when requested) is staged once per CTA in shared memory;
+//   * the pair is chosen so the fused epilogue is warp-local: (gate_i, up_i) for SwiGLU, (d, d + hd/2)
+//     of one head for RoPE + KV-cache append, two vocabulary rows for lm_head + argmax.
 // Rounding points follow the reference's bf16 torch ops (modeling_llama.py:429-431,186-191,221,668,682).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "srgpt_b200.h"
 
@@ -25,7 +24,6 @@ namespace gemv {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int MAX_NS = 8;
 enum { MODE_LM = 3 };
 
 struct Params {
@@ -34,7 +32,6 @@ struct Params {
   int ldw;
   bf16* y;
   int N, K;
-  int ns;  // ring depth (stages per warp)
   const bf16* norm_weight;
   float eps;
   const bf16* residual;
@@ -52,40 +49,35 @@ struct Params {
   int* part_idx;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :
-               : "r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-  return r;
+// stage x (optionally RMS-normalised) into shared memory as bf16
+__device__ __forceinline__ void stage_x(const bf16* __restrict__ x, const bf16* __restrict__ norm_weight, float eps, int K,
+                                        bf16* sx, float* red) {
+  const int nchunk = K >> 3;
+  if (norm_weight == nullptr) {
+    for (int c = threadIdx.x; c < nchunk; c += THREADS)
+      reinterpret_cast<uint4*>(sx)[c] = reinterpret_cast<const uint4*>(x)[c];
+  } else {
+    float sq = 0.f;
+    for (int c = threadIdx.x; c < nchunk; c += THREADS) {
+      float f[8];
+      unpack8(reinterpret_cast<const uint4*>(x)[c], f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sq += f[t] * f[t];
+    }
+    const float rstd = rsqrtf(block_sum(sq, red) / (float)K + eps);
+    for (int c = threadIdx.x; c < nchunk; c += THREADS) {
+      float f[8], w[8], o[8];
+      unpack8(reinterpret_cast<const uint4*>(x)[c], f);
+      unpack8(reinterpret_cast<const uint4*>(norm_weight)[c], w);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[t] = w[t] * bf16_round(f[t] * rstd);
+      reinterpret_cast<uint4*>(sx)[c] = pack8(o);
+    }
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ float dot8(const uint4& w, const float* xf) {
@@ -113,193 +105,132 @@ __device__ __forceinline__ void pair_rows(const Params& p, int pi, int& r0, int&
   }
 }
 
-// XC = 16-byte chunks of x (and of every weight row) owned by one lane; a warp's K slice is XC*32 chunks.
-template <int MODE, int XC>
-__global__ void __launch_bounds__(THREADS, (XC <= 2) ? 2 : 1) decode_gemv_kernel(const Params p) {
-  extern __shared__ __align__(128) uint8_t ring[];
-  __shared__ __align__(8) uint64_t bars[WARPS][MAX_NS];
-  __shared__ float part[2][WARPS][2];
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float red[32];
-  __shared__ float s_best[WARPS];
-  __shared__ int s_besti[WARPS];
+  __shared__ float sv[WARPS];
+  __shared__ int si[WARPS];
+  bf16* sx = reinterpret_cast<bf16*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunk = p.K >> 3;
-  constexpr int SLICE = XC * 32;           // chunks per warp slice (capacity)
-  constexpr int SLICE_BYTES = SLICE * 16;
-  const int w_start = warp * SLICE;        // first chunk of this warp's K slice
-  int my_len = nchunk - w_start;
-  my_len = my_len < 0 ? 0 : (my_len > SLICE ? SLICE : my_len);
-  const uint32_t my_bytes = (uint32_t)my_len * 16u;
-  const int NS = p.ns;
-  const uint32_t ring_base = smem_u32(ring) + (uint32_t)warp * (uint32_t)NS * 2u * SLICE_BYTES;
-
-  if (lane == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(smem_u32(&bars[warp][s]), 1);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-
   const int npairs = (MODE == MODE_LM) ? ((p.N + 1) >> 1) : (p.N >> 1);
-  const int n_my = ((int)blockIdx.x < npairs) ? (npairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int pi = blockIdx.x * WARPS + warp;
+  const bool active = pi < npairs;
+  int r0 = 0, r1 = 0;
+  if (active) pair_rows<MODE>(p, pi, r0, r1);
+  const uint4* p0 = reinterpret_cast<const uint4*>(p.W + (size_t)r0 * p.ldw);
+  const uint4* p1 = reinterpret_cast<const uint4*>(p.W + (size_t)r1 * p.ldw);
+  const uint4* px = reinterpret_cast<const uint4*>(sx);
+  const int nchunk = p.K >> 3;
 
-  auto issue = [&](int i) {  // called by lane 0: stream this warp's K slice of both rows of pair i
-    if (my_bytes == 0) return;
-    const int s = i % NS;
-    int r0, r1;
-    pair_rows<MODE>(p, (int)blockIdx.x + i * (int)gridDim.x, r0, r1);
-    const uint32_t bar = smem_u32(&bars[warp][s]);
-    const uint32_t dst = ring_base + (uint32_t)s * 2u * SLICE_BYTES;
-    mbar_expect_tx(bar, 2u * my_bytes);
-    bulk_g2s(dst, p.W + (size_t)r0 * p.ldw + (size_t)w_start * 8, my_bytes, bar);
-    bulk_g2s(dst + SLICE_BYTES, p.W + (size_t)r1 * p.ldw + (size_t)w_start * 8, my_bytes, bar);
-  };
-
-  // ---- prime the ring: weights do not depend on the previous kernel
-  if (lane == 0) {
-    const int n0 = n_my < NS ? n_my : NS;
-    for (int i = 0; i < n0; ++i) issue(i);
+  // ---- first 8 loads per lane: weights do not depend on the previous kernel
+  uint4 u0[4], u1[4];
+  int c = lane;
+  const bool first_full = active && (c + 96 < nchunk);
+  if (first_full) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      u0[i] = ld_stream16(p0 + c + 32 * i);
+      u1[i] = ld_stream16(p1 + c + 32 * i);
+    }
   }
   pdl_launch_dependents();
-  pdl_wait();  // from here on activations written by earlier kernels are visible
+  pdl_wait();  // activations written by earlier kernels are visible from here on
 
-  // ---- x slice -> registers (fused LlamaRMSNorm prologue when requested)
-  float xf[XC][8];
-  {
-    float sq = 0.f;
+  stage_x(p.x, p.norm_weight, p.eps, p.K, sx, red);
+
+  float a0 = 0.f, a1 = 0.f;
+  if (active) {
+    if (first_full) {
 #pragma unroll
-    for (int j = 0; j < XC; ++j) {
-      const int c = j * 32 + lane;
-      if (c < my_len) {
-        unpack8(*reinterpret_cast<const uint4*>(p.x + (size_t)(w_start + c) * 8), xf[j]);
+      for (int i = 0; i < 4; ++i) {
+        float xf[8];
+        unpack8(px[c + 32 * i], xf);
+        a0 += dot8(u0[i], xf);
+        a1 += dot8(u1[i], xf);
+      }
+      c += 128;
+    }
+    for (; c + 96 < nchunk; c += 128) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) sq += xf[j][t] * xf[j][t];
-      } else {
+      for (int i = 0; i < 4; ++i) {
+        u0[i] = ld_stream16(p0 + c + 32 * i);
+        u1[i] = ld_stream16(p1 + c + 32 * i);
+      }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) xf[j][t] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        float xf[8];
+        unpack8(px[c + 32 * i], xf);
+        a0 += dot8(u0[i], xf);
+        a1 += dot8(u1[i], xf);
       }
     }
-    if (p.norm_weight != nullptr) {
-      const float rstd = rsqrtf(block_sum(sq, red) / (float)p.K + p.eps);
-#pragma unroll
-      for (int j = 0; j < XC; ++j) {
-        const int c = j * 32 + lane;
-        if (c < my_len) {
-          float w[8];
-          unpack8(*reinterpret_cast<const uint4*>(p.norm_weight + (size_t)(w_start + c) * 8), w);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) xf[j][t] = bf16_round(w[t] * bf16_round(xf[j][t] * rstd));
-        }
-      }
+    for (; c < nchunk; c += 32) {
+      float xf[8];
+      unpack8(px[c], xf);
+      a0 += dot8(ld_stream16(p0 + c), xf);
+      a1 += dot8(ld_stream16(p1 + c), xf);
     }
   }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
 
-  // per-kernel constants of the RoPE epilogue
-  int pos = 0, page = 0, slot = 0;
-  if (MODE == SRGPT_GEMV_QKV_ROPE) {
-    pos = *p.pos;
-    page = p.page_table[pos / p.page_size];
-    slot = pos % p.page_size;
-  }
   float best = -INFINITY;
   int besti = 0x7fffffff;
-
-  for (int i = 0; i < n_my; ++i) {
-    const int s = i % NS;
-    const int pi = (int)blockIdx.x + i * (int)gridDim.x;
-    int r0, r1;
-    pair_rows<MODE>(p, pi, r0, r1);
-    const bool epi_lane = (lane == 0) && (warp == (i & (WARPS - 1)));  // epilogues rotate over the warps
-    // operands of the epilogue are fetched before the wait so their latency is hidden
-    float e0 = 0.f, e1 = 0.f;
-    if (epi_lane) {
-      if (MODE == SRGPT_GEMV_PLAIN && p.residual != nullptr) {
-        e0 = __bfloat162float(p.residual[r0]);
-        e1 = __bfloat162float(p.residual[r1]);
-      } else if (MODE == SRGPT_GEMV_QKV_ROPE) {
-        const int half = p.hd >> 1;
-        const int j = pi % half;
-        e0 = __bfloat162float(p.cos_tab[(size_t)pos * half + j]);
-        e1 = __bfloat162float(p.sin_tab[(size_t)pos * half + j]);
+  if (active && lane == 0) {
+    if (MODE == SRGPT_GEMV_PLAIN) {
+      float y0 = bf16_round(a0), y1 = bf16_round(a1);
+      if (p.residual != nullptr) {
+        y0 += __bfloat162float(p.residual[r0]);
+        y1 += __bfloat162float(p.residual[r1]);
       }
-    }
-    float a0 = 0.f, a1 = 0.f;
-    if (my_len > 0) {
-      mbar_wait(smem_u32(&bars[warp][s]), (uint32_t)((i / NS) & 1));
-      const uint32_t st = ring_base + (uint32_t)s * 2u * SLICE_BYTES;
-#pragma unroll
-      for (int j = 0; j < XC; ++j) {
-        const int c = j * 32 + lane;
-        if (c < my_len) {
-          const uint4 w0 = lds128(st + (uint32_t)c * 16u);
-          const uint4 w1 = lds128(st + SLICE_BYTES + (uint32_t)c * 16u);
-          a0 += dot8(w0, xf[j]);
-          a1 += dot8(w1, xf[j]);
-        }
+      *reinterpret_cast<uint32_t*>(p.y + r0) = pack_bf16x2(y0, y1);
+    } else if (MODE == SRGPT_GEMV_SWIGLU) {
+      const float g = bf16_round(a0), u = bf16_round(a1);
+      p.y[pi] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
+    } else if (MODE == SRGPT_GEMV_QKV_ROPE) {
+      const int half = p.hd >> 1;
+      const int head = pi / half, j = pi - head * half;
+      float v0 = bf16_round(a0), v1 = bf16_round(a1);
+      const int pos = *p.pos;
+      if (head < p.n_heads + p.n_kv_heads) {
+        const float cs = __bfloat162float(p.cos_tab[(size_t)pos * half + j]);
+        const float sn = __bfloat162float(p.sin_tab[(size_t)pos * half + j]);
+        const float o0 = bf16_round(bf16_round(v0 * cs) + bf16_round(-v1 * sn));
+        const float o1 = bf16_round(bf16_round(v1 * cs) + bf16_round(v0 * sn));
+        v0 = o0;
+        v1 = o1;
       }
-    }
-    __syncwarp();  // every lane is done with stage s -> refill it
-    if (lane == 0 && i + NS < n_my) issue(i + NS);
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (lane == 0) {
-      part[i & 1][warp][0] = a0;
-      part[i & 1][warp][1] = a1;
-    }
-    __syncthreads();
-    if (epi_lane) {
-      float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) {
-        t0 += part[i & 1][w][0];
-        t1 += part[i & 1][w][1];
+      if (head < p.n_heads) {
+        p.y[r0] = __float2bfloat16_rn(v0);
+        p.y[r1] = __float2bfloat16_rn(v1);
+      } else {
+        const int page = p.page_table[pos / p.page_size], slot = pos % p.page_size;
+        const bool is_v = head >= p.n_heads + p.n_kv_heads;
+        const int kh = head - p.n_heads - (is_v ? p.n_kv_heads : 0);
+        bf16* dst = p.kv_pages + (((size_t)page * 2 + (is_v ? 1 : 0)) * p.page_size + slot) * p.n_kv_heads * p.hd + kh * p.hd;
+        dst[j] = __float2bfloat16_rn(v0);
+        dst[j + half] = __float2bfloat16_rn(v1);
       }
-      if (MODE == SRGPT_GEMV_PLAIN) {
-        float y0 = bf16_round(t0), y1 = bf16_round(t1);
-        if (p.residual != nullptr) { y0 += e0; y1 += e1; }
-        *reinterpret_cast<uint32_t*>(p.y + r0) = pack_bf16x2(y0, y1);
-      } else if (MODE == SRGPT_GEMV_SWIGLU) {
-        const float g = bf16_round(t0), u = bf16_round(t1);
-        p.y[pi] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
-      } else if (MODE == SRGPT_GEMV_QKV_ROPE) {
-        const int half = p.hd >> 1;
-        const int head = pi / half, j = pi - head * half;
-        float v0 = bf16_round(t0), v1 = bf16_round(t1);
-        if (head < p.n_heads + p.n_kv_heads) {
-          const float o0 = bf16_round(bf16_round(v0 * e0) + bf16_round(-v1 * e1));
-          const float o1 = bf16_round(bf16_round(v1 * e0) + bf16_round(v0 * e1));
-          v0 = o0;
-          v1 = o1;
-        }
-        if (head < p.n_heads) {
-          p.y[r0] = __float2bfloat16_rn(v0);
-          p.y[r1] = __float2bfloat16_rn(v1);
-        } else {
-          const bool is_v = head >= p.n_heads + p.n_kv_heads;
-          const int kh = head - p.n_heads - (is_v ? p.n_kv_heads : 0);
-          bf16* dst = p.kv_pages + (((size_t)page * 2 + (is_v ? 1 : 0)) * p.page_size + slot) * p.n_kv_heads * p.hd + kh * p.hd;
-          dst[j] = __float2bfloat16_rn(v0);
-          dst[j + half] = __float2bfloat16_rn(v1);
-        }
-      } else {  // MODE_LM: logits = lm_head(h).float() -> bf16 rounding first (modeling_llama.py:1044-1045)
-        t0 = bf16_round(t0);
-        t1 = bf16_round(t1);
-        if (p.logits_out != nullptr) {
-          p.logits_out[r0] = t0;
-          if (r1 != r0) p.logits_out[r1] = t1;
-        }
-        if (better(t0, r0, best, besti)) { best = t0; besti = r0; }
-        if (r1 != r0 && better(t1, r1, best, besti)) { best = t1; besti = r1; }
+    } else {  // MODE_LM: logits = lm_head(h).float() -> bf16 rounding first (modeling_llama.py:1044-1045)
+      a0 = bf16_round(a0);
+      a1 = bf16_round(a1);
+      if (p.logits_out != nullptr) {
+        p.logits_out[r0] = a0;
+        if (r1 != r0) p.logits_out[r1] = a1;
       }
+      best = a0;
+      besti = r0;
+      if (r1 != r0 && better(a1, r1, best, besti)) { best = a1; besti = r1; }
     }
   }
-
   if (MODE == MODE_LM) {
-    if (lane == 0) { s_best[warp] = best; s_besti[warp] = besti; }
+    if (lane == 0) { sv[warp] = best; si[warp] = besti; }
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int w = 1; w < WARPS; ++w)
-        if (better(s_best[w], s_besti[w], best, besti)) { best = s_best[w]; besti = s_besti[w]; }
+        if (better(sv[w], si[w], best, besti)) { best = sv[w]; besti = si[w]; }
       p.part_val[blockIdx.x] = best;
       p.part_idx[blockIdx.x] = besti;
     }
@@ -347,76 +278,33 @@ lm_head_finalize_kernel(const float* __restrict__ part_val, const int* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static int xc_for(int K) {
-  const int per_lane = ceil_div(K >> 3, THREADS);  // chunks per lane
-  if (per_lane <= 1) return 1;
-  if (per_lane <= 2) return 2;
-  if (per_lane <= 4) return 4;
-  if (per_lane <= 7) return 7;
-  if (per_lane <= 8) return 8;
-  return 0;
-}
-// ring depth and CTAs per SM: ~96-128 KB of weights in flight per SM, and two consecutive kernels of the
-// decode step must fit on an SM together (programmatic dependent launch) -> <= ~112 KB per kernel per SM
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v != nullptr && v[0] != 0) ? atoi(v) : dflt;
-}
-static int ctas_per_sm(int xc) { return xc <= 2 ? 2 : 1; }
-static int ns_for(int xc) {
-  static const int ns_override = env_int("SRGPT_GEMV_NS", 0);  // tuning knob for experiments
-  if (ns_override > 0) return ns_override > MAX_NS ? MAX_NS : ns_override;
-  switch (xc) {
-    case 1: return 6;   // 8 warps * 6 * 1 KB  = 48 KB x 2 CTAs
-    case 2: return 3;   // 8 warps * 3 * 2 KB  = 48 KB x 2 CTAs
-    case 4: return 3;   // 8 warps * 3 * 4 KB  = 96 KB
-    default: return 2;  // 8 warps * 2 * 7-8 KB = 112-128 KB
-  }
-}
-static int grid_for(int npairs, int xc) {
-  const int cap = sm_count() * ctas_per_sm(xc);
-  return npairs < cap ? npairs : cap;
-}
+static int grid_for(int npairs) { return ceil_div(npairs, WARPS); }
 
-template <typename KernelT>
-static int launch_pdl(KernelT kernel, int grid, int block, int smem, cudaStream_t st, const Params& p) {
-  cudaLaunchConfig_t cfg = {};
+static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, int smem, cudaStream_t st) {
+  cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
-  return SRGPT_OK;
-}
-
-template <int MODE, int XC>
-static int launch_xc(Params& p, int npairs, cudaStream_t st) {
-  p.ns = ns_for(XC);
-  const int smem = WARPS * p.ns * 2 * XC * 32 * 16;
-  static bool configured = false;
-  if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE, XC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  return launch_pdl(decode_gemv_kernel<MODE, XC>, grid_for(npairs, XC), THREADS, smem, st, p);
 }
 
 template <int MODE>
-static int launch(Params& p, int npairs, cudaStream_t st) {
-  switch (xc_for(p.K)) {
-    case 1: return launch_xc<MODE, 1>(p, npairs, st);
-    case 2: return launch_xc<MODE, 2>(p, npairs, st);
-    case 4: return launch_xc<MODE, 4>(p, npairs, st);
-    case 7: return launch_xc<MODE, 7>(p, npairs, st);
-    case 8: return launch_xc<MODE, 8>(p, npairs, st);
+static int launch(const Params& p, int npairs, cudaStream_t st) {
+  const int smem = p.K * 2;
+  static int configured_smem = 0;
+  if (smem > 48 * 1024 && smem > configured_smem) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
   }
-  set_last_error("decode gemv: K = %d unsupported (max 16384)", p.K);
-  return SRGPT_ERR_UNSUPPORTED;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  pdl_config(cfg, attr, grid_for(npairs), THREADS, smem, st);
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE>, p));
+  return SRGPT_OK;
 }
 
 }  // namespace gemv
@@ -432,6 +320,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemv_bf16(const void
                                void* stream) {
   SRGPT_CHECK_ARG(x && W && y && N > 0 && K > 0);
   SRGPT_CHECK_ARG((N % 2) == 0 && (K % 8) == 0 && (ldw % 8) == 0 && ldw >= K);
+  SRGPT_CHECK_ARG(K * 2 <= 200 * 1024);
   SRGPT_CHECK_ARG(aligned16(x) && aligned16(W) && (reinterpret_cast<uintptr_t>(y) & 3) == 0);
   SRGPT_CHECK_ARG(norm_weight == nullptr || aligned16(norm_weight));
   SRGPT_CHECK_ARG(mode >= SRGPT_GEMV_PLAIN && mode <= SRGPT_GEMV_QKV_ROPE);
@@ -472,7 +361,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemv_bf16(const void
 
 extern "C" __attribute__((visibility("default"))) long long srgpt_lm_head_workspace(int V) {
   if (V <= 0) return -1;
-  const int g = 2 * sm_count();  // upper bound of the lm_head grid
+  const int g = gemv::grid_for((V + 1) / 2);
   return (long long)g * (long long)(sizeof(float) + sizeof(int));
 }
 
@@ -480,17 +369,12 @@ extern "C" __attribute__((visibility("default"))) int srgpt_lm_head_argmax_bf16(
                                          float* logits_out, void* workspace, const void* embed_table, void* next_x,
                                          long long* out_ids, int* step, int* pos, void* stream) {
   SRGPT_CHECK_ARG(x && W && workspace && out_ids && step && pos && V > 0 && K > 0);
-  SRGPT_CHECK_ARG((K % 8) == 0 && (ldw % 8) == 0 && ldw >= K);
+  SRGPT_CHECK_ARG((K % 8) == 0 && (ldw % 8) == 0 && ldw >= K && K * 2 <= 200 * 1024);
   SRGPT_CHECK_ARG(aligned16(x) && aligned16(W) && (norm_weight == nullptr || aligned16(norm_weight)));
   SRGPT_CHECK_ARG((embed_table == nullptr) == (next_x == nullptr));
   SRGPT_CHECK_ARG(embed_table == nullptr || (aligned16(embed_table) && aligned16(next_x)));
   const int npairs = (V + 1) / 2;
-  const int xc = gemv::xc_for(K);
-  if (xc == 0) {
-    set_last_error("lm_head: K = %d unsupported (max 16384)", K);
-    return SRGPT_ERR_UNSUPPORTED;
-  }
-  const int g = gemv::grid_for(npairs, xc);
+  const int g = gemv::grid_for(npairs);
   gemv::Params p = {};
   p.x = reinterpret_cast<const bf16*>(x);
   p.W = reinterpret_cast<const bf16*>(W);
@@ -505,15 +389,9 @@ extern "C" __attribute__((visibility("default"))) int srgpt_lm_head_argmax_bf16(
   int rc = gemv::launch<gemv::MODE_LM>(p, npairs, st);
   if (rc != SRGPT_OK) return rc;
   // finalize: also a programmatic dependent (its launch latency hides behind the lm_head kernel)
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(1);
-  cfg.blockDim = dim3(256);
-  cfg.stream = st;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  gemv::pdl_config(cfg, attr, 1, 256, 0, st);
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv::lm_head_finalize_kernel, (const float*)p.part_val, (const int*)p.part_idx, g,
                                       reinterpret_cast<const bf16*>(embed_table), reinterpret_cast<bf16*>(next_x), K, out_ids, step, pos));
   return SRGPT_OK;
