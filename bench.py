@@ -126,6 +126,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from spatialrgpt_b200 import baseline_config, ops
+    from spatialrgpt_b200.distributed import aggregate_throughput
     from spatialrgpt_b200.llava_llama import LlavaLlamaModel
     from spatialrgpt_b200.weights import random_init
 
@@ -172,15 +173,7 @@ def run_ours(args):
             n_tok += int(fn().numel())
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:  # max over ranks (device time), total tokens via allgather
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-            cnt = torch.tensor([n_tok], device=dev, dtype=torch.int64)
-            allc = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(allc, cnt)
-            n_tok = int(sum(int(c) for c in allc))
+        ms, n_tok, _ = aggregate_throughput(e0.elapsed_time(e1), n_tok, dev)  # max over ranks; tokens all-gathered
         return ms, n_tok
 
     for _ in range(max(args.warmup, 3)):

@@ -77,8 +77,9 @@ int srgpt_splice_rows_bf16(const void* src0, const void* src1, const void* src2,
  * bf16(sum + 1e-8).  w: [n_img, M, side*side] bf16 in the feature tensor's row order:
  * order = 0 row-major (y*side+x); order = 2 the 2-level 2x2-nested order the deconv GEMMs produce
  * (see DESIGN.md "hres layout").  rscale = (float)(1.0 / scale_factor) exactly as ATen computes it. */
-int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, int n_img, int M, int IH, int IW, int side,
-                       float rscale, int order, void* stream);
+long long srgpt_mask_weights_workspace(int n_img, int M); /* bytes of fp32 partial sums */
+int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW,
+                       int side, float rscale, int order, void* stream);
 /* Mask pooling proper (base_extractor.py:74-78): out[i,m,:] = sum_l w[i,m,l] * x[i,l,:].
  * x: [n_img, L, C] bf16 streamed once; partial: fp32 workspace of srgpt_mask_pool_workspace() bytes. */
 long long srgpt_mask_pool_workspace(int n_img, int M, int L, int C);

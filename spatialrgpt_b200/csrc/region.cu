@@ -41,31 +41,48 @@ __device__ __forceinline__ float bilinear_tap(const T* __restrict__ img, int IH,
 }
 
 // ---------------------------------------------------------------------------------------------
-// mask weights: one CTA per (mask, image).  pass 1: resample -> bf16, sum; pass 2: divide.
+// mask weights, two fully parallel passes (a single CTA per mask was latency-bound: 37 us for 8 masks):
+//   pass 1  grid (splits, M, n_img): resample -> bf16, per-split partial sums (fixed order -> deterministic)
+//   pass 2  same grid: denorm = bf16(bf16(sum) + 1e-8) (base_extractor.py:61), w = bf16(v / denorm)
 // ---------------------------------------------------------------------------------------------
+constexpr int MW_SPLITS = 16;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-mask_weights_kernel(const T* __restrict__ masks, bf16* __restrict__ w, int M, int IH, int IW, int side, float rscale, int order) {
+mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __restrict__ psum, int M, int IH, int IW, int side,
+                 float rscale, int order) {
   __shared__ float red[32];
-  const int m = blockIdx.x, img = blockIdx.y;
+  const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
   const T* src = masks + ((size_t)img * M + m) * IH * IW;
   const int L = side * side;
   bf16* dst = w + ((size_t)img * M + m) * L;
+  const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
+  const int l_end = min(L, (split + 1) * per);
   float sum = 0.f;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) {
-    const int oy = l / side, ox = l % side;
+  for (int l = split * per + threadIdx.x; l < l_end; l += blockDim.x) {
+    const int oy = l / side, ox = l - oy * side;
     const bf16 v = __float2bfloat16_rn(bilinear_tap(src, IH, IW, rscale, rscale, oy, ox));
     dst[feat_row(oy, ox, side, order)] = v;
     sum += __bfloat162float(v);
   }
   const float total = block_sum(sum, red);
-  // denorm = mask.sum() + 1e-8 with both results rounded to bf16 (base_extractor.py:61)
+  if (threadIdx.x == 0) psum[((size_t)img * M + m) * MW_SPLITS + split] = total;
+}
+
+__global__ void __launch_bounds__(256)
+mask_normalise_kernel(bf16* __restrict__ w, const float* __restrict__ psum, int M, int L) {
+  const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
+  const float* ps = psum + ((size_t)img * M + m) * MW_SPLITS;
+  float total = 0.f;
+#pragma unroll
+  for (int i = 0; i < MW_SPLITS; ++i) total += ps[i];
   const float denorm = bf16_round(bf16_round(total) + 1e-8f);
-  for (int l = threadIdx.x; l < L; l += blockDim.x) {
-    const int oy = l / side, ox = l % side;
-    const int r = feat_row(oy, ox, side, order);
-    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(dst[r]), denorm));  // same thread wrote dst[r]
-  }
+  bf16* dst = w + ((size_t)img * M + m) * L;
+  const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
+  const int l_end = min(L, (split + 1) * per);
+  // rows are a permutation of l; normalising the contiguous range [split*per, l_end) of ROWS covers every row once
+  for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x)
+    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(dst[r]), denorm));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -79,7 +96,7 @@ constexpr int MP_RL = 16;    // row lanes
 constexpr int MP_MT = 8;     // masks per pass
 constexpr int MP_MAX_ROWS = 512;  // rows per CTA (weights staged in smem: 8 * 512 * 4 = 16 KB)
 
-__global__ void __launch_bounds__(MP_THREADS)
+__global__ void __launch_bounds__(MP_THREADS, 2)
 mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
                  int rows_per_cta, int R) {
   // one buffer, two views (never live at the same time; 36 KB keeps us under the 48 KB static limit):
@@ -115,13 +132,13 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
 
     if (c_ok) {
       int r = rl;
-      // 4 independent 16-byte loads in flight per thread
-      for (; r + 3 * MP_RL < nrows; r += 4 * MP_RL) {
-        uint4 u[4];
+      // 8 independent 16-byte loads in flight per thread (64 KB per SM with 2 resident CTAs)
+      for (; r + 7 * MP_RL < nrows; r += 8 * MP_RL) {
+        uint4 u[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
+        for (int k = 0; k < 8; ++k) u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
           float f[8];
           unpack8(u[k], f);
 #pragma unroll
@@ -172,13 +189,24 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
   }
 }
 
-__global__ void mask_pool_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int M, int C, int R) {
-  const int m = blockIdx.x, img = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s += partial[(((size_t)img * R + r) * M + m) * C + c];
-    out[((size_t)img * M + m) * C + c] = __float2bfloat16_rn(s);
+__global__ void __launch_bounds__(256)
+mask_pool_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int M, int C, int R) {
+  const int m = blockIdx.y, img = blockIdx.z;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float* p = partial + ((size_t)img * R * M + m) * C + c;
+  const size_t stride = (size_t)M * C;
+  float s = 0.f;
+  int r = 0;
+  for (; r + 8 <= R; r += 8) {  // 8 independent loads in flight, summed in index order (deterministic)
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(r + k) * stride];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
   }
+  for (; r < R; ++r) s += p[(size_t)r * stride];
+  out[((size_t)img * M + m) * C + c] = __float2bfloat16_rn(s);
 }
 
 static void mask_pool_plan(int n_img, int L, int C, int* R, int* rows_per_cta, int* Q) {
@@ -283,16 +311,24 @@ using namespace srgpt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, int n_img, int M, int IH, int IW, int side,
+extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_workspace(int n_img, int M) {
+  if (n_img <= 0 || M <= 0) return -1;
+  return (long long)n_img * M * MW_SPLITS * (long long)sizeof(float);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW, int side,
                                   float rscale, int order, void* stream) {
-  SRGPT_CHECK_ARG(masks && w && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
+  SRGPT_CHECK_ARG(masks && w && workspace && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
   SRGPT_CHECK_ARG(order == 0 || (order == 2 && (side % 4) == 0));
-  dim3 grid(M, n_img);
+  dim3 grid(MW_SPLITS, M, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* psum = reinterpret_cast<float*>(workspace);
   if (mask_is_bf16)
-    mask_weights_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), reinterpret_cast<bf16*>(w), M, IH, IW, side, rscale, order);
+    mask_taps_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), reinterpret_cast<bf16*>(w), psum, M, IH, IW, side, rscale, order);
   else
-    mask_weights_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), reinterpret_cast<bf16*>(w), M, IH, IW, side, rscale, order);
+    mask_taps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), reinterpret_cast<bf16*>(w), psum, M, IH, IW, side, rscale, order);
+  SRGPT_CHECK_LAUNCH();
+  mask_normalise_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<bf16*>(w), psum, M, side * side);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }
@@ -315,7 +351,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const
   mask_pool_kernel<<<grid, MP_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
                                                 reinterpret_cast<float*>(workspace), M, L, C, rpc, R);
   SRGPT_CHECK_LAUNCH();
-  mask_pool_reduce_kernel<<<dim3(M, n_img), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), reinterpret_cast<bf16*>(out), M, C, R);
+  mask_pool_reduce_kernel<<<dim3(ceil_div(C, 256), M, n_img), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), reinterpret_cast<bf16*>(out), M, C, R);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

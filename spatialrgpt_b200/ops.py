@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import SrgptError
 from ._lib import check as _check_rc
 
-_KERNELS_PER_CALL = {"srgpt_mask_pool_bf16": 2, "srgpt_lm_head_argmax_bf16": 2, "srgpt_depth_to_u8x3": 3}
+_KERNELS_PER_CALL = {"srgpt_mask_pool_bf16": 2, "srgpt_mask_weights": 2, "srgpt_lm_head_argmax_bf16": 2, "srgpt_depth_to_u8x3": 3}
 
 
 def check(rc: int, what: str) -> None:
@@ -167,8 +167,9 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
         raise SrgptError(f"mask_weights: floor({IH}x{IW} * {scale_factor}) != {side} (non-square masks are unsupported)")
     rscale = float(torch.tensor(1.0 / scale_factor, dtype=torch.float64).to(torch.float32))
     w = torch.empty((n, M, side * side), dtype=BF16, device=masks.device)
-    check(_lib.load().srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), n, M, IH, IW, side, rscale, order,
-                                         _stream()), "srgpt_mask_weights")
+    ws = torch.empty(_lib.load().srgpt_mask_weights_workspace(n, M) // 4, dtype=torch.float32, device=masks.device)
+    check(_lib.load().srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), _p(ws), n, M, IH, IW, side, rscale,
+                                         order, _stream()), "srgpt_mask_weights")
     return w
 
 

@@ -1,0 +1,139 @@
+"""Host-side API surface vs fixtures produced by the reference's llava.conversation / llava.mm_utils."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from spatialrgpt_b200 import conversation as C
+from spatialrgpt_b200 import mm_utils as M
+from spatialrgpt_b200.constants import IMAGE_TOKEN_INDEX
+from tests.golden.make_host_golden import CONVERSATIONS, PROMPTS, ToyTokenizer
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "host_api.json")))
+
+
+def test_every_reference_template_renders_identically(gold):
+    assert set(gold["prompts"]) <= set(C.conv_templates)
+    for name, rows in gold["prompts"].items():
+        for conv_msgs, expect in zip(CONVERSATIONS, rows):
+            c = C.conv_templates[name].copy()
+            try:
+                for who, msg in conv_msgs:
+                    c.append_message(c.roles[0] if who == "U" else c.roles[1], tuple(msg) if isinstance(msg, list) else msg)
+                got = c.get_prompt()
+            except Exception as e:
+                got = f"raises {type(e).__name__}"
+            assert got == expect, f"template {name}: {got!r} != {expect!r}"
+
+
+def test_llama3_and_v1_stop_strings():
+    # eval_spatial.py:215-219: stop_str = sep unless SeparatorStyle.TWO -> sep2
+    l3, v1 = C.conv_templates["llama_3"], C.conv_templates["v1"]
+    assert l3.sep == "<|eot_id|>" and l3.sep_style == C.SeparatorStyle.LLAMA_3
+    assert v1.sep2 == "</s>" and v1.sep_style == C.SeparatorStyle.TWO
+    c = l3.copy()
+    c.append_message(c.roles[0], "hi")
+    c.append_message(c.roles[1], None)
+    assert c.get_prompt().endswith("<|start_header_id|>assistant<|end_header_id|>\n\n")
+    assert C.conv_templates["llama_3"].messages == []  # copy() does not alias the template's history
+
+
+def test_tokenizer_image_token(gold):
+    for row in gold["tokenize"]:
+        ids = M.tokenizer_image_token(row["prompt"], ToyTokenizer(), lstrip=row["lstrip"])
+        assert ids == row["ids"], row
+    t = M.tokenizer_image_token(PROMPTS[0], ToyTokenizer(), return_tensors="pt")
+    assert t.dtype == torch.long and int((t == IMAGE_TOKEN_INDEX).sum()) == 1
+    with pytest.raises(ValueError):
+        M.tokenizer_image_token("x", ToyTokenizer(), return_tensors="np")
+
+
+def test_keywords_stopping_criteria(gold):
+    tok = ToyTokenizer()
+    base = tok("the red chair is left of the table </s> extra").input_ids
+    assert base == gold["stopping_ids"]
+    crit = M.KeywordsStoppingCriteria(["</s>"], tok, torch.zeros(1, 0, dtype=torch.long))
+    got = [bool(crit(torch.tensor([base[:n]]), None)) for n in range(1, len(base) + 1)]
+    assert got == gold["stopping"]
+
+
+def test_model_name_from_path(gold):
+    for p, name in gold["model_names"].items():
+        assert M.get_model_name_from_path(p) == name
+
+
+def test_process_images_and_regions_shapes():
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+    from types import SimpleNamespace
+
+    proc = SiglipImageProcessor(size={"height": 56, "width": 56})
+    cfg = SimpleNamespace(image_aspect_ratio="resize", image_processor=proc)
+    rng = np.random.RandomState(0)
+    imgs = [Image.fromarray(rng.randint(0, 255, (40, 70, 3), dtype=np.uint8)) for _ in range(2)]
+    px = M.process_images(imgs, proc, cfg)
+    assert px.shape == (2, 3, 56, 56) and px.dtype == torch.float32
+    assert float(px.min()) >= -1.0 and float(px.max()) <= 1.0  # rescale 1/255, mean = std = 0.5
+    masks = M.boxes_to_masks([[5, 5, 30, 20], [-3, 0, 100, 100]], 40, 70)
+    assert masks[1].sum() == 40 * 70 and masks[0].sum() == 25 * 15
+    reg = M.process_regions(masks, proc, cfg)
+    assert reg.shape == (2, 56, 56) and reg.dtype == torch.float32
+    assert 0.9 < float(reg[1].mean()) <= 1.01  # resampled floats, not rescaled by 1/255 (mm_utils.py:479-482)
+
+
+def test_read_checkpoint_roundtrip(tmp_path):
+    """A synthetic checkpoint written in the reference's four-directory layout parses back (CPU only)."""
+    from safetensors.torch import save_file
+
+    from oracle import srgpt_oracle as O
+    from spatialrgpt_b200 import builder
+    from tests.golden.make_golden import CASES
+
+    oc = O.OracleConfig(**CASES["tiny_boxes"][0])
+    sd = O.make_weights(oc, seed=1)
+    root = str(tmp_path / "ckpt")
+    top = {"architectures": ["LlavaLlamaModel"], "model_type": "llava_llama", "enable_region": True, "enable_depth": True,
+           "mm_vision_select_layer": -2, "mm_vision_select_feature": "cls_patch", "mm_use_im_patch_token": False,
+           "image_aspect_ratio": "resize", "llm_cfg": {}, "vision_tower_cfg": {}, "mm_projector_cfg": {}, "region_extractor_cfg": {}}
+    subs = {
+        "llm": {"hidden_size": oc.hidden, "num_hidden_layers": oc.layers, "num_attention_heads": oc.heads,
+                "num_key_value_heads": oc.kv_heads, "head_dim": oc.head_dim, "intermediate_size": oc.inter, "vocab_size": oc.vocab,
+                "rope_theta": oc.rope_theta, "rms_norm_eps": oc.rms_eps, "max_position_embeddings": 4096},
+        "vision_tower": {"image_size": oc.image_size, "patch_size": 14, "hidden_size": oc.v_hidden, "num_hidden_layers": oc.v_layers,
+                         "num_attention_heads": oc.v_heads, "intermediate_size": oc.v_inter, "layer_norm_eps": 1e-6},
+        "mm_projector": {"mm_projector_type": "mlp_downsample"},
+        "region_extractor": {"region_extractor_type": "regiongpt"},
+    }
+    os.makedirs(root)
+    json.dump(top, open(os.path.join(root, "config.json"), "w"))
+    for name, cfg in subs.items():
+        d = os.path.join(root, name)
+        os.makedirs(d)
+        json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
+        tensors = {k: v.contiguous() for k, v in sd[name].items()}
+        if name == "llm":  # sharded, like a real 8B checkpoint
+            keys = sorted(tensors)
+            save_file({k: tensors[k] for k in keys[::2]}, os.path.join(d, "model-00001-of-00002.safetensors"))
+            save_file({k: tensors[k] for k in keys[1::2]}, os.path.join(d, "model-00002-of-00002.safetensors"))
+        else:
+            save_file(tensors, os.path.join(d, "model.safetensors"))
+    assert builder.is_mm_model(root)
+    cfg, got, tok, proc = builder.read_checkpoint(root, load_tokenizer=False)
+    assert cfg.enable_region and cfg.enable_depth and not cfg.mm_use_im_patch_token
+    assert cfg.llama.hidden_size == oc.hidden and cfg.llama.num_key_value_heads == oc.kv_heads and cfg.llama.rope_theta == oc.rope_theta
+    assert cfg.vision.image_size == oc.image_size and cfg.vision.intermediate_size == oc.v_inter
+    for part in ("llm", "vision_tower", "mm_projector", "region_extractor"):
+        assert set(got[part]) == set(sd[part])
+        for k in sd[part]:
+            assert torch.equal(got[part][k], sd[part][k])
+    # resize_token_embeddings semantics (builder.py:199)
+    builder._resize_token_embeddings(cfg, got["llm"], oc.vocab + 3)
+    assert got["llm"]["model.embed_tokens.weight"].shape[0] == oc.vocab + 3 and cfg.llama.vocab_size == oc.vocab + 3
+    assert torch.equal(got["llm"]["lm_head.weight"][: oc.vocab], sd["llm"]["lm_head.weight"])
+    with pytest.raises(NotImplementedError):
+        builder.load_pretrained_model(root, "x", load_4bit=True)
