@@ -28,6 +28,14 @@ const char* srgpt_last_error(void);
 /* sm count + compute capability of the current device; fails (<0) unless it is sm_100. */
 int srgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Optional in-kernel timeline for the decode-step kernels (debug / profiling aid; nsys is not available on
+ * the target boxes).  Between trace_begin and trace_end every traced launch (gemv / lm_head / decode attention)
+ * takes the next 4-u64 record of device_buf: {min CTA-start ns, min after-dependency-wait ns, max CTA-end ns,
+ * CTA count} from %globaltimer.  The caller pre-fills records with {~0, ~0, 0, 0}.  trace_end returns the
+ * number of records used.  Not thread-safe; launches captured into a CUDA graph keep their record. */
+int srgpt_trace_begin(void* device_buf, int capacity_records);
+int srgpt_trace_end(void);
+
 /* ---- dense GEMM on tcgen05/TMEM (gemm_tcgen05.cu) --------------------------------------------
  * C[M,N] = epilogue(A[M,K] · W[N,K]^T), bf16 in, fp32 accumulate.  W is the nn.Linear weight as
  * stored ([out, in]).  Replaces every F.linear / Conv2d(k=s) / ConvTranspose2d(k=s) on the path:

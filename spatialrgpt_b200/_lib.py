@@ -27,6 +27,8 @@ SIGNATURES = {
     "srgpt_abi_version": (ci, []),
     "srgpt_last_error": (C.c_char_p, []),
     "srgpt_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
+    "srgpt_trace_begin": (ci, [vp, ci]),
+    "srgpt_trace_end": (ci, []),
     "srgpt_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "srgpt_layernorm_bf16": (ci, [vp, ci, vp, vp, vp, ci, ci, ci, cf, ci, vp]),
     "srgpt_downsample_layernorm_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, vp]),

@@ -276,7 +276,7 @@ constexpr int DEC_MAX_PAGES = 1024;
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf16* __restrict__ kv_pages,
                    const int* __restrict__ page_table, int page_size, const int* __restrict__ kv_len_minus1, int n_kv_heads,
-                   int group, float scale_log2) {
+                   int group, float scale_log2, unsigned long long* trace) {
   constexpr int HD = 128;
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
@@ -285,8 +285,10 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   // programmatic dependent launch: let the next kernel (o_proj GEMV) start priming its weight ring now;
   // wait for the QKV kernel's q / KV-cache writes before reading them
+  trace_mark(trace, 0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_mark(trace, 1);
   const int kv_len = *kv_len_minus1 + 1;
   const int n_pages = (kv_len + page_size - 1) / page_size;
   const bool pages_in_smem = n_pages <= DEC_MAX_PAGES;
@@ -361,6 +363,7 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
     }
     out[head * HD + threadIdx.x] = __float2bfloat16_rn(at / lt);
   }
+  trace_mark(trace, 2);
 }
 
 template <int HD, int HDP, bool CAUSAL>
@@ -444,6 +447,6 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf1
   cfg.numAttrs = 1;
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn::attn_decode_kernel, reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out),
                                       reinterpret_cast<const bf16*>(kv_pages), page_table, page_size, kv_len_minus1, n_kv_heads,
-                                      n_heads / n_kv_heads, scale * 1.4426950408889634f));
+                                      n_heads / n_kv_heads, scale * 1.4426950408889634f, trace_next_slot()));
   return SRGPT_OK;
 }

@@ -29,9 +29,32 @@ int sm_count() {
   return cached;
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0, g_trace_n = 0;
+
+unsigned long long* trace_next_slot() {
+  if (g_trace_buf == nullptr || g_trace_n >= g_trace_cap) return nullptr;
+  return g_trace_buf + 4 * (size_t)(g_trace_n++);
+}
+
 }  // namespace srgpt
 
 using namespace srgpt;
+
+extern "C" __attribute__((visibility("default"))) int srgpt_trace_begin(void* device_buf, int capacity_records) {
+  SRGPT_CHECK_ARG(device_buf != nullptr && capacity_records > 0);
+  g_trace_buf = reinterpret_cast<unsigned long long*>(device_buf);
+  g_trace_cap = capacity_records;
+  g_trace_n = 0;
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_trace_end(void) {
+  const int n = g_trace_n;
+  g_trace_buf = nullptr;
+  g_trace_cap = g_trace_n = 0;
+  return n;
+}
 
 extern "C" __attribute__((visibility("default"))) int srgpt_abi_version(void) { return SRGPT_ABI_VERSION; }
 

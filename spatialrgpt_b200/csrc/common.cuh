@@ -40,6 +40,11 @@ void set_last_error(const char* fmt, ...);
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int sm_count();  // cached multiProcessorCount of the current device
 
+// ---- optional in-kernel timeline (srgpt_trace_begin / srgpt_trace_end): each traced launch owns 4 u64 slots
+//      [0] min globaltimer at CTA start, [1] min globaltimer after griddepcontrol.wait, [2] max globaltimer at CTA
+//      end, [3] CTA count.  Costs 3 atomics per CTA; disabled (nullptr) unless a trace buffer is installed.
+unsigned long long* trace_next_slot();  // host: returns the 4-slot record for the next launch, or nullptr
+
 // ---- device helpers
 typedef __nv_bfloat16 bf16;
 
@@ -76,6 +81,23 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* rec, int which) {
+  if (rec != nullptr && threadIdx.x == 0) {
+    const unsigned long long t = globaltimer_ns();
+    if (which == 2) {
+      atomicMax(rec + 2, t);
+      atomicAdd(rec + 3, 1ull);
+    } else {
+      atomicMin(rec + which, t);
+    }
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -47,6 +47,7 @@ struct Params {
   float* logits_out;
   float* part_val;
   int* part_idx;
+  unsigned long long* trace;  // optional timeline record (srgpt_trace_begin)
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   bf16* sx = reinterpret_cast<bf16*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  trace_mark(p.trace, 0);
   const int npairs = (MODE == MODE_LM) ? ((p.N + 1) >> 1) : (p.N >> 1);
   const int pi = blockIdx.x * WARPS + warp;
   const bool active = pi < npairs;
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   }
   pdl_launch_dependents();
   pdl_wait();  // activations written by earlier kernels are visible from here on
+  trace_mark(p.trace, 1);
 
   stage_x(p.x, p.norm_weight, p.eps, p.K, sx, red);
 
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
       p.part_idx[blockIdx.x] = besti;
     }
   }
+  trace_mark(p.trace, 2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -303,7 +307,9 @@ static int launch(const Params& p, int npairs, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   pdl_config(cfg, attr, grid_for(npairs), THREADS, smem, st);
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE>, p));
+  Params q = p;
+  q.trace = trace_next_slot();
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE>, q));
   return SRGPT_OK;
 }
 
