@@ -265,13 +265,28 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, int n_heads, int n_kv_heads, int h
 // ---------------------------------------------------------------------------------------------
 // decode attention: one CTA per query head, 32 half-warps; half-warp hw owns kv positions
 // j = hw, hw+32, ...; every lane holds 8 of the 128 head dims (one 16-byte load per K/V row).
-// The kernel is latency-bound (a few hundred KB per head), so the page table is staged in shared
-// memory and four positions' K/V rows are requested before any of them is consumed.
+//
+// The kernel is a pure latency chain (a few hundred KB per head), and the in-graph timeline
+// (profiles/r01_decode_trace_gemv_v3.txt) showed 7 us of exposed time per layer.  K/V rows of PAST positions
+// are immutable, so the first DEC_PRE*32 = 256 of them are requested BEFORE griddepcontrol.wait, i.e. while the
+// QKV kernel of this layer is still streaming its weights; only q, the true position and the newest row(s)
+// are read after the dependency resolves.  `*kv_len_minus1` read before the wait may be one step stale, which
+// is a valid lower bound (positions only grow and rows below it are final).
 // ---------------------------------------------------------------------------------------------
 constexpr int DEC_THREADS = 512;
 constexpr int DEC_HW = DEC_THREADS / 16;
+constexpr int DEC_PRE = 8;
 constexpr int DEC_UNROLL = 4;
-constexpr int DEC_MAX_PAGES = 1024;
+
+__device__ __forceinline__ void dec_load_kv(const bf16* __restrict__ kv_pages, const int* __restrict__ page_table, int page_size,
+                                            size_t row_stride, int kvh, int hl, int j, uint4& ku, uint4& vu) {
+  const int pg = j / page_size;
+  const int page = __ldg(page_table + pg);
+  const int slot = j - pg * page_size;
+  const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + slot) * row_stride + kvh * 128 + hl * 8;
+  ku = *reinterpret_cast<const uint4*>(kp);
+  vu = *reinterpret_cast<const uint4*>(kp + (size_t)page_size * row_stride);
+}
 
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf16* __restrict__ kv_pages,
@@ -280,60 +295,51 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
   constexpr int HD = 128;
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
-  __shared__ int s_pages[DEC_MAX_PAGES];
   const int head = blockIdx.x, kvh = head / group;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
-  // programmatic dependent launch: let the next kernel (o_proj GEMV) start priming its weight ring now;
-  // wait for the QKV kernel's q / KV-cache writes before reading them
+  const size_t row_stride = (size_t)n_kv_heads * HD;
   trace_mark(trace, 0);
+
+  // ---- before the dependency wait: immutable rows only
+  const int pos_early = *reinterpret_cast<const volatile int*>(kv_len_minus1);  // rows [0, pos_early) are final
+  uint4 kpre[DEC_PRE], vpre[DEC_PRE];
+#pragma unroll
+  for (int u = 0; u < DEC_PRE; ++u) {
+    const int j = u * DEC_HW + hw;
+    kpre[u] = make_uint4(0, 0, 0, 0);
+    vpre[u] = make_uint4(0, 0, 0, 0);
+    if (j < pos_early) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, kpre[u], vpre[u]);
+  }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   trace_mark(trace, 1);
-  const int kv_len = *kv_len_minus1 + 1;
-  const int n_pages = (kv_len + page_size - 1) / page_size;
-  const bool pages_in_smem = n_pages <= DEC_MAX_PAGES;
-  if (pages_in_smem)
-    for (int i = threadIdx.x; i < n_pages; i += DEC_THREADS) s_pages[i] = page_table[i];
+
+  const int kv_len = *reinterpret_cast<const volatile int*>(kv_len_minus1) + 1;
   float qf[8];
   unpack8(*reinterpret_cast<const uint4*>(q + head * HD + hl * 8), qf);
-  __syncthreads();
   float m = -INFINITY, l = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const size_t row_stride = (size_t)n_kv_heads * HD;
-  for (int j0 = 0; j0 < kv_len; j0 += DEC_HW * DEC_UNROLL) {  // warp-uniform trip count
-    uint4 ku[DEC_UNROLL], vu[DEC_UNROLL];
-    bool valid[DEC_UNROLL];
+
+  auto consume = [&](const uint4* ku, const uint4* vu, const bool* valid, int n) {
+    float d[DEC_PRE];
 #pragma unroll
-    for (int u = 0; u < DEC_UNROLL; ++u) {
-      const int j = j0 + u * DEC_HW + hw;
-      valid[u] = j < kv_len;
-      ku[u] = make_uint4(0, 0, 0, 0);
-      vu[u] = make_uint4(0, 0, 0, 0);
-      if (valid[u]) {
-        const int pg = j / page_size;
-        const int page = pages_in_smem ? s_pages[pg] : page_table[pg];
-        const int slot = j - pg * page_size;
-        const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + slot) * row_stride + kvh * HD + hl * 8;
-        ku[u] = *reinterpret_cast<const uint4*>(kp);
-        vu[u] = *reinterpret_cast<const uint4*>(kp + (size_t)page_size * row_stride);
+    for (int u = 0; u < DEC_PRE; ++u) {
+      if (u < n) {
+        float kf[8];
+        unpack8(ku[u], kf);
+        d[u] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d[u] = fmaf(qf[t], kf[t], d[u]);
       }
-    }
-    float d[DEC_UNROLL];
-#pragma unroll
-    for (int u = 0; u < DEC_UNROLL; ++u) {
-      float kf[8];
-      unpack8(ku[u], kf);
-      d[u] = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) d[u] = fmaf(qf[t], kf[t], d[u]);
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
-      for (int u = 0; u < DEC_UNROLL; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);  // stays inside the half-warp
+      for (int u = 0; u < DEC_PRE; ++u)
+        if (u < n) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);  // stays inside the half-warp; n is warp-uniform
     }
 #pragma unroll
-    for (int u = 0; u < DEC_UNROLL; ++u) {
-      if (valid[u]) {
+    for (int u = 0; u < DEC_PRE; ++u) {
+      if (u < n && valid[u]) {
         float vf[8];
         unpack8(vu[u], vf);
         const float dd = d[u] * scale_log2;
@@ -345,7 +351,30 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
         m = m_new;
       }
     }
+  };
+
+  {  // prefetched window
+    bool valid[DEC_PRE];
+#pragma unroll
+    for (int u = 0; u < DEC_PRE; ++u) valid[u] = (u * DEC_HW + hw) < pos_early;
+    consume(kpre, vpre, valid, DEC_PRE);
   }
+  // ---- everything the prefetch did not cover: the newest row(s) and positions >= DEC_PRE*32
+  const int done_upto = pos_early < DEC_PRE * DEC_HW ? pos_early : DEC_PRE * DEC_HW;  // positions [0, done_upto) are consumed
+  for (int j0 = (done_upto / DEC_HW) * DEC_HW; j0 < kv_len; j0 += DEC_HW * DEC_UNROLL) {  // warp-uniform trip count
+    uint4 ku[DEC_UNROLL], vu[DEC_UNROLL];
+    bool valid[DEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int j = j0 + u * DEC_HW + hw;
+      valid[u] = j < kv_len && j >= done_upto;
+      ku[u] = make_uint4(0, 0, 0, 0);
+      vu[u] = make_uint4(0, 0, 0, 0);
+      if (valid[u]) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, ku[u], vu[u]);
+    }
+    consume(ku, vu, valid, DEC_UNROLL);
+  }
+
   if (hl == 0) { s_m[hw] = m; s_l[hw] = l; }
 #pragma unroll
   for (int t = 0; t < 8; ++t) s_acc[hw][hl * 8 + t] = acc[t];
