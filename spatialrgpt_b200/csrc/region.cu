@@ -89,23 +89,49 @@ mask_normalise_kernel(bf16* __restrict__ w, const float* __restrict__ psum, int 
 // mask pooling: out[img,m,c] = sum_l w[img,m,l] * x[img,l,c]
 // CTA = 16 channel-threads (8 channels each = 128 channels, one 256-byte row segment) x 16 row lanes.
 // grid = (row chunks R, channel chunks Q, images).  fp32 partials [img][R][M][C], then a tiny reduce.
+// Inner loop per 16-byte feature load: 2 x LDS.128 (the row's 8 mask weights, broadcast), 8 ALU ops to widen
+// bf16 -> fp32 pairs, 32 packed FFMA2 (fma.rn.f32x2, new on sm_100) instead of 64 FFMA; rows whose 8 weights
+// are all zero (most rows of a region mask) are skipped.
 // ---------------------------------------------------------------------------------------------
 constexpr int MP_THREADS = 256;
 constexpr int MP_CH = 128;   // channels per CTA
 constexpr int MP_RL = 16;    // row lanes
 constexpr int MP_MT = 8;     // masks per pass
-constexpr int MP_MAX_ROWS = 512;  // rows per CTA (weights staged in smem: 8 * 512 * 4 = 16 KB)
+constexpr int MP_MAX_ROWS = 512;  // rows per CTA (weights staged in smem: 512 * 8 * 4 = 16 KB)
+
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, float w) {
+  // d += a * {w, w}
+  unsigned long long dd, aa, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
+__device__ __forceinline__ void mp_accumulate(float2 (*acc)[4], const uint4& u, const float4& wa, const float4& wb) {
+  float2 f[4];
+  f[0] = make_float2(bf16_lo(u.x), bf16_hi(u.x));
+  f[1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+  f[2] = make_float2(bf16_lo(u.z), bf16_hi(u.z));
+  f[3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
+  const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+  for (int mm = 0; mm < MP_MT; ++mm)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ffma2(acc[mm][t], f[t], wv[mm]);
+}
 
 __global__ void __launch_bounds__(MP_THREADS, 2)
 mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
                  int rows_per_cta, int R) {
   // one buffer, two views (never live at the same time; 36 KB keeps us under the 48 KB static limit):
-  //   sw  [MP_MT][MP_MAX_ROWS]            staged mask weights for this CTA's rows
+  //   sw  [MP_MAX_ROWS][MP_MT]            staged mask weights of this CTA's rows (row-major: one row = 2 x float4)
   //   sred[warps][MP_MT][MP_CH/8][9]      cross-warp reduction of the accumulators (+1 pad)
   constexpr int SRED_FLOATS = (MP_THREADS / 32) * MP_MT * (MP_CH / 8) * 9;
   constexpr int SW_FLOATS = MP_MT * MP_MAX_ROWS;
-  __shared__ float sbuf[SRED_FLOATS > SW_FLOATS ? SRED_FLOATS : SW_FLOATS];
-  float (*sw)[MP_MAX_ROWS] = reinterpret_cast<float (*)[MP_MAX_ROWS]>(sbuf);
+  __shared__ __align__(16) float sbuf[SRED_FLOATS > SW_FLOATS ? SRED_FLOATS : SW_FLOATS];
+  float4* sw4 = reinterpret_cast<float4*>(sbuf);  // sw4[2*r], sw4[2*r+1]
   float (*sred)[MP_MT][MP_CH / 8][9] = reinterpret_cast<float (*)[MP_MT][MP_CH / 8][9]>(sbuf);
   const int img = blockIdx.z;
   const int cthr = threadIdx.x & 15, rl = threadIdx.x >> 4;
@@ -120,15 +146,15 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
     const int mt = min(MP_MT, M - m0);
     __syncthreads();
     for (int i = threadIdx.x; i < MP_MT * rows_per_cta; i += MP_THREADS) {
-      const int mm = i / rows_per_cta, r = i % rows_per_cta;
-      sw[mm][r] = (mm < mt && r < nrows) ? __bfloat162float(w[((size_t)img * M + m0 + mm) * L + l0 + r]) : 0.f;
+      const int mm = i / rows_per_cta, r = i - mm * rows_per_cta;  // r fastest: coalesced reads of w
+      sbuf[r * MP_MT + mm] = (mm < mt && r < nrows) ? __bfloat162float(w[((size_t)img * M + m0 + mm) * L + l0 + r]) : 0.f;
     }
     __syncthreads();
-    float acc[MP_MT][8];
+    float2 acc[MP_MT][4];
 #pragma unroll
     for (int mm = 0; mm < MP_MT; ++mm)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[mm][t] = 0.f;
+      for (int t = 0; t < 4; ++t) acc[mm][t] = make_float2(0.f, 0.f);
 
     if (c_ok) {
       int r = rl;
@@ -139,40 +165,34 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
         for (int k = 0; k < 8; ++k) u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float f[8];
-          unpack8(u[k], f);
-#pragma unroll
-          for (int mm = 0; mm < MP_MT; ++mm) {
-            const float wm = sw[mm][r + k * MP_RL];
-            if (wm != 0.f) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) acc[mm][t] = fmaf(wm, f[t], acc[mm][t]);
-            }
-          }
+          const float4 wa = sw4[2 * (r + k * MP_RL)], wb = sw4[2 * (r + k * MP_RL) + 1];
+          const bool nz = (wa.x != 0.f) | (wa.y != 0.f) | (wa.z != 0.f) | (wa.w != 0.f) | (wb.x != 0.f) | (wb.y != 0.f) |
+                          (wb.z != 0.f) | (wb.w != 0.f);
+          if (nz) mp_accumulate(acc, u[k], wa, wb);
         }
       }
       for (; r < nrows; r += MP_RL) {
-        float f[8];
-        unpack8(ld_stream16(xb + (size_t)r * C), f);
-#pragma unroll
-        for (int mm = 0; mm < MP_MT; ++mm) {
-          const float wm = sw[mm][r];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) acc[mm][t] = fmaf(wm, f[t], acc[mm][t]);
-        }
+        const uint4 u = ld_stream16(xb + (size_t)r * C);
+        mp_accumulate(acc, u, sw4[2 * r], sw4[2 * r + 1]);
       }
     }
     // reduce over the 16 row lanes: 2 lanes inside each warp (xor 16), then 8 warps via smem
 #pragma unroll
     for (int mm = 0; mm < MP_MT; ++mm)
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[mm][t] += __shfl_xor_sync(0xffffffffu, acc[mm][t], 16);
+      for (int t = 0; t < 4; ++t) {
+        acc[mm][t].x += __shfl_xor_sync(0xffffffffu, acc[mm][t].x, 16);
+        acc[mm][t].y += __shfl_xor_sync(0xffffffffu, acc[mm][t].y, 16);
+      }
     __syncthreads();  // everyone is done reading sw before sred (same storage) is written
     if (lane < 16) {
 #pragma unroll
       for (int mm = 0; mm < MP_MT; ++mm)
 #pragma unroll
-        for (int t = 0; t < 8; ++t) sred[warp][mm][cthr][t] = acc[mm][t];
+        for (int t = 0; t < 4; ++t) {
+          sred[warp][mm][cthr][2 * t] = acc[mm][t].x;
+          sred[warp][mm][cthr][2 * t + 1] = acc[mm][t].y;
+        }
     }
     __syncthreads();
     // 8 masks x 128 channels = 1024 outputs, 256 threads -> 4 each
