@@ -189,6 +189,14 @@ def run_ours(args):
         step_e2e()
     ms_e2e, n_tok_e2e = timed(step_e2e, args.steps)
 
+    # ---- TTFT (2 tower passes + refinement + pooling + projector + splice + Llama prefill + first token): the
+    #      "prefill TFLOPS vs roofline" half of BASELINE.json's metric, algorithmic FLOPs of SURVEY.md §8d
+    def step_ttft():
+        return model.generate(d_ids, images=d_img, depths=d_dep, masks=[d_msk], do_sample=False, max_new_tokens=1)
+    step_ttft()
+    ms_ttft, _ = timed(step_ttft, args.steps)
+    ttft_ms = ms_ttft / args.steps
+
     # ---- per-kernel roofline of the dominant kernel, timed live with CUDA events: the gate/up GEMV
     roof = None
     if rank == 0:
@@ -240,6 +248,10 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_ids, h_img, h_dep, h_msk))),
                 "d2h_bytes_per_step": NEW_TOKENS * 8, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
+        "prefill": {"ttft_ms": round(ttft_ms, 3), "algorithmic_tflop": round(nums["flops_ttft"] / 1e12, 3),
+                    "tflops": round(nums["flops_ttft"] / ttft_ms / 1e9, 1), "peak_tflops": tensor_peak,
+                    "frac_tensor": round(nums["flops_ttft"] / ttft_ms / 1e9 / tensor_peak, 4),
+                    "note": "S=259 rows per Llama GEMM: weight-streaming bound (15 GB), not tensor bound"},
         "roofline": roof,
         "cpu_baseline": cpu,
     }

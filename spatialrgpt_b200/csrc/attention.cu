@@ -291,7 +291,7 @@ __device__ __forceinline__ void dec_load_kv(const bf16* __restrict__ kv_pages, c
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf16* __restrict__ kv_pages,
                    const int* __restrict__ page_table, int page_size, const int* __restrict__ kv_len_minus1, int n_kv_heads,
-                   int group, float scale_log2, unsigned long long* trace) {
+                   int group, float scale_log2, unsigned long long* trace, int prefetch) {
   constexpr int HD = 128;
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
@@ -301,7 +301,7 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
   trace_mark(trace, 0);
 
   // ---- before the dependency wait: immutable rows only
-  const int pos_early = *reinterpret_cast<const volatile int*>(kv_len_minus1);  // rows [0, pos_early) are final
+  const int pos_early = prefetch ? *reinterpret_cast<const volatile int*>(kv_len_minus1) : 0;  // rows [0, pos_early) are final
   uint4 kpre[DEC_PRE], vpre[DEC_PRE];
 #pragma unroll
   for (int u = 0; u < DEC_PRE; ++u) {
@@ -473,9 +473,10 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf1
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  static const bool no_prefetch = env_flag("SRGPT_ATTN_NO_PREFETCH");
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn::attn_decode_kernel, reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out),
                                       reinterpret_cast<const bf16*>(kv_pages), page_table, page_size, kv_len_minus1, n_kv_heads,
-                                      n_heads / n_kv_heads, scale * 1.4426950408889634f, trace_next_slot()));
+                                      n_heads / n_kv_heads, scale * 1.4426950408889634f, trace_next_slot(), no_prefetch ? 0 : 1));
   return SRGPT_OK;
 }

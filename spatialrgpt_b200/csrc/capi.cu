@@ -1,5 +1,6 @@
 // Library-level entry points of the srgpt C-ABI: version, last error, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,6 +28,15 @@ int sm_count() {
       return 148;  // B200
   }
   return cached;
+}
+
+bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && v[0] != 0 && v[0] != '0';
+}
+bool pdl_enabled() {
+  static const bool on = !env_flag("SRGPT_NO_PDL");
+  return on;
 }
 
 static unsigned long long* g_trace_buf = nullptr;

@@ -44,6 +44,8 @@ int sm_count();  // cached multiProcessorCount of the current device
 //      [0] min globaltimer at CTA start, [1] min globaltimer after griddepcontrol.wait, [2] max globaltimer at CTA
 //      end, [3] CTA count.  Costs 3 atomics per CTA; disabled (nullptr) unless a trace buffer is installed.
 unsigned long long* trace_next_slot();  // host: returns the 4-slot record for the next launch, or nullptr
+bool pdl_enabled();                      // false when SRGPT_NO_PDL=1 (debug knob: plain stream-ordered launches)
+bool env_flag(const char* name);
 
 // ---- device helpers
 typedef __nv_bfloat16 bf16;

@@ -15,6 +15,7 @@
 // Out-of-bounds rows/cols/K are zero-filled by TMA, so M, N need no padding and K only has to
 // be a multiple of 8 elements (16-byte global strides).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "srgpt_b200.h"
@@ -22,16 +23,25 @@
 namespace srgpt {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 6;
+constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int B_STAGE_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_BUFS = 2;
-constexpr int TMEM_COLS = ACC_BUFS * BN;  // 256 (power of two >= 32)
 constexpr int NUM_THREADS = 192;           // warp0 TMA, warp1 MMA, warps 2..5 epilogue
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int MAX_STAGES = 6;
+
+// Tile configuration.  BN = 128: 32 KB / stage, 6 stages, 256 TMEM columns.  BN = 256: 48 KB / stage, 4 stages,
+// all 512 TMEM columns — 1.33x the FLOPs per byte pulled from L2, which is what bounds 128x128 tiles
+// (every SM pulls ~45 B/clk through TMA while the MMA pipe could eat 128 B/clk; see DESIGN.md "GEMM").
+template <int BN_>
+struct Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = BN_ == 128 ? 6 : 4;
+  static constexpr int B_STAGE_BYTES = BN_ * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TMEM_COLS = ACC_BUFS * BN_;  // 256 / 512 (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -189,9 +199,13 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned stage buffers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -393,16 +407,41 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, 
   return SRGPT_OK;
 }
 
-template <int EPI>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+template <int EPI, int BN>
+static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+  using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  gemm_bf16_tn_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_bf16_tn_kernel<EPI, BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
+}
+
+// 128x256 tiles when that still leaves >= 2 full waves of tiles (large M x N), else 128x128
+static int pick_bn(int M, int N) {
+  static const int forced = [] {
+    const char* v = getenv("SRGPT_GEMM_BN");
+    return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
+  }();
+  if (forced == 128 || forced == 256) return forced;
+  const long tiles256 = (long)ceil_div(M, BM) * ceil_div(N, 256);
+  return tiles256 >= 2L * sm_count() ? 256 : 128;
+}
+
+template <int EPI>
+static int launch(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
+  const int bn = pick_bn(p.M, p.N);
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  if (rc != SRGPT_OK) return rc;
+  rc = make_tmap(&tb, W, p.N, p.K, ldw, bn);
+  if (rc != SRGPT_OK) return rc;
+  const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, bn);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  return bn == 256 ? launch_bn<EPI, 256>(ta, tb, p, grid, stream) : launch_bn<EPI, 128>(ta, tb, p, grid, stream);
 }
 
 }  // namespace gemm
@@ -432,12 +471,6 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
   }
   if (bias != nullptr) SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 
-  CUtensorMap ta, tb;
-  int rc = gemm::make_tmap(&ta, A, M, K, lda, gemm::BM);
-  if (rc != SRGPT_OK) return rc;
-  rc = gemm::make_tmap(&tb, W, N, K, ldw, gemm::BN);
-  if (rc != SRGPT_OK) return rc;
-
   gemm::Params p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc;
   p.bias = reinterpret_cast<const bf16*>(bias);
@@ -445,16 +478,14 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
   p.ldr = ldr; p.res_row_mod = res_row_mod;
   p.C = C; p.epilogue = epilogue; p.out_fp32 = out_fp32;
 
-  const int tiles = ceil_div(M, gemm::BM) * ceil_div(N, gemm::BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (epilogue) {
-    case SRGPT_EPI_NONE: return gemm::launch<SRGPT_EPI_NONE>(ta, tb, p, grid, st);
-    case SRGPT_EPI_BIAS: return gemm::launch<SRGPT_EPI_BIAS>(ta, tb, p, grid, st);
-    case SRGPT_EPI_BIAS_GELU_TANH: return gemm::launch<SRGPT_EPI_BIAS_GELU_TANH>(ta, tb, p, grid, st);
-    case SRGPT_EPI_BIAS_GELU_ERF: return gemm::launch<SRGPT_EPI_BIAS_GELU_ERF>(ta, tb, p, grid, st);
-    case SRGPT_EPI_BIAS_RESIDUAL: return gemm::launch<SRGPT_EPI_BIAS_RESIDUAL>(ta, tb, p, grid, st);
-    case SRGPT_EPI_SWIGLU: return gemm::launch<SRGPT_EPI_SWIGLU>(ta, tb, p, grid, st);
+    case SRGPT_EPI_NONE: return gemm::launch<SRGPT_EPI_NONE>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_BIAS: return gemm::launch<SRGPT_EPI_BIAS>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_BIAS_GELU_TANH: return gemm::launch<SRGPT_EPI_BIAS_GELU_TANH>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_BIAS_GELU_ERF: return gemm::launch<SRGPT_EPI_BIAS_GELU_ERF>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_BIAS_RESIDUAL: return gemm::launch<SRGPT_EPI_BIAS_RESIDUAL>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_SWIGLU: return gemm::launch<SRGPT_EPI_SWIGLU>(A, lda, W, ldw, p, st);
   }
   return SRGPT_ERR_INVALID;
 }

@@ -153,9 +153,9 @@ class LlamaDecoder:
         if self._graph is not None:
             return
         # warm up once outside capture (lazy cudaFuncSetAttribute calls etc.), on a side stream
-        s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream())
         saved = (self.pos.clone(), self.step.clone(), self.h.clone(), self.out_ids.clone())
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())  # after the clones are enqueued
         with torch.cuda.stream(s):
             self._decode_step_launch(seq)
         torch.cuda.current_stream().wait_stream(s)

@@ -33,6 +33,7 @@ def rnd(*shape, seed=0, scale=1.0, dtype=BF):
 GEMM_SHAPES = [
     (128, 128, 64), (128, 128, 128), (256, 256, 512), (259, 384, 512), (1, 128, 64), (3, 8, 8), (77, 200, 72),
     (300, 4304, 1152), (300, 1152, 4304), (1024, 1152, 592), (259, 6144, 4096), (130, 272, 4096),
+    (4096, 4608, 320), (2100, 9000, 136),  # >= 2 waves of 128x256 tiles -> the BN=256 configuration (N tail: 9000 % 256 = 40)
 ]
 
 
@@ -46,7 +47,7 @@ def test_gemm_plain(ops, M, N, K):
     assert_close(out32, ref, rel_rms=1e-4, rel_max=1e-3, what=f"gemm fp32-out {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("M,N,K", [(259, 384, 512), (200, 296, 144), (1024, 1152, 1152), (77, 304, 72)])
+@pytest.mark.parametrize("M,N,K", [(259, 384, 512), (200, 296, 144), (1024, 1152, 1152), (77, 304, 72), (4100, 4624, 192)])
 def test_gemm_epilogues(ops, M, N, K):
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
     bias, res = rnd(N, seed=3), rnd(M, N, seed=4)

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_gpu_full.log 2>&1; echo "pytest gpu exit $?"; tail -6 gpurun_out/pytest_gpu_full.log
-timeout 600 python tools/microbench.py maskpool > gpurun_out/microbench_maskpool.log 2>&1; echo "microbench exit $?"; grep -E "mask_pool n1 L16384 C1152 M8|n4" gpurun_out/microbench_maskpool.log
+timeout 600 python tools/microbench.py gemm > gpurun_out/microbench_gemm.log 2>&1; echo "microbench exit $?"; cat gpurun_out/microbench_gemm.log | cut -c1-200
 timeout 600 python tools/decode_trace.py > gpurun_out/decode_trace.log 2>&1; echo "trace exit $?"; tail -8 gpurun_out/decode_trace.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; python -c "
 import json; d=json.load(open('gpurun_out/bench_n1.json')); print({k:d[k] for k in ('value','ms_per_step','e2e')}); print(d['roofline'])"; tail -3 gpurun_out/bench_n1.err
