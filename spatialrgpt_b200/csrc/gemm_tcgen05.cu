@@ -9,7 +9,7 @@
 //   * persistent kernel, one CTA per SM, static round-robin over 128x128 output tiles;
 //   * warp 0  : TMA producer  (cp.async.bulk.tensor 2D, 128B-swizzled K-major boxes, 6-stage ring);
 //   * warp 1  : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM;
-//   * warps 2-5: epilogue (tcgen05.ld 32x32b -> registers -> fused bias/activation/residual ->
+//   * warps 2-9: epilogue (tcgen05.ld 32x32b -> registers -> fused bias/activation/residual ->
 //                 16-byte global stores); overlaps the next tile's main loop.
 //   * mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // Out-of-bounds rows/cols/K are zero-filled by TMA, so M, N need no padding and K only has to
@@ -27,7 +27,8 @@ constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ACC_BUFS = 2;
-constexpr int NUM_THREADS = 192;           // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane group, each owns half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int MAX_STAGES = 6;
 
 // Tile configuration.  BN = 128: 32 KB / stage, 6 stages, 256 TMEM columns.  BN = 256: 48 KB / stage, 4 stages,
@@ -232,7 +233,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < ACC_BUFS; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[a]), NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -290,8 +291,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    // With short K (SigLIP: 18 k-blocks) the epilogue of a tile costs as many issue slots as its main loop, and one
+    // warp per scheduler cannot hide the TMEM / global latencies -> two warps per lane group, half the columns each.
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    const int chalf = (warp - 2) >> 2;  // 0: columns [0, BN/2), 1: columns [BN/2, BN)
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * BM;
@@ -300,7 +304,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_after();
       const int row = m0 + lg * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];

@@ -69,20 +69,29 @@ mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __res
   if (threadIdx.x == 0) psum[((size_t)img * M + m) * MW_SPLITS + split] = total;
 }
 
+// `w` (optional) keeps the reference layout [img][M][L]; `wt` is what mask_pool streams: [img][ceil(M/8)][L][8]
+// bf16, i.e. the 8 weights of a feature row are one 16-byte vector (zero for m >= M).
 __global__ void __launch_bounds__(256)
-mask_normalise_kernel(bf16* __restrict__ w, const float* __restrict__ psum, int M, int L) {
+mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, bf16* __restrict__ wt, const float* __restrict__ psum,
+                      int M, int L) {
   const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
   const float* ps = psum + ((size_t)img * M + m) * MW_SPLITS;
   float total = 0.f;
 #pragma unroll
   for (int i = 0; i < MW_SPLITS; ++i) total += ps[i];
   const float denorm = bf16_round(bf16_round(total) + 1e-8f);
-  bf16* dst = w + ((size_t)img * M + m) * L;
+  const bf16* src = v + ((size_t)img * M + m) * L;
+  const int mt_tiles = (M + 7) >> 3;
+  bf16* dst_t = wt + (((size_t)img * mt_tiles + (m >> 3)) * L) * 8 + (m & 7);
+  bf16* dst = (w != nullptr) ? w + ((size_t)img * M + m) * L : nullptr;
   const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
   const int l_end = min(L, (split + 1) * per);
   // rows are a permutation of l; normalising the contiguous range [split*per, l_end) of ROWS covers every row once
-  for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x)
-    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(dst[r]), denorm));
+  for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x) {
+    const bf16 q = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(src[r]), denorm));
+    dst_t[(size_t)r * 8] = q;
+    if (dst != nullptr) dst[r] = q;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +106,7 @@ constexpr int MP_THREADS = 256;
 constexpr int MP_CH = 128;   // channels per CTA
 constexpr int MP_RL = 16;    // row lanes
 constexpr int MP_MT = 8;     // masks per pass
-constexpr int MP_MAX_ROWS = 512;  // rows per CTA (weights staged in smem: 512 * 8 * 4 = 16 KB)
+constexpr int MP_MAX_ROWS = 512;  // rows per CTA
 
 __device__ __forceinline__ void ffma2(float2& d, const float2& a, float w) {
   // d += a * {w, w}
@@ -123,16 +132,10 @@ __device__ __forceinline__ void mp_accumulate(float2 (*acc)[4], const uint4& u, 
 }
 
 __global__ void __launch_bounds__(MP_THREADS, 2)
-mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
+mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wt, float* __restrict__ partial, int M, int L, int C,
                  int rows_per_cta, int R) {
-  // one buffer, two views (never live at the same time; 36 KB keeps us under the 48 KB static limit):
-  //   sw  [MP_MAX_ROWS][MP_MT]            staged mask weights of this CTA's rows (row-major: one row = 2 x float4)
-  //   sred[warps][MP_MT][MP_CH/8][9]      cross-warp reduction of the accumulators (+1 pad)
-  constexpr int SRED_FLOATS = (MP_THREADS / 32) * MP_MT * (MP_CH / 8) * 9;
-  constexpr int SW_FLOATS = MP_MT * MP_MAX_ROWS;
-  __shared__ __align__(16) float sbuf[SRED_FLOATS > SW_FLOATS ? SRED_FLOATS : SW_FLOATS];
-  float4* sw4 = reinterpret_cast<float4*>(sbuf);  // sw4[2*r], sw4[2*r+1]
-  float (*sred)[MP_MT][MP_CH / 8][9] = reinterpret_cast<float (*)[MP_MT][MP_CH / 8][9]>(sbuf);
+  // cross-warp reduction buffer [warps][MP_MT][MP_CH/8][8 (+1 pad)]
+  __shared__ float sred[MP_THREADS / 32][MP_MT][MP_CH / 8][9];
   const int img = blockIdx.z;
   const int cthr = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,15 +144,13 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
   const int l0 = blockIdx.x * rows_per_cta;
   const int nrows = min(rows_per_cta, L - l0);
   const bf16* xb = x + ((size_t)img * L + l0) * C + c0;
+  const int mt_tiles = (M + MP_MT - 1) / MP_MT;
 
-  for (int m0 = 0; m0 < M; m0 += MP_MT) {
+  for (int mtile = 0; mtile < mt_tiles; ++mtile) {
+    const int m0 = mtile * MP_MT;
     const int mt = min(MP_MT, M - m0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < MP_MT * rows_per_cta; i += MP_THREADS) {
-      const int mm = i / rows_per_cta, r = i - mm * rows_per_cta;  // r fastest: coalesced reads of w
-      sbuf[r * MP_MT + mm] = (mm < mt && r < nrows) ? __bfloat162float(w[((size_t)img * M + m0 + mm) * L + l0 + r]) : 0.f;
-    }
-    __syncthreads();
+    // the 8 weights of row r: one 16-byte vector, identical for the 16 channel-threads of a row (L1 broadcast)
+    const uint4* wrow = reinterpret_cast<const uint4*>(wt + (((size_t)img * mt_tiles + mtile) * L + l0) * 8);
     float2 acc[MP_MT][4];
 #pragma unroll
     for (int mm = 0; mm < MP_MT; ++mm)
@@ -158,22 +159,29 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
 
     if (c_ok) {
       int r = rl;
-      // 8 independent 16-byte loads in flight per thread (64 KB per SM with 2 resident CTAs)
+      // 8 feature + 8 weight 16-byte loads in flight per thread; no prologue, the first loads leave at kernel start
       for (; r + 7 * MP_RL < nrows; r += 8 * MP_RL) {
-        uint4 u[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
+        uint4 u[8], wv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float4 wa = sw4[2 * (r + k * MP_RL)], wb = sw4[2 * (r + k * MP_RL) + 1];
-          const bool nz = (wa.x != 0.f) | (wa.y != 0.f) | (wa.z != 0.f) | (wa.w != 0.f) | (wb.x != 0.f) | (wb.y != 0.f) |
-                          (wb.z != 0.f) | (wb.w != 0.f);
-          if (nz) mp_accumulate(acc, u[k], wa, wb);
+          u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
+          wv[k] = __ldg(wrow + r + k * MP_RL);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if ((wv[k].x | wv[k].y | wv[k].z | wv[k].w) != 0u) {  // rows outside every region are skipped
+            const float4 wa = make_float4(bf16_lo(wv[k].x), bf16_hi(wv[k].x), bf16_lo(wv[k].y), bf16_hi(wv[k].y));
+            const float4 wb = make_float4(bf16_lo(wv[k].z), bf16_hi(wv[k].z), bf16_lo(wv[k].w), bf16_hi(wv[k].w));
+            mp_accumulate(acc, u[k], wa, wb);
+          }
         }
       }
       for (; r < nrows; r += MP_RL) {
         const uint4 u = ld_stream16(xb + (size_t)r * C);
-        mp_accumulate(acc, u, sw4[2 * r], sw4[2 * r + 1]);
+        const uint4 wq = __ldg(wrow + r);
+        const float4 wa = make_float4(bf16_lo(wq.x), bf16_hi(wq.x), bf16_lo(wq.y), bf16_hi(wq.y));
+        const float4 wb = make_float4(bf16_lo(wq.z), bf16_hi(wq.z), bf16_lo(wq.w), bf16_hi(wq.w));
+        mp_accumulate(acc, u, wa, wb);
       }
     }
     // reduce over the 16 row lanes: 2 lanes inside each warp (xor 16), then 8 warps via smem
@@ -184,7 +192,7 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
         acc[mm][t].x += __shfl_xor_sync(0xffffffffu, acc[mm][t].x, 16);
         acc[mm][t].y += __shfl_xor_sync(0xffffffffu, acc[mm][t].y, 16);
       }
-    __syncthreads();  // everyone is done reading sw before sred (same storage) is written
+    __syncthreads();  // previous pass finished reading sred
     if (lane < 16) {
 #pragma unroll
       for (int mm = 0; mm < MP_MT; ++mm)
@@ -331,24 +339,30 @@ using namespace srgpt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_workspace(int n_img, int M) {
-  if (n_img <= 0 || M <= 0) return -1;
-  return (long long)n_img * M * MW_SPLITS * (long long)sizeof(float);
+extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_workspace(int n_img, int M, int side) {
+  if (n_img <= 0 || M <= 0 || side <= 0) return -1;
+  return (long long)n_img * M * (MW_SPLITS * (long long)sizeof(float) + (long long)side * side * (long long)sizeof(bf16));
 }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW, int side,
-                                  float rscale, int order, void* stream) {
-  SRGPT_CHECK_ARG(masks && w && workspace && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
+extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* wt, void* workspace, int n_img, int M, int IH, int IW,
+                                  int side, float rscale, int order, void* stream) {
+  SRGPT_CHECK_ARG(masks && wt && workspace && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
   SRGPT_CHECK_ARG(order == 0 || (order == 2 && (side % 4) == 0));
+  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(wt) & 15) == 0);
   dim3 grid(MW_SPLITS, M, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int L = side * side;
+  // workspace: [n_img*M*MW_SPLITS] fp32 partial sums, then [n_img*M*L] bf16 un-normalised resampled masks
   float* psum = reinterpret_cast<float*>(workspace);
+  bf16* v = reinterpret_cast<bf16*>(psum + (size_t)n_img * M * MW_SPLITS);
+  const int mt_tiles = (M + 7) / 8;
+  if ((M & 7) != 0) SRGPT_CHECK_CUDA(cudaMemsetAsync(wt, 0, (size_t)n_img * mt_tiles * L * 8 * sizeof(bf16), st));  // zero rows m >= M
   if (mask_is_bf16)
-    mask_taps_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), reinterpret_cast<bf16*>(w), psum, M, IH, IW, side, rscale, order);
+    mask_taps_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), v, psum, M, IH, IW, side, rscale, order);
   else
-    mask_taps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), reinterpret_cast<bf16*>(w), psum, M, IH, IW, side, rscale, order);
+    mask_taps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), v, psum, M, IH, IW, side, rscale, order);
   SRGPT_CHECK_LAUNCH();
-  mask_normalise_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<bf16*>(w), psum, M, side * side);
+  mask_normalise_kernel<<<grid, 256, 0, st>>>(v, reinterpret_cast<bf16*>(w), reinterpret_cast<bf16*>(wt), psum, M, L);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }
@@ -363,7 +377,7 @@ extern "C" __attribute__((visibility("default"))) long long srgpt_mask_pool_work
 extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const void* x, const void* w, void* out, void* workspace, int n_img, int M, int L, int C,
                                     void* stream) {
   SRGPT_CHECK_ARG(x && w && out && workspace && n_img > 0 && M > 0 && L > 0 && C > 0);
-  SRGPT_CHECK_ARG((C % 8) == 0 && aligned16(x));
+  SRGPT_CHECK_ARG((C % 8) == 0 && aligned16(x) && aligned16(w));
   int R, rpc, Q;
   mask_pool_plan(n_img, L, C, &R, &rpc, &Q);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -29,7 +29,7 @@ def assert_close(out: torch.Tensor, ref: torch.Tensor, rel_rms: float, rel_max: 
 #   one bf16 rounding of an fp32-accumulated result            -> rms 2^-9 ~ 2e-3, max 2^-8 ~ 4e-3 of the value
 BF16_1ROUND = dict(rel_rms=4e-3, rel_max=3e-2)
 #   a few chained bf16 ops (norm/activation/residual epilogues) -> 1e-2 rms
-BF16_CHAIN = dict(rel_rms=1.5e-2, rel_max=1.5e-1)
+BF16_CHAIN = dict(rel_rms=1.5e-2, rel_max=2.5e-1)  # max over up to ~2e7 elements: a few-sigma tail of bf16 roundings
 #   a whole network stage (tens of layers) vs the fp32 oracle    -> 5e-2 rms
 BF16_STAGE = dict(rel_rms=5e-2, rel_max=6e-1)
 
