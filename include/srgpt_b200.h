@@ -158,6 +158,34 @@ int srgpt_lm_head_argmax_bf16(const void* x, const void* W, int ldw, int V, int 
 /* Plain argmax over fp32 rows (first index on ties), e.g. first token after prefill. */
 int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream);
 
+/* ---- composite entry points (layers.cu): one call per tower pass / prompt / decode step -------------------
+ * Pure sequencing of the kernels above on `stream` (no allocation, no sync); they exist because a Python-side
+ * launch costs more host time than several of these kernels take on the device.  Weights are the re-laid-out
+ * tensors described in DESIGN.md §3 (fused qkv, interleaved gate/up).  Workspaces (bf16): ws_h [M, D|H],
+ * ws_qkv [M, 3D | (nh+2nkv)hd], ws_attn [M, D | nh*hd], ws_mlp [M, I] / ws_act [S, I]. */
+typedef struct {
+  const void *ln1_w, *ln1_b, *qkv_w, *qkv_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} srgpt_siglip_layer_weights;
+typedef struct {
+  const void *in_norm, *qkv_w, *o_w, *post_norm, *gateup_w, *down_w;
+  void* kv_pages; /* this layer's KV pages [n_pages, 2, page_size, nkv, hd] */
+} srgpt_llama_layer_weights;
+/* n_layers SigLIP encoder layers in place on x [n_img*T, D] (HF SiglipEncoderLayer; call site vision_encoder.py:119-130). */
+int srgpt_siglip_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
+                             void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps, void* stream);
+/* n_layers Llama decoder layers over one prompt x [S, H] in place, appending K/V to the paged cache
+ * (LlamaDecoderLayer.forward, modeling_llama.py:623-684). */
+int srgpt_llama_prefill_layers_bf16(void* x, const srgpt_llama_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
+                                    void* ws_attn, void* ws_act, int S, int H, int n_heads, int n_kv_heads, int head_dim, int I,
+                                    float eps, const void* cos_tab, const void* sin_tab, const int* start_pos,
+                                    const int* page_table, int page_size, void* stream);
+/* One whole decode step (5 kernels per layer + lm_head + argmax), h [H] in/out = residual stream of the new token. */
+int srgpt_llama_decode_step_bf16(void* h, const srgpt_llama_layer_weights* layers, int n_layers, void* q_buf, void* attn_buf,
+                                 void* act_buf, int H, int n_heads, int n_kv_heads, int head_dim, int I, float eps,
+                                 const void* cos_tab, const void* sin_tab, int* pos, const int* page_table, int page_size,
+                                 const void* final_norm, const void* lm_head, int V, const void* embed_table, void* lm_workspace,
+                                 float* logits_out, long long* out_ids, int* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

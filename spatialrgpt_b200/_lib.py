@@ -49,7 +49,19 @@ SIGNATURES = {
     "srgpt_lm_head_workspace": (cll, [ci]),
     "srgpt_lm_head_argmax_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp, vp, vp]),
     "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
+    "srgpt_siglip_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]),
+    "srgpt_llama_prefill_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp]),
+    "srgpt_llama_decode_step_bf16": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp,
+                                          vp, vp]),
 }
+
+
+class SiglipLayerWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class LlamaLayerWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("in_norm", "qkv_w", "o_w", "post_norm", "gateup_w", "down_w", "kv_pages")]
 
 
 def lib_path() -> str:

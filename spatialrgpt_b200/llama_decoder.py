@@ -91,6 +91,7 @@ class LlamaDecoder:
         self.act_buf = torch.zeros(I, dtype=torch.bfloat16, device=dev)
         self.lm_ws = ops.lm_head_workspace(dims.vocab_size, dev)
         self.scale = hd ** -0.5
+        self._layer_array = ops.make_llama_layer_array(w.layers, [self.cache.layer(l) for l in range(dims.num_hidden_layers)])
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.kernels_per_decode_step = 5 * dims.num_hidden_layers + 2
 
@@ -108,23 +109,12 @@ class LlamaDecoder:
         if start_pos + S > self.max_seq_len:
             raise RuntimeError(f"prompt of {S} tokens at {start_pos} exceeds max_seq_len {self.max_seq_len}")
         self.cache.reserve(seq, start_pos + S)
-        nh, nkv, hd = d.num_attention_heads, d.num_key_value_heads, d.head_dim
-        qd, kd = nh * hd, nkv * hd
         sp = torch.tensor([start_pos], dtype=torch.int32, device=self.device)
         pt = self.cache.page_tables[seq]
         x = inputs_embeds.to(torch.bfloat16).contiguous().clone()
         if start_pos != 0:
             raise NotImplementedError("chunked prefill (prompt attention over cached pages) is a next-round item")
-        for l, lw in enumerate(w.layers):
-            h = ops.rmsnorm(x, lw.in_norm, d.rms_norm_eps)
-            qkv = ops.gemm(h, lw.qkv_w)
-            ops.rope_kv_append(qkv, nh, nkv, hd, self.cos, self.sin, sp, self.cache.layer(l), pt, PAGE_SIZE)
-            o = ops.attention_prefill(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], 1, S, nh, nkv, hd, self.scale, causal=True)
-            x = ops.gemm(o, lw.o_w, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
-            h = ops.rmsnorm(x, lw.post_norm, d.rms_norm_eps, out=h)
-            a = ops.gemm(h, lw.gateup_w, epilogue=ops.EPI_SWIGLU)
-            x = ops.gemm(a, lw.down_w, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
-        return x
+        return ops.llama_prefill_layers(x, self._layer_array, d.num_hidden_layers, d, self.cos, self.sin, sp, pt, PAGE_SIZE)
 
     def logits_all(self, hidden: torch.Tensor) -> torch.Tensor:
         """lm_head over every row -> fp32 logits [S, V] (LlamaForCausalLM.forward semantics, 1044-1045)."""
@@ -135,19 +125,9 @@ class LlamaDecoder:
     # ---------------------------------------------------------------------------------------------
     def _decode_step_launch(self, seq: int, logits_out: Optional[torch.Tensor] = None) -> None:
         d, w = self.dims, self.w
-        nh, nkv, hd = d.num_attention_heads, d.num_key_value_heads, d.head_dim
-        pt = self.cache.page_tables[seq]
-        for l, lw in enumerate(w.layers):
-            pages = self.cache.layer(l)
-            ops.gemv(self.h, lw.qkv_w, self.q_buf, norm_weight=lw.in_norm, eps=d.rms_norm_eps, mode=ops.GEMV_QKV_ROPE,
-                     n_heads=nh, n_kv_heads=nkv, head_dim=hd, cos_tab=self.cos, sin_tab=self.sin, pos=self.pos, kv_pages=pages,
-                     page_table=pt, page_size=PAGE_SIZE)
-            ops.attention_decode(self.q_buf, self.attn_buf, pages, pt, PAGE_SIZE, self.pos, nh, nkv, hd, self.scale)
-            ops.gemv(self.attn_buf, lw.o_w, self.h, residual=self.h, mode=ops.GEMV_PLAIN)
-            ops.gemv(self.h, lw.gateup_w, self.act_buf, norm_weight=lw.post_norm, eps=d.rms_norm_eps, mode=ops.GEMV_SWIGLU)
-            ops.gemv(self.act_buf, lw.down_w, self.h, residual=self.h, mode=ops.GEMV_PLAIN)
-        ops.lm_head_argmax(self.h, w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
-                           embed_table=w.embed, next_x=self.h, logits_out=logits_out)
+        ops.llama_decode_step(self.h, self._layer_array, d.num_hidden_layers, self.q_buf, self.attn_buf, self.act_buf, d, self.cos,
+                              self.sin, self.pos, self.cache.page_tables[seq], PAGE_SIZE, w.norm, w.lm_head, w.embed, self.lm_ws,
+                              self.out_ids, self.step, logits_out)
 
     def _ensure_graph(self, seq: int) -> None:
         if self._graph is not None:

@@ -41,6 +41,7 @@ class VisionTower:
             raise ValueError(f"need {self.n_layers} vision layers, weights hold {len(w.layers)}")
         self.is_loaded = True
         self.image_processor = image_processor
+        self._layer_array = ops.make_siglip_layer_array(w.layers[: self.n_layers])  # one C call runs the whole stack
         # builder.py:190-192 records the special token ids here
         self.config = SimpleNamespace(llm_mask_token_id=cfg.llm_mask_token_id, llm_depth_token_id=cfg.llm_depth_token_id,
                                       hidden_size=self.vc.hidden_size, image_size=self.vc.image_size,
@@ -76,16 +77,7 @@ class VisionTower:
         N, T, D, nh, hd = images.shape[0], vc.grid ** 2, vc.hidden_size, vc.num_attention_heads, vc.head_dim
         a = ops.patchify(images, vc.patch_size, patch_ldk(vc.patch_size))
         x = ops.gemm(a, w.patch_w, bias=w.patch_b, residual=w.pos_emb, epilogue=ops.EPI_BIAS_RESIDUAL, res_row_mod=T)
-        scale = hd ** -0.5
-        for i in range(self.n_layers):
-            lw = w.layers[i]
-            h = ops.layernorm(x, lw.ln1_w, lw.ln1_b, vc.layer_norm_eps)
-            qkv = ops.gemm(h, lw.qkv_w, bias=lw.qkv_b, epilogue=ops.EPI_BIAS)
-            o = ops.attention_prefill(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], N, T, nh, nh, hd, scale, causal=False)
-            x = ops.gemm(o, lw.out_w, bias=lw.out_b, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
-            h = ops.layernorm(x, lw.ln2_w, lw.ln2_b, vc.layer_norm_eps, out=h)
-            h1 = ops.gemm(h, lw.fc1_w, bias=lw.fc1_b, epilogue=ops.EPI_BIAS_GELU_TANH)
-            x = ops.gemm(h1, lw.fc2_w, bias=lw.fc2_b, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)
+        ops.siglip_layers(x, self._layer_array, self.n_layers, N, T, D, nh, vc.intermediate_size, vc.layer_norm_eps)
         return x.view(N, T, D)
 
     __call__ = forward

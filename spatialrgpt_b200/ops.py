@@ -294,3 +294,73 @@ def argmax_f32(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(rows, dtype=torch.int64, device=x.device)
     check(_lib.load().srgpt_argmax_f32(_p(x), rows, cols, _p(out), _stream()), "srgpt_argmax_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ composite stacks
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n - 1  # check() adds 1
+
+
+def make_siglip_layer_array(layers):
+    """ctypes array of srgpt_siglip_layer_weights over a list of VisionLayerW (keeps no tensor alive: the caller does)."""
+    arr = (_lib.SiglipLayerWeights * len(layers))()
+    for i, lw in enumerate(layers):
+        for name in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"):
+            setattr(arr[i], name, getattr(lw, name).data_ptr())
+    return arr
+
+
+def make_llama_layer_array(layers, kv_pages_per_layer):
+    arr = (_lib.LlamaLayerWeights * len(layers))()
+    for i, lw in enumerate(layers):
+        for name in ("in_norm", "qkv_w", "o_w", "post_norm", "gateup_w", "down_w"):
+            setattr(arr[i], name, getattr(lw, name).data_ptr())
+        arr[i].kv_pages = kv_pages_per_layer[i].data_ptr()
+    return arr
+
+
+def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: int, D: int, heads: int, I: int, eps: float) -> torch.Tensor:
+    """n_layers SigLIP encoder layers in place on x [n_img*T, D]."""
+    _need(x, BF16, "siglip_layers.x")
+    M = n_img * T
+    dev = x.device
+    ws_h = torch.empty((M, D), dtype=BF16, device=dev)
+    ws_qkv = torch.empty((M, 3 * D), dtype=BF16, device=dev)
+    ws_attn = torch.empty((M, D), dtype=BF16, device=dev)
+    ws_mlp = torch.empty((M, I), dtype=BF16, device=dev)
+    import ctypes
+    check(_lib.load().srgpt_siglip_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
+                                               _p(ws_attn), _p(ws_mlp), n_img, T, D, heads, I, eps, _stream()), "srgpt_siglip_layers_bf16")
+    _count(7 * n_layers)
+    return x
+
+
+def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos, sin, start_pos, page_table, page_size: int) -> torch.Tensor:
+    """All decoder layers over one prompt x [S, H] in place (K/V appended to the paged cache)."""
+    _need(x, BF16, "llama_prefill_layers.x")
+    S, H = x.shape
+    nh, nkv, hd, I = dims.num_attention_heads, dims.num_key_value_heads, dims.head_dim, dims.intermediate_size
+    dev = x.device
+    ws_h = torch.empty((S, H), dtype=BF16, device=dev)
+    ws_qkv = torch.empty((S, (nh + 2 * nkv) * hd), dtype=BF16, device=dev)
+    ws_attn = torch.empty((S, nh * hd), dtype=BF16, device=dev)
+    ws_act = torch.empty((S, I), dtype=BF16, device=dev)
+    import ctypes
+    check(_lib.load().srgpt_llama_prefill_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
+                                                      _p(ws_attn), _p(ws_act), S, H, nh, nkv, hd, I, dims.rms_norm_eps, _p(cos), _p(sin),
+                                                      _p(start_pos), _p(page_table), page_size, _stream()), "srgpt_llama_prefill_layers_bf16")
+    _count(8 * n_layers)
+    return x
+
+
+def llama_decode_step(h, layer_array, n_layers: int, q_buf, attn_buf, act_buf, dims, cos, sin, pos, page_table, page_size: int,
+                      final_norm, lm_head, embed, lm_ws, out_ids, step, logits_out=None) -> None:
+    import ctypes
+    nh, nkv, hd, I = dims.num_attention_heads, dims.num_key_value_heads, dims.head_dim, dims.intermediate_size
+    check(_lib.load().srgpt_llama_decode_step_bf16(_p(h), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(q_buf), _p(attn_buf),
+                                                   _p(act_buf), dims.hidden_size, nh, nkv, hd, I, dims.rms_norm_eps, _p(cos), _p(sin),
+                                                   _p(pos), _p(page_table), page_size, _p(final_norm), _p(lm_head), dims.vocab_size,
+                                                   _p(embed), _p(lm_ws), _p(logits_out), _p(out_ids), _p(step), _stream()),
+          "srgpt_llama_decode_step_bf16")
+    _count(5 * n_layers + 2)
