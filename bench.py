@@ -133,6 +133,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -247,7 +248,7 @@ def run_ours(args):
         "e2e": {"value": round(n_tok_e2e / (ms_e2e / 1e3), 2), "unit": UNIT,
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in (h_ids, h_img, h_dep, h_msk))),
                 "d2h_bytes_per_step": NEW_TOKENS * 8, "ms_per_step": round(ms_e2e / args.steps, 3)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * world,  # every rank launches the same kernels (replicas)
         "prefill": {"ttft_ms": round(ttft_ms, 3), "algorithmic_tflop": round(nums["flops_ttft"] / 1e12, 3),
                     "tflops": round(nums["flops_ttft"] / ttft_ms / 1e9, 1), "peak_tflops": tensor_peak,
                     "frac_tensor": round(nums["flops_ttft"] / ttft_ms / 1e9 / tensor_peak, 4),

@@ -16,6 +16,8 @@
 //   * the pair is chosen so the fused epilogue is warp-local: (gate_i, up_i) for SwiGLU, (d, d + hd/2)
 //     of one head for RoPE + KV-cache append, two vocabulary rows for lm_head + argmax.
 // Rounding points follow the reference's bf16 torch ops (modeling_llama.py:429-431,186-191,221,668,682).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "srgpt_b200.h"
 
@@ -135,29 +137,36 @@ __device__ __forceinline__ void pair_rows(const Params& p, int pi, int& r0, int&
   }
 }
 
-template <int MODE>
+// KS = warps sharing one row pair (K split): 1 for K <= 8192; 2 for the long rows of down_proj (K = 14336), where
+// 2048 warps x 4 KB in flight could not cover the HBM latency-bandwidth product (0.58 waves, ncu) — twice the warps,
+// half the row each, partial sums combined through shared memory.
+template <int MODE, int KS>
 __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float red[32];
   __shared__ float sv[WARPS];
   __shared__ int si[WARPS];
+  __shared__ float spart[WARPS][2];
   bf16* sx = reinterpret_cast<bf16*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   trace_mark(p.trace, 0);
   const int npairs = (MODE == MODE_LM) ? ((p.N + 1) >> 1) : (p.N >> 1);
-  const int pi = blockIdx.x * WARPS + warp;
+  const int pi = blockIdx.x * (WARPS / KS) + warp / KS;
+  const int kpart = warp % KS;
   const bool active = pi < npairs;
   int r0 = 0, r1 = 0;
   if (active) pair_rows<MODE>(p, pi, r0, r1);
   const uint4* p0 = reinterpret_cast<const uint4*>(p.W + (size_t)r0 * p.ldw);
   const uint4* p1 = reinterpret_cast<const uint4*>(p.W + (size_t)r1 * p.ldw);
   const uint4* px = reinterpret_cast<const uint4*>(sx);
-  const int nchunk = p.K >> 3;
+  const int nchunk_all = p.K >> 3;
+  const int cbeg = kpart * (nchunk_all / KS);
+  const int nchunk = (kpart == KS - 1) ? nchunk_all : cbeg + nchunk_all / KS;  // this warp covers chunks [cbeg, nchunk)
 
   // ---- first 8 loads per lane: weights do not depend on the previous kernel
   uint4 u0[4], u1[4];
-  int c = lane;
+  int c = cbeg + lane;
   const bool first_full = active && (c + 96 < nchunk);
   if (first_full) {
 #pragma unroll
@@ -168,12 +177,12 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   }
   // norm weights are static too: fetch them before the wait when a thread owns at most 2 chunks of x
   uint4 nw_pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-  const bool nw_pre_valid = (p.norm_weight != nullptr) && (nchunk <= 2 * THREADS);
+  const bool nw_pre_valid = (p.norm_weight != nullptr) && (nchunk_all <= 2 * THREADS);
   if (nw_pre_valid) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int cc = threadIdx.x + k * THREADS;
-      if (cc < nchunk) nw_pre[k] = reinterpret_cast<const uint4*>(p.norm_weight)[cc];
+      if (cc < nchunk_all) nw_pre[k] = reinterpret_cast<const uint4*>(p.norm_weight)[cc];
     }
   }
   pdl_launch_dependents();
@@ -217,10 +226,18 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   }
   a0 = warp_sum(a0);
   a1 = warp_sum(a1);
+  if (KS > 1) {  // combine the K parts of a pair (fixed order: deterministic)
+    if (lane == 0) { spart[warp][0] = a0; spart[warp][1] = a1; }
+    __syncthreads();
+    if (kpart == 0) {
+#pragma unroll
+      for (int k = 1; k < KS; ++k) { a0 += spart[warp + k][0]; a1 += spart[warp + k][1]; }
+    }
+  }
 
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  if (active && lane == 0) {
+  if (active && lane == 0 && kpart == 0) {
     if (MODE == SRGPT_GEMV_PLAIN) {
       float y0 = bf16_round(a0), y1 = bf16_round(a1);
       if (p.residual != nullptr) {
@@ -321,7 +338,7 @@ lm_head_finalize_kernel(const float* __restrict__ part_val, const int* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static int grid_for(int npairs) { return ceil_div(npairs, WARPS); }
+static int grid_for(int npairs, int ks = 1) { return ceil_div(npairs, WARPS / ks); }
 
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, int smem, cudaStream_t st) {
   cfg = {};
@@ -335,21 +352,32 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int g
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
 }
 
-template <int MODE>
-static int launch(const Params& p, int npairs, cudaStream_t st) {
+template <int MODE, int KS>
+static int launch_ks(const Params& p, int npairs, cudaStream_t st) {
   const int smem = p.K * 2;
   static int configured_smem = 0;
   if (smem > 48 * 1024 && smem > configured_smem) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  pdl_config(cfg, attr, grid_for(npairs), THREADS, smem, st);
+  pdl_config(cfg, attr, grid_for(npairs, KS), THREADS, smem, st);
   Params q = p;
   q.trace = trace_next_slot();
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE>, q));
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, KS>, q));
   return SRGPT_OK;
+}
+
+template <int MODE>
+static int launch(const Params& p, int npairs, cudaStream_t st) {
+  static const int force = [] {
+    const char* v = getenv("SRGPT_GEMV_KS");
+    return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
+  }();
+  const bool split = force ? (force == 2) : (p.K > 8192);
+  if (MODE == SRGPT_GEMV_PLAIN && split) return launch_ks<MODE, 2>(p, npairs, st);
+  return launch_ks<MODE, 1>(p, npairs, st);
 }
 
 }  // namespace gemv
