@@ -82,21 +82,18 @@ int srgpt_splice_rows_bf16(const void* src0, const void* src1, const void* src2,
 /* ---- region extractor HBM kernels (region.cu) -------------------------------------------------
  * MaskPooling weights (base_extractor.py:52-72): bilinear (align_corners=False, no antialias)
  * resample of masks [n_img, M, IH, IW] to the feature grid (side x side), cast to bf16, divide by
- * bf16(sum + 1e-8).  Feature-row order: order = 0 row-major (y*side+x); order = 2 the 2-level 2x2-nested
- * order the deconv GEMMs produce (see DESIGN.md "hres layout").  rscale = (float)(1.0 / scale_factor)
- * exactly as ATen computes it.  Outputs:
- *   w  (may be NULL): [n_img, M, side*side] bf16 — the reference's `mask / denorm` layout;
- *   wt              : [n_img, ceil(M/8), side*side, 8] bf16 — the 8 weights of a feature row as one 16-byte
- *                     vector (zero for m >= M); this is what srgpt_mask_pool_bf16 streams.
- * workspace: srgpt_mask_weights_workspace(n_img, M, side) bytes. */
+ * bf16(sum + 1e-8).  w: [n_img, M, side*side] bf16 (the reference's `mask / denorm`) in the feature
+ * tensor's row order: order = 0 row-major (y*side+x); order = 2 the 2-level 2x2-nested order the deconv
+ * GEMMs produce (see DESIGN.md "hres layout").  rscale = (float)(1.0 / scale_factor) exactly as ATen
+ * computes it.  workspace: srgpt_mask_weights_workspace(n_img, M, side) bytes. */
 long long srgpt_mask_weights_workspace(int n_img, int M, int side);
-int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* wt, void* workspace, int n_img, int M, int IH,
-                       int IW, int side, float rscale, int order, void* stream);
-/* Mask pooling proper (base_extractor.py:74-78): out[i,m,:] = sum_l w[i,m,l] * x[i,l,:].
- * x: [n_img, L, C] bf16 streamed once; wt: the transposed weights above; workspace: fp32 partials,
- * srgpt_mask_pool_workspace() bytes. */
+int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW,
+                       int side, float rscale, int order, void* stream);
+/* Mask pooling proper (base_extractor.py:74-78): out[i,m,:] = sum_l w[i,m,l] * x[i,l,:] — bf16 tensor-core
+ * product with fp32 accumulation like the reference's einsum.  x: [n_img, L, C] bf16 streamed once;
+ * workspace: fp32 partials, srgpt_mask_pool_workspace() bytes. */
 long long srgpt_mask_pool_workspace(int n_img, int M, int L, int C);
-int srgpt_mask_pool_bf16(const void* x, const void* wt, void* out, void* workspace, int n_img, int M, int L, int C,
+int srgpt_mask_pool_bf16(const void* x, const void* w, void* out, void* workspace, int n_img, int M, int L, int C,
                          void* stream);
 /* AdaptiveAvgPool2d(out_side) over the (side x side) feature map (base_extractor.py:123,145).
  * x: [n_img, side*side, C] in `order` (as above) -> y: [n_img, out_side*out_side, C] row-major. */

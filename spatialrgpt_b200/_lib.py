@@ -36,7 +36,7 @@ SIGNATURES = {
     "srgpt_patchify_bf16": (ci, [vp, ci, vp, ci, ci, ci, ci, vp]),
     "srgpt_splice_rows_bf16": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
     "srgpt_mask_weights_workspace": (cll, [ci, ci, ci]),
-    "srgpt_mask_weights": (ci, [vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, vp]),
+    "srgpt_mask_weights": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, ci, vp]),
     "srgpt_mask_pool_workspace": (cll, [ci, ci, ci, ci]),
     "srgpt_mask_pool_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "srgpt_adaptive_avgpool_bf16": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),

@@ -137,9 +137,7 @@ __device__ __forceinline__ void pair_rows(const Params& p, int pi, int& r0, int&
   }
 }
 
-// KS = warps sharing one row pair (K split): 1 for K <= 8192; 2 for the long rows of down_proj (K = 14336), where
-// 2048 warps x 4 KB in flight could not cover the HBM latency-bandwidth product (0.58 waves, ncu) — twice the warps,
-// half the row each, partial sums combined through shared memory.
+// KS = warps sharing one row pair (K split).  KS = 2 is an experiment knob (SRGPT_GEMV_KS=2): see launch().
 template <int MODE, int KS>
 __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -375,7 +373,9 @@ static int launch(const Params& p, int npairs, cudaStream_t st) {
     const char* v = getenv("SRGPT_GEMV_KS");
     return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
   }();
-  const bool split = force ? (force == 2) : (p.K > 8192);
+  // measured (profiles/r01_decode_trace_ksplit.txt): splitting down_proj's K=14336 rows over 2 warps made the kernel
+  // SLOWER (exposed 20.3 -> 23.9 us: twice the CTAs each re-staging the 28 KB x vector), so it stays opt-in
+  const bool split = force == 2;
   if (MODE == SRGPT_GEMV_PLAIN && split) return launch_ks<MODE, 2>(p, npairs, st);
   return launch_ks<MODE, 1>(p, npairs, st);
 }

@@ -69,11 +69,8 @@ mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __res
   if (threadIdx.x == 0) psum[((size_t)img * M + m) * MW_SPLITS + split] = total;
 }
 
-// `w` (optional) keeps the reference layout [img][M][L]; `wt` is what mask_pool streams: [img][ceil(M/8)][L][8]
-// bf16, i.e. the 8 weights of a feature row are one 16-byte vector (zero for m >= M).
 __global__ void __launch_bounds__(256)
-mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, bf16* __restrict__ wt, const float* __restrict__ psum,
-                      int M, int L) {
+mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, const float* __restrict__ psum, int M, int L) {
   const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
   const float* ps = psum + ((size_t)img * M + m) * MW_SPLITS;
   float total = 0.f;
@@ -81,137 +78,131 @@ mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, bf16* __
   for (int i = 0; i < MW_SPLITS; ++i) total += ps[i];
   const float denorm = bf16_round(bf16_round(total) + 1e-8f);
   const bf16* src = v + ((size_t)img * M + m) * L;
-  const int mt_tiles = (M + 7) >> 3;
-  bf16* dst_t = wt + (((size_t)img * mt_tiles + (m >> 3)) * L) * 8 + (m & 7);
-  bf16* dst = (w != nullptr) ? w + ((size_t)img * M + m) * L : nullptr;
+  bf16* dst = w + ((size_t)img * M + m) * L;
   const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
   const int l_end = min(L, (split + 1) * per);
   // rows are a permutation of l; normalising the contiguous range [split*per, l_end) of ROWS covers every row once
-  for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x) {
-    const bf16 q = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(src[r]), denorm));
-    dst_t[(size_t)r * 8] = q;
-    if (dst != nullptr) dst[r] = q;
-  }
+  for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x)
+    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(src[r]), denorm));
 }
 
 // ---------------------------------------------------------------------------------------------
-// mask pooling: out[img,m,c] = sum_l w[img,m,l] * x[img,l,c]
-// CTA = 16 channel-threads (8 channels each = 128 channels, one 256-byte row segment) x 16 row lanes.
-// grid = (row chunks R, channel chunks Q, images).  fp32 partials [img][R][M][C], then a tiny reduce.
-// Inner loop per 16-byte feature load: 2 x LDS.128 (the row's 8 mask weights, broadcast), 8 ALU ops to widen
-// bf16 -> fp32 pairs, 32 packed FFMA2 (fma.rn.f32x2, new on sm_100) instead of 64 FFMA; rows whose 8 weights
-// are all zero (most rows of a region mask) are skipped.
+// mask pooling: out[img,m,c] = sum_l w[img,m,l] * x[img,l,c]   (torch.einsum("lc,ml->mc"), base_extractor.py:74-78)
+//
+// The reference runs this einsum as a bf16 tensor-core GEMM with fp32 accumulation; so do we, but shaped for what
+// it is — a [<=16 x L] x [L x C] product whose only cost is streaming x once:
+//   * CTA = 128 channels x rows_per_cta rows; features go global -> shared with cp.async (16-byte chunks, 4-stage
+//     ring, ~50 KB in flight per CTA, no registers involved), 64 rows per stage;
+//   * each of the 8 warps owns 16 channels: per 16 rows one ldmatrix.x4 of the mask weights (A, [m][l] row-major),
+//     one ldmatrix.x4.trans of the features (B) and two mma.sync.m16n8k16 (bf16 x bf16 -> fp32);
+//   * up to 16 masks per pass; fp32 partials [img][R][M][C] + a tiny deterministic reduce.
+// History (profiles/): scalar FFMA 0.11-0.20 of HBM peak, packed FFMA2 + row skipping 0.23-0.49, this version: see
+// DESIGN.md.  ~5 instructions per 512 bytes of features per warp instead of ~90.
 // ---------------------------------------------------------------------------------------------
 constexpr int MP_THREADS = 256;
-constexpr int MP_CH = 128;   // channels per CTA
-constexpr int MP_RL = 16;    // row lanes
-constexpr int MP_MT = 8;     // masks per pass
-constexpr int MP_MAX_ROWS = 512;  // rows per CTA
+constexpr int MP_CH = 128;        // channels per CTA
+constexpr int MP_MT = 16;         // masks per pass (MMA M)
+constexpr int MP_SROWS = 64;      // feature rows per pipeline stage
+constexpr int MP_NST = 4;         // pipeline stages
+constexpr int MP_XLD = MP_CH + 8; // smem row stride of the feature tile (elements): +16 B -> conflict-free ldmatrix
+constexpr int MP_WLD = MP_SROWS + 8;
+constexpr int MP_MAX_ROWS = 1024; // rows per CTA upper bound (planning only)
+constexpr int MP_STAGE_X = MP_SROWS * MP_XLD;  // elements
+constexpr int MP_STAGE_W = MP_MT * MP_WLD;
+constexpr int MP_SMEM_BYTES = MP_NST * (MP_STAGE_X + MP_STAGE_W) * 2;
 
-__device__ __forceinline__ void ffma2(float2& d, const float2& a, float w) {
-  // d += a * {w, w}
-  unsigned long long dd, aa, ww;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(ww));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
-}
-
-__device__ __forceinline__ void mp_accumulate(float2 (*acc)[4], const uint4& u, const float4& wa, const float4& wb) {
-  float2 f[4];
-  f[0] = make_float2(bf16_lo(u.x), bf16_hi(u.x));
-  f[1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
-  f[2] = make_float2(bf16_lo(u.z), bf16_hi(u.z));
-  f[3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
-  const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-  for (int mm = 0; mm < MP_MT; ++mm)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) ffma2(acc[mm][t], f[t], wv[mm]);
+__device__ __forceinline__ uint32_t mp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mp_cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(mp_smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 
 __global__ void __launch_bounds__(MP_THREADS, 2)
-mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wt, float* __restrict__ partial, int M, int L, int C,
+mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
                  int rows_per_cta, int R) {
-  // cross-warp reduction buffer [warps][MP_MT][MP_CH/8][8 (+1 pad)]
-  __shared__ float sred[MP_THREADS / 32][MP_MT][MP_CH / 8][9];
+  extern __shared__ __align__(16) uint8_t mp_smem[];
+  bf16* sx = reinterpret_cast<bf16*>(mp_smem);                     // [NST][SROWS][XLD]
+  bf16* sw = sx + MP_NST * MP_STAGE_X;                              // [NST][MT][WLD]
   const int img = blockIdx.z;
-  const int cthr = threadIdx.x & 15, rl = threadIdx.x >> 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.y * MP_CH + cthr * 8;
-  const bool c_ok = c0 < C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cbase = blockIdx.y * MP_CH;
   const int l0 = blockIdx.x * rows_per_cta;
   const int nrows = min(rows_per_cta, L - l0);
-  const bf16* xb = x + ((size_t)img * L + l0) * C + c0;
-  const int mt_tiles = (M + MP_MT - 1) / MP_MT;
+  const int nstages = (nrows + MP_SROWS - 1) / MP_SROWS;
+  const bf16* xb = x + ((size_t)img * L + l0) * C;
+  const int lr = lane & 7, lmat = lane >> 3, g = lane >> 2, t4 = lane & 3;
 
-  for (int mtile = 0; mtile < mt_tiles; ++mtile) {
-    const int m0 = mtile * MP_MT;
+  for (int m0 = 0; m0 < M; m0 += MP_MT) {
     const int mt = min(MP_MT, M - m0);
-    // the 8 weights of row r: one 16-byte vector, identical for the 16 channel-threads of a row (L1 broadcast)
-    const uint4* wrow = reinterpret_cast<const uint4*>(wt + (((size_t)img * mt_tiles + mtile) * L + l0) * 8);
-    float2 acc[MP_MT][4];
-#pragma unroll
-    for (int mm = 0; mm < MP_MT; ++mm)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) acc[mm][t] = make_float2(0.f, 0.f);
+    const bf16* wb = w + ((size_t)img * M + m0) * L + l0;
 
-    if (c_ok) {
-      int r = rl;
-      // 8 feature + 8 weight 16-byte loads in flight per thread; no prologue, the first loads leave at kernel start
-      for (; r + 7 * MP_RL < nrows; r += 8 * MP_RL) {
-        uint4 u[8], wv[8];
+    auto issue = [&](int st) {  // stage `st` of this CTA's rows -> ring slot st % NST (zero-filled outside the tensor)
+      bf16* dx = sx + (st % MP_NST) * MP_STAGE_X;
+      bf16* dw = sw + (st % MP_NST) * MP_STAGE_W;
+      const int r0 = st * MP_SROWS;
+      for (int i = threadIdx.x; i < MP_SROWS * (MP_CH / 8); i += MP_THREADS) {
+        const int r = i >> 4, ch = (i & 15) * 8;
+        const bool ok = (r0 + r < nrows) && (cbase + ch < C);
+        const bf16* src = ok ? xb + (size_t)(r0 + r) * C + cbase + ch : x;
+        mp_cp_async16(dx + r * MP_XLD + ch, src, ok ? 16 : 0);
+      }
+      if (threadIdx.x < MP_MT * (MP_SROWS / 8)) {  // 16 masks x 8 chunks of 8 rows
+        const int mm = threadIdx.x >> 3, rc = (threadIdx.x & 7) * 8;
+        // a 16-byte chunk of weights is used only when all 8 rows are inside the CTA's range and 16-byte aligned
+        const bool ok = (mm < mt) && (r0 + rc + 8 <= nrows) && ((((size_t)(wb - w) + (size_t)mm * L + r0 + rc) & 7) == 0);
+        if (ok) {
+          mp_cp_async16(dw + mm * MP_WLD + rc, wb + (size_t)mm * L + r0 + rc, 16);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          u[k] = ld_stream16(xb + (size_t)(r + k * MP_RL) * C);
-          wv[k] = __ldg(wrow + r + k * MP_RL);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if ((wv[k].x | wv[k].y | wv[k].z | wv[k].w) != 0u) {  // rows outside every region are skipped
-            const float4 wa = make_float4(bf16_lo(wv[k].x), bf16_hi(wv[k].x), bf16_lo(wv[k].y), bf16_hi(wv[k].y));
-            const float4 wb = make_float4(bf16_lo(wv[k].z), bf16_hi(wv[k].z), bf16_lo(wv[k].w), bf16_hi(wv[k].w));
-            mp_accumulate(acc, u[k], wa, wb);
-          }
+          for (int k = 0; k < 8; ++k)
+            dw[mm * MP_WLD + rc + k] = (mm < mt && r0 + rc + k < nrows) ? wb[(size_t)mm * L + r0 + rc + k] : __float2bfloat16_rn(0.f);
         }
       }
-      for (; r < nrows; r += MP_RL) {
-        const uint4 u = ld_stream16(xb + (size_t)r * C);
-        const uint4 wq = __ldg(wrow + r);
-        const float4 wa = make_float4(bf16_lo(wq.x), bf16_hi(wq.x), bf16_lo(wq.y), bf16_hi(wq.y));
-        const float4 wb = make_float4(bf16_lo(wq.z), bf16_hi(wq.z), bf16_lo(wq.w), bf16_hi(wq.w));
-        mp_accumulate(acc, u, wa, wb);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    __syncthreads();  // ring is free (previous pass finished)
+    for (int st = 0; st < MP_NST - 1; ++st) {
+      if (st < nstages) issue(st);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float acc[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+
+    for (int st = 0; st < nstages; ++st) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(MP_NST - 2) : "memory");
+      __syncthreads();  // stage st visible to every warp; slot (st-1) % NST is free again
+      if (st + MP_NST - 1 < nstages) issue(st + MP_NST - 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      const bf16* tx = sx + (st % MP_NST) * MP_STAGE_X;
+      const bf16* tw = sw + (st % MP_NST) * MP_STAGE_W;
+#pragma unroll
+      for (int kk = 0; kk < MP_SROWS / 16; ++kk) {
+        uint32_t a[4], b[4];
+        // A (weights [m][l]): matrices (m0..7,k0..7) (m8..15,k0..7) (m0..7,k8..15) (m8..15,k8..15)
+        const bf16* ap = tw + (lr + (lmat & 1) * 8) * MP_WLD + kk * 16 + (lmat >> 1) * 8;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(mp_smem_u32(ap)));
+        // B (features [l][c], transposed on load): (k0..7,c0..7) (k8..15,c0..7) (k0..7,c8..15) (k8..15,c8..15)
+        const bf16* bp = tx + (kk * 16 + lr + (lmat & 1) * 8) * MP_XLD + warp * 16 + (lmat >> 1) * 8;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(mp_smem_u32(bp)));
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[nb][0]), "+f"(acc[nb][1]), "+f"(acc[nb][2]), "+f"(acc[nb][3])
+                       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[2 * nb]), "r"(b[2 * nb + 1]));
       }
     }
-    // reduce over the 16 row lanes: 2 lanes inside each warp (xor 16), then 8 warps via smem
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // accumulator fragment: c0,c1 -> (m = g, ch = 2*t4, +1); c2,c3 -> (m = g + 8, ...)
+    float* pb = partial + (((size_t)img * R + blockIdx.x) * M + m0) * C;
 #pragma unroll
-    for (int mm = 0; mm < MP_MT; ++mm)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        acc[mm][t].x += __shfl_xor_sync(0xffffffffu, acc[mm][t].x, 16);
-        acc[mm][t].y += __shfl_xor_sync(0xffffffffu, acc[mm][t].y, 16);
-      }
-    __syncthreads();  // previous pass finished reading sred
-    if (lane < 16) {
-#pragma unroll
-      for (int mm = 0; mm < MP_MT; ++mm)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          sred[warp][mm][cthr][2 * t] = acc[mm][t].x;
-          sred[warp][mm][cthr][2 * t + 1] = acc[mm][t].y;
-        }
-    }
-    __syncthreads();
-    // 8 masks x 128 channels = 1024 outputs, 256 threads -> 4 each
-    for (int i = threadIdx.x; i < MP_MT * MP_CH; i += MP_THREADS) {
-      const int mm = i / MP_CH, ch = i % MP_CH;
-      const int c = blockIdx.y * MP_CH + ch;
-      if (mm < mt && c < C) {
-        float s = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < MP_THREADS / 32; ++wv) s += sred[wv][mm][ch >> 3][ch & 7];
-        partial[(((size_t)img * R + blockIdx.x) * M + m0 + mm) * C + c] = s;
+    for (int nb = 0; nb < 2; ++nb) {
+      const int c = cbase + warp * 16 + nb * 8 + 2 * t4;
+      if (c < C) {
+        if (g < mt) { pb[(size_t)g * C + c] = acc[nb][0]; pb[(size_t)g * C + c + 1] = acc[nb][1]; }
+        if (g + 8 < mt) { pb[(size_t)(g + 8) * C + c] = acc[nb][2]; pb[(size_t)(g + 8) * C + c + 1] = acc[nb][3]; }
       }
     }
   }
@@ -241,11 +232,9 @@ static void mask_pool_plan(int n_img, int L, int C, int* R, int* rows_per_cta, i
   *Q = ceil_div(C, MP_CH);
   int want = ceil_div(2 * sm_count(), (*Q) * n_img);  // ~2 CTAs per SM
   if (want < 1) want = 1;
-  int rpc = ceil_div(L, want);
+  int rpc = ceil_div(ceil_div(L, want), MP_SROWS) * MP_SROWS;  // whole pipeline stages
   if (rpc > MP_MAX_ROWS) rpc = MP_MAX_ROWS;
-  if (rpc < MP_RL) rpc = MP_RL;
-  rpc = ceil_div(rpc, MP_RL) * MP_RL;
-  if (rpc > MP_MAX_ROWS) rpc = MP_MAX_ROWS;
+  if (rpc < MP_SROWS) rpc = MP_SROWS;
   *rows_per_cta = rpc;
   *R = ceil_div(L, rpc);
 }
@@ -344,25 +333,22 @@ extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_w
   return (long long)n_img * M * (MW_SPLITS * (long long)sizeof(float) + (long long)side * side * (long long)sizeof(bf16));
 }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* wt, void* workspace, int n_img, int M, int IH, int IW,
+extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW,
                                   int side, float rscale, int order, void* stream) {
-  SRGPT_CHECK_ARG(masks && wt && workspace && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
+  SRGPT_CHECK_ARG(masks && w && workspace && n_img > 0 && M > 0 && IH > 0 && IW > 0 && side > 0);
   SRGPT_CHECK_ARG(order == 0 || (order == 2 && (side % 4) == 0));
-  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(wt) & 15) == 0);
   dim3 grid(MW_SPLITS, M, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int L = side * side;
   // workspace: [n_img*M*MW_SPLITS] fp32 partial sums, then [n_img*M*L] bf16 un-normalised resampled masks
   float* psum = reinterpret_cast<float*>(workspace);
   bf16* v = reinterpret_cast<bf16*>(psum + (size_t)n_img * M * MW_SPLITS);
-  const int mt_tiles = (M + 7) / 8;
-  if ((M & 7) != 0) SRGPT_CHECK_CUDA(cudaMemsetAsync(wt, 0, (size_t)n_img * mt_tiles * L * 8 * sizeof(bf16), st));  // zero rows m >= M
   if (mask_is_bf16)
     mask_taps_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(masks), v, psum, M, IH, IW, side, rscale, order);
   else
     mask_taps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), v, psum, M, IH, IW, side, rscale, order);
   SRGPT_CHECK_LAUNCH();
-  mask_normalise_kernel<<<grid, 256, 0, st>>>(v, reinterpret_cast<bf16*>(w), reinterpret_cast<bf16*>(wt), psum, M, L);
+  mask_normalise_kernel<<<grid, 256, 0, st>>>(v, reinterpret_cast<bf16*>(w), psum, M, L);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }
@@ -381,9 +367,14 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const
   int R, rpc, Q;
   mask_pool_plan(n_img, L, C, &R, &rpc, &Q);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool configured = false;
+  if (!configured) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(mask_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
+    configured = true;
+  }
   dim3 grid(R, Q, n_img);
-  mask_pool_kernel<<<grid, MP_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
-                                                reinterpret_cast<float*>(workspace), M, L, C, rpc, R);
+  mask_pool_kernel<<<grid, MP_THREADS, MP_SMEM_BYTES, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
+                                                            reinterpret_cast<float*>(workspace), M, L, C, rpc, R);
   SRGPT_CHECK_LAUNCH();
   mask_pool_reduce_kernel<<<dim3(ceil_div(C, 256), M, n_img), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), reinterpret_cast<bf16*>(out), M, C, R);
   SRGPT_CHECK_LAUNCH();

@@ -167,13 +167,10 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
         raise SrgptError(f"mask_weights: floor({IH}x{IW} * {scale_factor}) != {side} (non-square masks are unsupported)")
     rscale = float(torch.tensor(1.0 / scale_factor, dtype=torch.float64).to(torch.float32))
     lib = _lib.load()
-    L = side * side
-    w = torch.empty((n, M, L), dtype=BF16, device=masks.device)
-    wt = torch.empty((n, (M + 7) // 8, L, 8), dtype=BF16, device=masks.device)
+    w = torch.empty((n, M, side * side), dtype=BF16, device=masks.device)
     ws = torch.empty(lib.srgpt_mask_weights_workspace(n, M, side), dtype=torch.uint8, device=masks.device)
-    check(lib.srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), _p(wt), _p(ws), n, M, IH, IW, side, rscale,
-                                 order, _stream()), "srgpt_mask_weights")
-    w.wt = wt  # kernel-layout copy consumed by mask_pool (the reference-layout `w` is for parity / API users)
+    check(lib.srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), _p(ws), n, M, IH, IW, side, rscale, order,
+                                 _stream()), "srgpt_mask_weights")
     return w
 
 
@@ -186,14 +183,11 @@ def mask_pool(x: torch.Tensor, w: torch.Tensor, workspace: Optional[torch.Tensor
     n2, M, L2 = w.shape
     if n != n2 or L != L2:
         raise SrgptError("mask_pool: shape mismatch between x and w")
-    wt = getattr(w, "wt", None)
-    if wt is None:
-        raise SrgptError("mask_pool: `w` must come from ops.mask_weights() (it carries the kernel-layout copy `w.wt`)")
     need = _lib.load().srgpt_mask_pool_workspace(n, M, L, Cc)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
     out = torch.empty((n, M, Cc), dtype=BF16, device=x.device)
-    check(_lib.load().srgpt_mask_pool_bf16(_p(x), _p(wt), _p(out), _p(workspace), n, M, L, Cc, _stream()), "srgpt_mask_pool_bf16")
+    check(_lib.load().srgpt_mask_pool_bf16(_p(x), _p(w), _p(out), _p(workspace), n, M, L, Cc, _stream()), "srgpt_mask_pool_bf16")
     return out
 
 
