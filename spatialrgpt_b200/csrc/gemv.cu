@@ -137,38 +137,39 @@ __device__ __forceinline__ void pair_rows(const Params& p, int pi, int& r0, int&
   }
 }
 
-// KS = warps sharing one row pair (K split).  KS = 2 is an experiment knob (SRGPT_GEMV_KS=2): see launch().
-template <int MODE, int KS>
-__global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p) {
+// PRE = number of 4-chunk batches (per row) requested BEFORE the dependency wait: 1 -> 8 loads per lane (3 CTAs/SM),
+// 2 -> 16 loads (2 CTAs/SM), 4 -> 32 loads = a whole K=4096 row pair per warp (1 CTA/SM).  The small matrices of a
+// layer (qkv 50 MB, o_proj 33 MB) run behind a kernel that leaves HBM idle (decode attention / the previous tail), so
+// the more of their weights is in flight before the dependency resolves, the less of them is exposed afterwards.
+template <int MODE, int PRE>
+__global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) decode_gemv_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float red[32];
   __shared__ float sv[WARPS];
   __shared__ int si[WARPS];
-  __shared__ float spart[WARPS][2];
   bf16* sx = reinterpret_cast<bf16*>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   trace_mark(p.trace, 0);
   const int npairs = (MODE == MODE_LM) ? ((p.N + 1) >> 1) : (p.N >> 1);
-  const int pi = blockIdx.x * (WARPS / KS) + warp / KS;
-  const int kpart = warp % KS;
+  const int pi = blockIdx.x * WARPS + warp;
   const bool active = pi < npairs;
   int r0 = 0, r1 = 0;
   if (active) pair_rows<MODE>(p, pi, r0, r1);
   const uint4* p0 = reinterpret_cast<const uint4*>(p.W + (size_t)r0 * p.ldw);
   const uint4* p1 = reinterpret_cast<const uint4*>(p.W + (size_t)r1 * p.ldw);
   const uint4* px = reinterpret_cast<const uint4*>(sx);
-  const int nchunk_all = p.K >> 3;
-  const int cbeg = kpart * (nchunk_all / KS);
-  const int nchunk = (kpart == KS - 1) ? nchunk_all : cbeg + nchunk_all / KS;  // this warp covers chunks [cbeg, nchunk)
+  const int nchunk = p.K >> 3;
+  const int nchunk_all = nchunk;
 
-  // ---- first 8 loads per lane: weights do not depend on the previous kernel
-  uint4 u0[4], u1[4];
-  int c = cbeg + lane;
-  const bool first_full = active && (c + 96 < nchunk);
+  // ---- first 8*PRE loads per lane: weights do not depend on the previous kernel
+  constexpr int NPRE = 4 * PRE;
+  uint4 u0[NPRE], u1[NPRE];
+  int c = lane;
+  const bool first_full = active && (c + 32 * (NPRE - 1) < nchunk);
   if (first_full) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NPRE; ++i) {
       u0[i] = ld_stream16(p0 + c + 32 * i);
       u1[i] = ld_stream16(p1 + c + 32 * i);
     }
@@ -193,13 +194,13 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   if (active) {
     if (first_full) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NPRE; ++i) {
         float xf[8];
         unpack8(px[c + 32 * i], xf);
         a0 += dot8(u0[i], xf);
         a1 += dot8(u1[i], xf);
       }
-      c += 128;
+      c += 32 * NPRE;
     }
     for (; c + 96 < nchunk; c += 128) {
 #pragma unroll
@@ -224,18 +225,9 @@ __global__ void __launch_bounds__(THREADS, 3) decode_gemv_kernel(const Params p)
   }
   a0 = warp_sum(a0);
   a1 = warp_sum(a1);
-  if (KS > 1) {  // combine the K parts of a pair (fixed order: deterministic)
-    if (lane == 0) { spart[warp][0] = a0; spart[warp][1] = a1; }
-    __syncthreads();
-    if (kpart == 0) {
-#pragma unroll
-      for (int k = 1; k < KS; ++k) { a0 += spart[warp + k][0]; a1 += spart[warp + k][1]; }
-    }
-  }
-
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  if (active && lane == 0 && kpart == 0) {
+  if (active && lane == 0) {
     if (MODE == SRGPT_GEMV_PLAIN) {
       float y0 = bf16_round(a0), y1 = bf16_round(a1);
       if (p.residual != nullptr) {
@@ -336,7 +328,7 @@ lm_head_finalize_kernel(const float* __restrict__ part_val, const int* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static int grid_for(int npairs, int ks = 1) { return ceil_div(npairs, WARPS / ks); }
+static int grid_for(int npairs) { return ceil_div(npairs, WARPS); }
 
 static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int block, int smem, cudaStream_t st) {
   cfg = {};
@@ -350,34 +342,36 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int g
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
 }
 
-template <int MODE, int KS>
-static int launch_ks(const Params& p, int npairs, cudaStream_t st) {
+template <int MODE, int PRE>
+static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
   const int smem = p.K * 2;
   static int configured_smem = 0;
   if (smem > 48 * 1024 && smem > configured_smem) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  pdl_config(cfg, attr, grid_for(npairs, KS), THREADS, smem, st);
+  pdl_config(cfg, attr, grid_for(npairs), THREADS, smem, st);
   Params q = p;
   q.trace = trace_next_slot();
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, KS>, q));
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, PRE>, q));
   return SRGPT_OK;
 }
 
+// Prefetch depth: deep for the small matrices (the whole matrix fits in the first wave's registers), shallow for the
+// big ones (gate/up already runs at the copy roofline with 3 CTAs/SM).  SRGPT_GEMV_PRE_SMALL overrides (1, 2 or 4).
 template <int MODE>
 static int launch(const Params& p, int npairs, cudaStream_t st) {
-  static const int force = [] {
-    const char* v = getenv("SRGPT_GEMV_KS");
-    return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
+  static const int pre_small = [] {
+    const char* v = getenv("SRGPT_GEMV_PRE_SMALL");
+    const int x = (v != nullptr && v[0] != 0) ? atoi(v) : 2;
+    return (x == 1 || x == 2 || x == 4) ? x : 2;
   }();
-  // measured (profiles/r01_decode_trace_ksplit.txt): splitting down_proj's K=14336 rows over 2 warps made the kernel
-  // SLOWER (exposed 20.3 -> 23.9 us: twice the CTAs each re-staging the 28 KB x vector), so it stays opt-in
-  const bool split = force == 2;
-  if (MODE == SRGPT_GEMV_PLAIN && split) return launch_ks<MODE, 2>(p, npairs, st);
-  return launch_ks<MODE, 1>(p, npairs, st);
+  const bool small = (MODE == SRGPT_GEMV_PLAIN || MODE == SRGPT_GEMV_QKV_ROPE) && ((size_t)p.N * p.K * 2 <= (size_t)64 << 20);
+  if (small && pre_small == 4 && (p.K >> 3) >= 512) return launch_pre<MODE, 4>(p, npairs, st);
+  if (small && pre_small >= 2 && (p.K >> 3) >= 256) return launch_pre<MODE, 2>(p, npairs, st);
+  return launch_pre<MODE, 1>(p, npairs, st);
 }
 
 }  // namespace gemv
