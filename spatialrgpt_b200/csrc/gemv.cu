@@ -359,14 +359,16 @@ static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
   return SRGPT_OK;
 }
 
-// Prefetch depth: deep for the small matrices (the whole matrix fits in the first wave's registers), shallow for the
-// big ones (gate/up already runs at the copy roofline with 3 CTAs/SM).  SRGPT_GEMV_PRE_SMALL overrides (1, 2 or 4).
+// Prefetch depth.  Measured on the in-graph timeline (profiles/r01_decode_trace_pre{1,2,4}.txt): deeper prefetch for the
+// small matrices (PRE 2 / 4) trims o_proj by ~0.9 us but costs occupancy (2 / 1 CTAs per SM), so the NEXT kernel can no
+// longer co-reside and start early: the step gets slower (2.732 / 2.746 / 2.833 ms).  Default 1; SRGPT_GEMV_PRE_SMALL
+// keeps the experiment reproducible.
 template <int MODE>
 static int launch(const Params& p, int npairs, cudaStream_t st) {
   static const int pre_small = [] {
     const char* v = getenv("SRGPT_GEMV_PRE_SMALL");
-    const int x = (v != nullptr && v[0] != 0) ? atoi(v) : 2;
-    return (x == 1 || x == 2 || x == 4) ? x : 2;
+    const int x = (v != nullptr && v[0] != 0) ? atoi(v) : 1;
+    return (x == 1 || x == 2 || x == 4) ? x : 1;
   }();
   const bool small = (MODE == SRGPT_GEMV_PLAIN || MODE == SRGPT_GEMV_QKV_ROPE) && ((size_t)p.N * p.K * 2 <= (size_t)64 << 20);
   if (small && pre_small == 4 && (p.K >> 3) >= 512) return launch_pre<MODE, 4>(p, npairs, st);
