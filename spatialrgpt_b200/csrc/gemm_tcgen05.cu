@@ -84,6 +84,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+// same copy delivered to the same shared-memory offset (and mbarrier offset) of every CTA in `cta_mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int x, int y, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -108,6 +125,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, but the arrive is delivered to the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -200,7 +222,12 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
   }
 }
 
-template <int EPI, int BN>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster own vertically adjacent 128-row tiles and SHARE
+// the B (weight) tile: each CTA fetches half of its rows and multicasts them into both CTAs' shared memory, so the bytes
+// pulled from L2 per CTA and k-block drop from 16+BN/8 KB... (A + B) to A + B/2 — the quantity that bounds this kernel.
+// A stage may be refilled only after BOTH CTAs' MMAs have read it, hence the multicast tcgen05.commit on the
+// empty barriers (count CL).
+template <int EPI, int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using C = Cfg<BN>;
@@ -221,15 +248,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  // work unit = CL vertically adjacent tiles x one n-tile; unit u -> m-unit u % tiles_mu, n-tile u / tiles_mu
+  const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const int tiles_mu = (tiles_m + CL - 1) / CL;
+  const int num_units = tiles_mu * tiles_n;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), CL);  // one tcgen05.commit per CTA sharing the B tile
     }
     for (int a = 0; a < ACC_BUFS; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
@@ -240,6 +271,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -247,16 +279,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM;
-        const int n0 = (tile / tiles_m) * BN;
+      for (int unit = cid; unit < num_units; unit += ncl) {
+        const int m0 = ((unit % tiles_mu) * CL + crank) * BM;
+        const int n0 = (unit / tiles_mu) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, STAGE_BYTES);
+          mbar_expect_tx(fb, STAGE_BYTES);  // own A tile + the whole B tile (one half from each CTA when CL == 2)
           uint8_t* sa = smem + stage * STAGE_BYTES;
           tma_load_2d(smem_u32(sa), &tmap_a, fb, kb * BK, m0);
-          tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &tmap_b, fb, kb * BK, n0);
+          if (CL == 2) {
+            constexpr int HALF = BN / 2;
+            tma_load_2d_mc(smem_u32(sa + A_STAGE_BYTES + crank * HALF * BK * 2), &tmap_b, fb, kb * BK, n0 + crank * HALF, (uint16_t)0x3);
+          } else {
+            tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &tmap_b, fb, kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -267,7 +304,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = cid; unit < num_units; unit += ncl) {
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -283,7 +320,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // advancing 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (>>4) address field
             umma_f16(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (in both CTAs that write into it when the B tile is shared)
+          if (CL == 2) umma_commit_mc(smem_u32(&empty_bar[stage]), (uint16_t)0x3);
+          else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator complete -> epilogue
@@ -297,9 +336,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
     const int chalf = (warp - 2) >> 2;  // 0: columns [0, BN/2), 1: columns [BN/2, BN)
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * BN;
+    for (int unit = cid; unit < num_units; unit += ncl) {
+      const int m0 = ((unit % tiles_mu) * CL + crank) * BM;
+      const int n0 = (unit / tiles_mu) * BN;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const int row = m0 + lg * 32 + lane;
@@ -364,6 +403,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -411,41 +451,59 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, 
   return SRGPT_OK;
 }
 
-template <int EPI, int BN>
-static int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+template <int EPI, int BN, int CL>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  gemm_bf16_tn_kernel<EPI, BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
-  SRGPT_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, BN, CL>, ta, tb, p));
   return SRGPT_OK;
 }
 
-// 128x256 tiles when that still leaves >= 2 full waves of tiles (large M x N), else 128x128
-static int pick_bn(int M, int N) {
-  static const int forced = [] {
-    const char* v = getenv("SRGPT_GEMM_BN");
-    return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
-  }();
-  if (forced == 128 || forced == 256) return forced;
-  const long tiles256 = (long)ceil_div(M, BM) * ceil_div(N, 256);
-  return tiles256 >= 2L * sm_count() ? 256 : 128;
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
+}
+
+// Configuration choice.  Clusters of 2 (shared, multicast B tile) whenever there are at least two row tiles; 128x256
+// tiles when that still leaves >= 2 full waves of work units, else 128x128.  SRGPT_GEMM_BN / SRGPT_GEMM_CL force a choice.
+static void pick_cfg(int M, int N, int* bn, int* cl) {
+  static const int force_bn = env_int("SRGPT_GEMM_BN"), force_cl = env_int("SRGPT_GEMM_CL");
+  const int tiles_m = ceil_div(M, BM);
+  *cl = (force_cl == 1 || force_cl == 2) ? force_cl : (tiles_m >= 2 ? 2 : 1);
+  const long units256 = (long)ceil_div(tiles_m, *cl) * ceil_div(N, 256);
+  *bn = (force_bn == 128 || force_bn == 256) ? force_bn : (units256 >= 2L * (sm_count() / *cl) ? 256 : 128);
 }
 
 template <int EPI>
 static int launch(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
-  const int bn = pick_bn(p.M, p.N);
+  int bn, cl;
+  pick_cfg(p.M, p.N, &bn, &cl);
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
   if (rc != SRGPT_OK) return rc;
-  rc = make_tmap(&tb, W, p.N, p.K, ldw, bn);
+  rc = make_tmap(&tb, W, p.N, p.K, ldw, bn / cl);  // each CTA of a cluster loads (and multicasts) its share of the B rows
   if (rc != SRGPT_OK) return rc;
-  const int tiles = ceil_div(p.M, BM) * ceil_div(p.N, bn);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  return bn == 256 ? launch_bn<EPI, 256>(ta, tb, p, grid, stream) : launch_bn<EPI, 128>(ta, tb, p, grid, stream);
+  const int units = ceil_div(ceil_div(p.M, BM), cl) * ceil_div(p.N, bn);
+  const int max_clusters = sm_count() / cl;
+  const int grid = (units < max_clusters ? units : max_clusters) * cl;
+  if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, p, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, p, grid, stream);
+  return bn == 256 ? launch_cfg<EPI, 256, 1>(ta, tb, p, grid, stream) : launch_cfg<EPI, 128, 1>(ta, tb, p, grid, stream);
 }
 
 }  // namespace gemm
