@@ -480,12 +480,15 @@ static int env_int(const char* name) {
   return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
 }
 
-// Configuration choice.  Clusters of 2 (shared, multicast B tile) whenever there are at least two row tiles; 128x256
-// tiles when that still leaves >= 2 full waves of work units, else 128x128.  SRGPT_GEMM_BN / SRGPT_GEMM_CL force a choice.
+// Configuration choice: 128x256 tiles when that still leaves >= 2 full waves of work units, else 128x128.
+// Clusters of 2 with a shared (multicast) B tile are implemented and correct but NOT the default: measured on B200
+// (profiles/r01_microbench_gemm_cl{1,2}.jsonl) they change nothing at M=8288 (1404 vs 1404 TFLOP/s — with 128x256
+// tiles the kernel is no longer bound by L2->SM bytes) and lose at M=259 (58 vs 38 us: half as many independent
+// producers).  SRGPT_GEMM_BN / SRGPT_GEMM_CL force a choice.
 static void pick_cfg(int M, int N, int* bn, int* cl) {
   static const int force_bn = env_int("SRGPT_GEMM_BN"), force_cl = env_int("SRGPT_GEMM_CL");
   const int tiles_m = ceil_div(M, BM);
-  *cl = (force_cl == 1 || force_cl == 2) ? force_cl : (tiles_m >= 2 ? 2 : 1);
+  *cl = (force_cl == 2 && tiles_m >= 2) ? 2 : 1;
   const long units256 = (long)ceil_div(tiles_m, *cl) * ceil_div(N, 256);
   *bn = (force_bn == 128 || force_bn == 256) ? force_bn : (units256 >= 2L * (sm_count() / *cl) ? 256 : 128);
 }
