@@ -80,6 +80,28 @@ def test_gemm_epilogues(ops, M, N, K):
             ops.gemm(ad, wd, epilogue=ops.EPI_SWIGLU)
 
 
+def test_gemm_cluster_multicast_path():
+    """The opt-in 2-CTA cluster configuration (TMA-multicast weight tile, multicast tcgen05.commit) stays correct.
+    The choice is read once per process, so it runs in a child process with SRGPT_GEMM_CL=2."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from spatialrgpt_b200 import ops\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "for (M, N, K) in [(259, 640, 512), (1024, 1152, 1152), (4096, 4608, 320), (300, 4304, 1152)]:\n"
+        "    a = torch.randn(M, K, generator=g).bfloat16(); w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()\n"
+        "    out = ops.gemm(a.cuda(), w.cuda(), out_fp32=True).cpu()\n"
+        "    ref = a.float() @ w.float().t()\n"
+        "    err = (out - ref).abs().max().item() / ref.pow(2).mean().sqrt().item()\n"
+        "    assert err < 1e-3, (M, N, K, err)\n"
+        "print('CLUSTER_OK')\n")
+    env = dict(os.environ, SRGPT_GEMM_CL="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "CLUSTER_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_gemm_strided_views(ops):
     """A and the output may be column slices of wider buffers (fused qkv)."""
     M, K, N = 200, 144, 136
