@@ -36,6 +36,15 @@ WORKLOAD = ("c2: SigLIP-so400m@448px + Llama-3-8B, 1 image, 8 mask regions, dept
             "(S=259 after splice), 128 greedy tokens, batch 1 per GPU")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return int(json.load(open(p))["decode_gemv_gateup_dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -228,7 +237,7 @@ def run_ours(args):
         step_bytes = nums["w_stream"] + nums["kv_per_tok"] * (nums["S"] + 16)
         roof = {"kernel": "gemv_kernel<SWIGLU> (rmsnorm + gate/up_proj 4096->2x14336 + SwiGLU), decode", "bound": "hbm",
                 "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": nums["gateup_bytes"], "avg_launch_ms": round(avg_ms, 5),
+                "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": nums["gateup_bytes"], "avg_launch_ms": round(avg_ms, 5),
                 "decode_step": {"ms": round(step_ms, 4), "algorithmic_GBps": round(step_bytes / step_ms / 1e6, 1),
                                 "frac_hbm": round(step_bytes / step_ms / 1e6 / hbm_peak, 4), "kernels": llm.kernels_per_decode_step}}
 
