@@ -26,6 +26,8 @@ namespace gemv {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
+constexpr int SPRE_MAX = 2;                       // up to 2 x 4 chunks per row per lane in shared memory
+constexpr int SPRE_WARP_BYTES = 2 * 4 * 32 * 16;  // per batch: 2 rows x 4 chunks x 32 lanes x 16 B = 4 KB
 enum { MODE_LM = 3 };
 
 struct Params {
@@ -50,6 +52,7 @@ struct Params {
   float* part_val;
   int* part_idx;
   unsigned long long* trace;  // optional timeline record (srgpt_trace_begin)
+  int spre;                   // number of extra 4-chunk batches per row staged in shared memory before the wait (0..SPRE_MAX)
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -174,6 +177,26 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
       u1[i] = ld_stream16(p1 + c + 32 * i);
     }
   }
+  // ---- a second, register-free prefetch level: the next p.spre batches of both rows go to shared memory with
+  //      cp.async (every lane later reads back exactly the 16-byte slots it filled, so no barrier is needed).
+  //      Occupancy stays at 3 CTAs/SM, unlike the deeper register prefetch (PRE = 2/4) that was measured and rejected.
+  uint8_t* spre_base = smem_raw + (size_t)p.K * 2 + (size_t)warp * ((size_t)p.spre * SPRE_WARP_BYTES);
+  int n_spre = 0;
+  if (first_full) {
+    for (int b = 0; b < p.spre; ++b) {
+      const int cb = c + 32 * NPRE + 128 * b;
+      if (cb + 96 >= nchunk) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(spre_base + ((b * 2 + 0) * 4 + i) * 512 + lane * 16);
+        const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(spre_base + ((b * 2 + 1) * 4 + i) * 512 + lane * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(p0 + cb + 32 * i) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(p1 + cb + 32 * i) : "memory");
+      }
+      ++n_spre;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   // norm weights are static too: fetch them before the wait when a thread owns at most 2 chunks of x
   uint4 nw_pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
   const bool nw_pre_valid = (p.norm_weight != nullptr) && (nchunk_all <= 2 * THREADS);
@@ -201,6 +224,21 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
         a1 += dot8(u1[i], xf);
       }
       c += 32 * NPRE;
+      if (n_spre > 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int b = 0; b < n_spre; ++b) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float xf[8];
+            unpack8(px[c + 32 * i], xf);
+            const uint4 w0 = *reinterpret_cast<const uint4*>(spre_base + ((b * 2 + 0) * 4 + i) * 512 + lane * 16);
+            const uint4 w1 = *reinterpret_cast<const uint4*>(spre_base + ((b * 2 + 1) * 4 + i) * 512 + lane * 16);
+            a0 += dot8(w0, xf);
+            a1 += dot8(w1, xf);
+          }
+          c += 128;
+        }
+      }
     }
     for (; c + 96 < nchunk; c += 128) {
 #pragma unroll
@@ -342,9 +380,18 @@ static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int g
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
 }
 
+static int spre_default() {
+  static const int v = [] {
+    const char* e = getenv("SRGPT_GEMV_SPRE");
+    const int x = (e != nullptr && e[0] != 0) ? atoi(e) : 1;
+    return x < 0 ? 0 : (x > SPRE_MAX ? SPRE_MAX : x);
+  }();
+  return v;
+}
+
 template <int MODE, int PRE>
 static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
-  const int smem = p.K * 2;
+  const int smem = p.K * 2 + WARPS * spre_default() * SPRE_WARP_BYTES;
   static int configured_smem = 0;
   if (smem > 48 * 1024 && smem > configured_smem) {
     SRGPT_CHECK_CUDA(cudaFuncSetAttribute(decode_gemv_kernel<MODE, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -355,6 +402,7 @@ static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
   pdl_config(cfg, attr, grid_for(npairs), THREADS, smem, st);
   Params q = p;
   q.trace = trace_next_slot();
+  q.spre = spre_default();
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, PRE>, q));
   return SRGPT_OK;
 }
