@@ -222,6 +222,53 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
   }
 }
 
+// one thread's 32 consecutive accumulator columns of one output row: fused epilogue + 16-byte stores
+template <int EPI>
+__device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, int row, int col0) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (EPI == SRGPT_EPI_SWIGLU) {
+    // interleaved weight rows: column 2i = gate_i, 2i+1 = up_i -> out[:, i]
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = bf16_round(v[2 * j]), u = bf16_round(v[2 * j + 1]);
+      o[j] = bf16_round(silu(g)) * u;
+    }
+    bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + (col0 >> 1);
+    const int ncols_out = p.N >> 1;
+    if ((col0 >> 1) + 16 <= ncols_out) {
+      *reinterpret_cast<uint4*>(cp) = pack8(o);
+      *reinterpret_cast<uint4*>(cp + 8) = pack8(o + 8);
+    } else {
+      for (int j = 0; j < 16; ++j)
+        if ((col0 >> 1) + j < ncols_out) cp[j] = __float2bfloat16_rn(o[j]);
+    }
+  } else {
+    apply_epilogue<EPI>(v, p, row, col0);
+    if (p.out_fp32) {
+      float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+      if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) cp[j] = v[j];
+      }
+    } else {
+      bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
+      if (col0 + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(v + j);
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
+
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster own vertically adjacent 128-row tiles and SHARE
 // the B (weight) tile: each CTA fetches half of its rows and multicasts them into both CTAs' shared memory, so the bytes
 // pulled from L2 per CTA and k-block drop from 16+BN/8 KB... (A + B) to A + B/2 — the quantity that bounds this kernel.
@@ -349,50 +396,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
         tmem_ld_wait();
-        if (row < p.M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (EPI == SRGPT_EPI_SWIGLU) {
-            // interleaved weight rows: column 2i = gate_i, 2i+1 = up_i -> out[:, i]
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float g = bf16_round(v[2 * j]), u = bf16_round(v[2 * j + 1]);
-              o[j] = bf16_round(silu(g)) * u;
-            }
-            bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + (col0 >> 1);
-            const int ncols_out = p.N >> 1;
-            if ((col0 >> 1) + 16 <= ncols_out) {
-              *reinterpret_cast<uint4*>(cp) = pack8(o);
-              *reinterpret_cast<uint4*>(cp + 8) = pack8(o + 8);
-            } else {
-              for (int j = 0; j < 16; ++j)
-                if ((col0 >> 1) + j < ncols_out) cp[j] = __float2bfloat16_rn(o[j]);
-            }
-          } else {
-            apply_epilogue<EPI>(v, p, row, col0);
-            if (p.out_fp32) {
-              float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-              if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) cp[j] = v[j];
-              }
-            } else {
-              bf16* cp = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
-              if (col0 + 32 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(v + j);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
-              }
-            }
-          }
-        }
+        if (row < p.M) store_chunk<EPI>(r, p, row, col0);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -407,6 +411,148 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Tall" configuration for short prompts (128 < M <= 384, e.g. the S = 259 rows of config c2).
+// With 128-row tiles every weight tile is pulled from L2 once per row tile and the activation tile once per
+// column tile: 1.0 GB of L2->SM traffic for the 235 MB gate/up weights, 95 us instead of the 37 us HBM floor.
+// Here ONE CTA owns all M rows (3 x 128-row accumulators, 384 TMEM columns) of a BN-column tile, so weights cross
+// L2->SM once, and the 4 CTAs of a cluster (4 neighbouring column tiles) each fetch a quarter of the 48 KB activation
+// tile and multicast it to the others: per CTA and k-block 12 KB of A + BN*128 B of W for 3*BN*128*64*2 FLOP.
+// ---------------------------------------------------------------------------------------------
+constexpr int TALL_MT = 3;
+constexpr int TALL_CS = 4;
+constexpr int TALL_A_BYTES = TALL_MT * A_STAGE_BYTES;        // 48 KB
+constexpr int TALL_A_SLICE_ROWS = TALL_MT * BM / TALL_CS;    // 96 rows loaded (and multicast) by each CTA
+
+template <int BN_>
+struct TallCfg {
+  static constexpr int B_BYTES = BN_ * BK * 2;
+  static constexpr int STAGE_BYTES = TALL_A_BYTES + B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int TMEM_COLS = (TALL_MT * BN_ <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int EPI, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tall_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = TallCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int crank = (int)cluster_ctarank();
+  const int cid = (int)blockIdx.x / TALL_CS, ncl = (int)gridDim.x / TALL_CS;
+  const int num_units = (tiles_n + TALL_CS - 1) / TALL_CS;  // a unit = 4 neighbouring column tiles, one per CTA
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), TALL_CS);  // every CTA of the cluster reads the shared A tile
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    mbar_init(smem_u32(tmem_empty_bar), NUM_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), C::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int unit = cid; unit < num_units; unit += ncl) {
+        const int n0 = (unit * TALL_CS + crank) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);  // the whole A tile (4 multicast slices) + my B tile
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d_mc(smem_u32(sa + crank * TALL_A_SLICE_ROWS * BK * 2), &tmap_a, fb, kb * BK, crank * TALL_A_SLICE_ROWS, (uint16_t)0xF);
+          tma_load_2d(smem_u32(sa + TALL_A_BYTES), &tmap_b, fb, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (int unit = cid; unit < num_units; unit += ncl) {
+        mbar_wait(smem_u32(tmem_empty_bar), acc_phase ^ 1);
+        tcgen05_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + TALL_A_BYTES);
+#pragma unroll
+          for (int mt = 0; mt < TALL_MT; ++mt) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + mt * A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(tmem_base + mt * BN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_mc(smem_u32(&empty_bar[stage]), (uint16_t)0xF);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(tmem_full_bar));
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    uint32_t acc_phase = 0;
+    for (int unit = cid; unit < num_units; unit += ncl) {
+      const int n0 = (unit * TALL_CS + crank) * BN;
+      mbar_wait(smem_u32(tmem_full_bar), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < TALL_MT; ++mt) {
+        const int row = mt * BM + lg * 32 + lane;
+        if (mt * BM >= p.M) break;  // warp-uniform: no valid rows in this accumulator
+#pragma unroll 1
+        for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + mt * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
+          tmem_ld_wait();
+          if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar));
+      acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -493,8 +639,46 @@ static void pick_cfg(int M, int N, int* bn, int* cl) {
   *bn = (force_bn == 128 || force_bn == 256) ? force_bn : (units256 >= 2L * (sm_count() / *cl) ? 256 : 128);
 }
 
+template <int EPI, int BN>
+static int launch_tall(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
+  using C = TallCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tall_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, p.M, p.K, lda, TALL_A_SLICE_ROWS);
+  if (rc != SRGPT_OK) return rc;
+  rc = make_tmap(&tb, W, p.N, p.K, ldw, BN);
+  if (rc != SRGPT_OK) return rc;
+  const int units = ceil_div(ceil_div(p.N, BN), TALL_CS);
+  const int max_clusters = sm_count() / TALL_CS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((units < max_clusters ? units : max_clusters) * TALL_CS);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TALL_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tall_kernel<EPI, BN>, ta, tb, p));
+  return SRGPT_OK;
+}
+
 template <int EPI>
 static int launch(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
+  // short prompts: all rows in one CTA, activation tile multicast across a 4-CTA cluster (SRGPT_GEMM_TALL=0 disables)
+  static const int tall_off = env_int("SRGPT_GEMM_NO_TALL");
+  if (!tall_off && p.M > BM && p.M <= TALL_MT * BM && !p.out_fp32) {
+    // 128-column tiles when they give every SM a tile, else 64-column tiles (more CTAs pulling weights)
+    if (ceil_div(p.N, 128) >= sm_count() - 4) return launch_tall<EPI, 128>(A, lda, W, ldw, p, stream);
+    return launch_tall<EPI, 64>(A, lda, W, ldw, p, stream);
+  }
   int bn, cl;
   pick_cfg(p.M, p.N, &bn, &cl);
   CUtensorMap ta, tb;
