@@ -415,7 +415,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// "Tall" configuration for short prompts (128 < M <= 384, e.g. the S = 259 rows of config c2).
+// "Tall" configuration for short prompts (128 < M <= 384, e.g. the S = 259 rows of config c2) — an EXPERIMENT that is
+// correct but slower than the default tiles (see launch()); kept opt-in so the measurement stays reproducible.
 // With 128-row tiles every weight tile is pulled from L2 once per row tile and the activation tile once per
 // column tile: 1.0 GB of L2->SM traffic for the 235 MB gate/up weights, 95 us instead of the 37 us HBM floor.
 // Here ONE CTA owns all M rows (3 x 128-row accumulators, 384 TMEM columns) of a BN-column tile, so weights cross
@@ -672,9 +673,12 @@ static int launch_tall(const void* A, int lda, const void* W, int ldw, const Par
 
 template <int EPI>
 static int launch(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
-  // short prompts: all rows in one CTA, activation tile multicast across a 4-CTA cluster (SRGPT_GEMM_TALL=0 disables)
-  static const int tall_off = env_int("SRGPT_GEMM_NO_TALL");
-  if (!tall_off && p.M > BM && p.M <= TALL_MT * BM && !p.out_fp32) {
+  // short prompts: all rows in one CTA, activation tile multicast across a 4-CTA cluster.  Implemented, parity-tested and
+  // MEASURED SLOWER (profiles/r01_microbench_gemm_tall.jsonl: 259x4096x14336 147 vs 82 us, TTFT 17.6 vs 13.4 ms): multicast
+  // removes L2 reads but every SM still has to ingest the whole 48 KB activation tile per k-block, and the per-SM TMA ingest
+  // rate (~45 B/clk) is what bounds these kernels, not L2 read bandwidth.  Opt-in: SRGPT_GEMM_TALL=1.
+  static const int tall_on = env_int("SRGPT_GEMM_TALL");
+  if (tall_on && p.M > BM && p.M <= TALL_MT * BM && !p.out_fp32) {
     // 128-column tiles when they give every SM a tile, else 64-column tiles (more CTAs pulling weights)
     if (ceil_div(p.N, 128) >= sm_count() - 4) return launch_tall<EPI, 128>(A, lda, W, ldw, p, stream);
     return launch_tall<EPI, 64>(A, lda, W, ldw, p, stream);

@@ -96,10 +96,11 @@ def test_gemm_cluster_multicast_path():
         "    err = (out - ref).abs().max().item() / ref.pow(2).mean().sqrt().item()\n"
         "    assert err < 1e-3, (M, N, K, err)\n"
         "print('CLUSTER_OK')\n")
-    env = dict(os.environ, SRGPT_GEMM_CL="2")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0 and "CLUSTER_OK" in r.stdout, r.stdout + r.stderr
+    for knob in ("SRGPT_GEMM_CL", "SRGPT_GEMM_TALL"):  # 2-CTA shared weight tile; 4-CTA shared activation tile (M <= 384)
+        env = dict(os.environ, **{knob: "2" if knob.endswith("CL") else "1"})
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0 and "CLUSTER_OK" in r.stdout, knob + ": " + r.stdout + r.stderr
 
 
 def test_gemm_strided_views(ops):
