@@ -297,13 +297,13 @@ def _rope_tables(hd, theta, max_pos):
     return build_rope_tables(LlamaDims(head_dim=hd, rope_theta=theta), max_pos, DEV)
 
 
-@pytest.mark.parametrize("S,nh,nkv,theta", [(37, 4, 2, 10000.0), (259, 8, 2, 500000.0), (16, 2, 2, 10000.0)])
+@pytest.mark.parametrize("S,nh,nkv,theta", [(37, 4, 2, 10000.0), (259, 8, 2, 500000.0), (16, 2, 2, 10000.0), (700, 4, 1, 500000.0), (513, 2, 2, 10000.0)])
 def test_rope_kv_append_and_decode_attention(ops, S, nh, nkv, theta):
     hd, page = 128, 16
     cfg = O.OracleConfig(head_dim=hd, rope_theta=theta)
     qkv = rnd(S, (nh + 2 * nkv) * hd, seed=12)
-    cos, sin = _rope_tables(hd, theta, 512)
-    cr, sr = O.rope_cos_sin(cfg, torch.arange(512), BF)
+    cos, sin = _rope_tables(hd, theta, 1024)
+    cr, sr = O.rope_cos_sin(cfg, torch.arange(1024), BF)
     assert torch.equal(cos.cpu(), cr[:, : hd // 2]) and torch.equal(sin.cpu(), sr[:, : hd // 2])
     n_pages = (S + 1 + page - 1) // page + 2
     pages = torch.zeros(n_pages, 2, page, nkv, hd, dtype=BF, device=DEV)
