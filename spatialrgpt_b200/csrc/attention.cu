@@ -272,13 +272,15 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, int n_heads, int n_kv_heads, int h
 // QKV kernel of this layer is still streaming its weights; only q, the true position and the newest row(s)
 // are read after the dependency resolves.  `*kv_len_minus1` read before the wait may be one step stale, which
 // is a valid lower bound (positions only grow and rows below it are final).
+// Two further ideas were built and measured on the in-graph timeline, then dropped (profiles/
+// r01_decode_trace_attn_smemwindow.txt): a 128 KB shared-memory prefetch window for rows [256, 512) (the kernel no longer
+// co-resides with the QKV GEMV CTAs, starts late: 7.8 us exposed) and speculative loads of the newest row(s) right after
+// the wait (6.3 us).  This version measures 4.1-5.1 us.
 // ---------------------------------------------------------------------------------------------
 constexpr int DEC_THREADS = 512;
 constexpr int DEC_HW = DEC_THREADS / 16;
-constexpr int DEC_PRE = 8;      // positions per half-warp prefetched into registers  -> rows [0, 256)
-constexpr int DEC_SPRE = 8;     // positions per half-warp prefetched into shared memory -> rows [256, 512)
+constexpr int DEC_PRE = 8;
 constexpr int DEC_UNROLL = 4;
-constexpr int DEC_SMEM_BYTES = DEC_SPRE * DEC_HW * 16 * 16 * 2;  // K and V slots: 128 KB
 
 __device__ __forceinline__ void dec_load_kv(const bf16* __restrict__ kv_pages, const int* __restrict__ page_table, int page_size,
                                             size_t row_stride, int kvh, int hl, int j, uint4& ku, uint4& vu) {
@@ -295,18 +297,15 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
                    const int* __restrict__ page_table, int page_size, const int* __restrict__ kv_len_minus1, int n_kv_heads,
                    int group, float scale_log2, unsigned long long* trace, int prefetch) {
   constexpr int HD = 128;
-  extern __shared__ __align__(16) uint8_t dec_smem[];  // [DEC_SPRE][DEC_HW][16 lanes] uint4 for K, then the same for V
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
   const int head = blockIdx.x, kvh = head / group;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const size_t row_stride = (size_t)n_kv_heads * HD;
-  uint4* sk = reinterpret_cast<uint4*>(dec_smem);
-  uint4* sv = sk + DEC_SPRE * DEC_HW * 16;
   trace_mark(trace, 0);
 
-  // ---- before the dependency wait: immutable rows only (rows [0, pos_early) are final; pos may be one step stale)
-  const int pos_early = prefetch ? *reinterpret_cast<const volatile int*>(kv_len_minus1) : 0;
+  // ---- before the dependency wait: immutable rows only
+  const int pos_early = prefetch ? *reinterpret_cast<const volatile int*>(kv_len_minus1) : 0;  // rows [0, pos_early) are final
   uint4 kpre[DEC_PRE], vpre[DEC_PRE];
 #pragma unroll
   for (int u = 0; u < DEC_PRE; ++u) {
@@ -315,41 +314,13 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
     vpre[u] = make_uint4(0, 0, 0, 0);
     if (j < pos_early) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, kpre[u], vpre[u]);
   }
-#pragma unroll
-  for (int u = 0; u < DEC_SPRE; ++u) {  // second level: cp.async into this lane's own shared-memory slots
-    const int j = (DEC_PRE + u) * DEC_HW + hw;
-    if (j < pos_early) {
-      const int pg = j / page_size;
-      const int page = __ldg(page_table + pg);
-      const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + (j - pg * page_size)) * row_stride + kvh * HD + hl * 8;
-      const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sk + (u * DEC_HW + hw) * 16 + hl);
-      const uint32_t dv = (uint32_t)__cvta_generic_to_shared(sv + (u * DEC_HW + hw) * 16 + hl);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk), "l"(kp) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv), "l"(kp + (size_t)page_size * row_stride) : "memory");
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  // the newest row(s) are written by this layer's QKV kernel: only their (static) page ids can be fetched early.
-  // half-warp 0 will take row pos_early, half-warp 1 row pos_early + 1 (exists only when pos_early was stale)
-  const int spec_j = pos_early + hw;
-  int spec_page = 0;
-  if (hw < 2) spec_page = __ldg(page_table + spec_j / page_size);
-
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   trace_mark(trace, 1);
 
-  // ---- after the wait: everything below is issued together (one round trip): true length, q, speculative newest rows
   const int kv_len = *reinterpret_cast<const volatile int*>(kv_len_minus1) + 1;
-  uint4 kq = *reinterpret_cast<const uint4*>(q + head * HD + hl * 8);
-  uint4 kspec = make_uint4(0, 0, 0, 0), vspec = make_uint4(0, 0, 0, 0);
-  if (hw < 2) {
-    const bf16* kp = kv_pages + (((size_t)spec_page * 2 + 0) * page_size + (spec_j % page_size)) * row_stride + kvh * HD + hl * 8;
-    kspec = *reinterpret_cast<const uint4*>(kp);
-    vspec = *reinterpret_cast<const uint4*>(kp + (size_t)page_size * row_stride);
-  }
   float qf[8];
-  unpack8(kq, qf);
+  unpack8(*reinterpret_cast<const uint4*>(q + head * HD + hl * 8), qf);
   float m = -INFINITY, l = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   auto consume = [&](const uint4* ku, const uint4* vu, const bool* valid, int n) {
@@ -386,38 +357,21 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
     }
   };
 
-  {  // register window [0, 256)
+  {  // prefetched window
     bool valid[DEC_PRE];
 #pragma unroll
     for (int u = 0; u < DEC_PRE; ++u) valid[u] = (u * DEC_HW + hw) < pos_early;
     consume(kpre, vpre, valid, DEC_PRE);
   }
-  if (pos_early > DEC_PRE * DEC_HW) {  // shared-memory window [256, 512): each lane reads back its own slots
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint4 ku[DEC_SPRE], vu[DEC_SPRE];
-    bool valid[DEC_SPRE];
-#pragma unroll
-    for (int u = 0; u < DEC_SPRE; ++u) {
-      valid[u] = ((DEC_PRE + u) * DEC_HW + hw) < pos_early;
-      ku[u] = valid[u] ? sk[(u * DEC_HW + hw) * 16 + hl] : make_uint4(0, 0, 0, 0);
-      vu[u] = valid[u] ? sv[(u * DEC_HW + hw) * 16 + hl] : make_uint4(0, 0, 0, 0);
-    }
-    consume(ku, vu, valid, DEC_SPRE);
-  }
-  {  // speculative newest rows (half-warps 0 and 1)
-    bool valid[1] = {hw < 2 && spec_j < kv_len};
-    consume(&kspec, &vspec, valid, 1);
-  }
-  // ---- whatever is left: positions >= 512 that are neither prefetched nor speculated
-  const int win = (DEC_PRE + DEC_SPRE) * DEC_HW;
-  const int done_upto = pos_early < win ? pos_early : win;  // positions [0, done_upto) are consumed
+  // ---- everything the prefetch did not cover: the newest row(s) and positions >= DEC_PRE*32
+  const int done_upto = pos_early < DEC_PRE * DEC_HW ? pos_early : DEC_PRE * DEC_HW;  // positions [0, done_upto) are consumed
   for (int j0 = (done_upto / DEC_HW) * DEC_HW; j0 < kv_len; j0 += DEC_HW * DEC_UNROLL) {  // warp-uniform trip count
     uint4 ku[DEC_UNROLL], vu[DEC_UNROLL];
     bool valid[DEC_UNROLL];
 #pragma unroll
     for (int u = 0; u < DEC_UNROLL; ++u) {
       const int j = j0 + u * DEC_HW + hw;
-      valid[u] = j < kv_len && j >= done_upto && j != pos_early && j != pos_early + 1;
+      valid[u] = j < kv_len && j >= done_upto;
       ku[u] = make_uint4(0, 0, 0, 0);
       vu[u] = make_uint4(0, 0, 0, 0);
       if (valid[u]) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, ku[u], vu[u]);
@@ -515,15 +469,9 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf1
     set_last_error("srgpt_attention_decode_bf16: head_dim %d unsupported (128 only)", head_dim);
     return SRGPT_ERR_UNSUPPORTED;
   }
-  static bool configured = false;
-  if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(attn::attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::DEC_SMEM_BYTES));
-    configured = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_heads);
   cfg.blockDim = dim3(attn::DEC_THREADS);
-  cfg.dynamicSmemBytes = attn::DEC_SMEM_BYTES;
   cfg.stream = reinterpret_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
