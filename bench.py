@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 N_REGIONS, T_TEXT, NEW_TOKENS = 8, 64, 128
+C3_BATCH, C3_REGIONS = 32, 4
 METRIC = "generated_tokens_per_sec"
 UNIT = "tokens/s"
 WORKLOAD = ("c2: SigLIP-so400m@448px + Llama-3-8B, 1 image, 8 mask regions, depth ON, 64-token prompt "
@@ -109,6 +110,13 @@ class ClockSampler:
 def make_request(cfg, seed):
     from spatialrgpt_b200.synth import synth_request
     return synth_request(cfg, N_REGIONS, T_TEXT, seed)
+
+
+def make_batch(cfg, n_requests, n_regions, seed):
+    """n_requests synthetic requests stacked into one generate() batch (config c3: 32 images, 4 regions each)."""
+    from spatialrgpt_b200.synth import synth_request
+    reqs = [synth_request(cfg, n_regions, T_TEXT, seed + 1000 * i) for i in range(n_requests)]
+    return (torch.cat([r[0] for r in reqs]), torch.cat([r[1] for r in reqs]), torch.cat([r[2] for r in reqs]), [r[3][0] for r in reqs])
 
 
 def algorithmic_numbers(cfg):
@@ -207,6 +215,30 @@ def run_ours(args):
     ms_ttft, _ = timed(step_ttft, args.steps)
     ttft_ms = ms_ttft / args.steps
 
+    # ---- config c3: batch of 32 images x 4 regions, prefill only (generate(max_new_tokens=1)): every GEMM of the tower and
+    #      of the Llama prefill runs over the whole batch (64 x 1024 ViT rows, 32 x 259 prompt rows) -> tensor-core bound
+    c3 = None
+    if not args.no_c3:
+        b_ids, b_img, b_dep, b_msk = make_batch(cfg, C3_BATCH, C3_REGIONS, 4321 + rank)
+        b_ids, b_img, b_dep = b_ids.to(dev), b_img.to(dev), b_dep.to(dev)
+        b_msk = [m.to(dev) for m in b_msk]
+
+        def step_c3():
+            return model.generate(b_ids, images=b_img, depths=b_dep, masks=b_msk, do_sample=False, max_new_tokens=1)
+        for _ in range(2):
+            step_c3()
+        l0 = ops.LAUNCHES
+        ms_c3, n_c3 = timed(step_c3, args.steps)
+        c3_launches = (ops.LAUNCHES - l0) // args.steps
+        c3_ms = ms_c3 / args.steps
+        c3_flops = C3_BATCH * nums["flops_ttft"]
+        c3 = {"workload": f"c3: {C3_BATCH} images x {C3_REGIONS} mask regions, depth ON, 64-token prompts, prefill + first token, per GPU",
+              "ms_per_batch": round(c3_ms, 2), "algorithmic_tflop": round(c3_flops / 1e12, 2),
+              "tflops_per_gpu": round(c3_flops / c3_ms / 1e9, 1), "peak_tflops": tensor_peak,
+              "frac_tensor": round(c3_flops / c3_ms / 1e9 / tensor_peak, 4), "requests_per_s": round(C3_BATCH * world / (c3_ms / 1e3), 1),
+              "gpu_launches_per_batch": int(c3_launches)}
+        del b_ids, b_img, b_dep, b_msk
+
     # ---- per-kernel roofline of the dominant kernel, timed live with CUDA events: the gate/up GEMV
     roof = None
     if rank == 0:
@@ -261,7 +293,8 @@ def run_ours(args):
         "prefill": {"ttft_ms": round(ttft_ms, 3), "algorithmic_tflop": round(nums["flops_ttft"] / 1e12, 3),
                     "tflops": round(nums["flops_ttft"] / ttft_ms / 1e9, 1), "peak_tflops": tensor_peak,
                     "frac_tensor": round(nums["flops_ttft"] / ttft_ms / 1e9 / tensor_peak, 4),
-                    "note": "S=259 rows per Llama GEMM: weight-streaming bound (15 GB), not tensor bound"},
+                    "note": "S=259 rows per Llama GEMM: weight-streaming bound (15 GB), not tensor bound",
+                    "batch32": c3},
         "roofline": roof,
         "cpu_baseline": cpu,
     }
@@ -383,6 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-c3", action="store_true", help="skip the batch-32 prefill-only measurement (config c3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

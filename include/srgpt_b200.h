@@ -115,6 +115,12 @@ int srgpt_depth_to_u8x3(const void* depth, int h, int w, void* out, int H, int W
 int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld,
                                  int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
                                  int causal, void* stream);
+/* Same, for `n_seqs` variable-length sequences packed back to back: sequence b owns rows
+ * [cu_seqlens[b], cu_seqlens[b+1]) (device int32 [n_seqs+1]); max_seqlen bounds the grid.  This is the
+ * varlen form of modeling_llama.py:540-562 (flash_attn_varlen_func over unpadded rows). */
+int srgpt_attention_prefill_varlen_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld,
+                                        int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int n_heads,
+                                        int n_kv_heads, int head_dim, float scale, int causal, void* stream);
 /* RoPE + KV-cache append for `rows` new tokens of one sequence (modeling_llama.py:448-456):
  * rotates q and k in place inside the fused qkv buffer [rows, (nh + 2*nkv)*hd] using the bf16
  * cos/sin tables [max_pos, hd/2], and writes k, v into the paged cache.
@@ -123,6 +129,11 @@ int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, vo
 int srgpt_rope_kv_append_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
                               const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_table,
                               int page_size, void* stream);
+/* Packed-sequence form: row r belongs to sequence b with cu_seqlens[b] <= r < cu_seqlens[b+1], its position is
+ * start_pos[b] + r - cu_seqlens[b], and its page table is page_tables + b * page_table_stride. */
+int srgpt_rope_kv_append_varlen_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
+                                     const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_tables,
+                                     int page_table_stride, int page_size, int n_seqs, const int* cu_seqlens, void* stream);
 /* Decode attention for ONE new token over the paged cache (replaces torch.cat of the cache +
  * flash_attn_func with q_len 1, modeling_llama.py:451-456,564).  q: [nh*hd] bf16 (already rotated),
  * kv_len_minus1: device int = position of the new token (its k/v are already in the cache). */
@@ -154,6 +165,8 @@ int srgpt_lm_head_argmax_bf16(const void* x, const void* W, int ldw, int V, int 
                               long long* out_ids, int* step, int* pos, void* stream);
 /* Plain argmax over fp32 rows (first index on ties), e.g. first token after prefill. */
 int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream);
+/* Same over bf16 rows [rows, ldx] (the bf16-rounded logits of a batched lm_head GEMM, modeling_llama.py:1044). */
+int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream);
 
 /* ---- composite entry points (layers.cu): one call per tower pass / prompt / decode step -------------------
  * Pure sequencing of the kernels above on `stream` (no allocation, no sync); they exist because a Python-side
@@ -170,12 +183,16 @@ typedef struct {
 /* n_layers SigLIP encoder layers in place on x [n_img*T, D] (HF SiglipEncoderLayer; call site vision_encoder.py:119-130). */
 int srgpt_siglip_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
                              void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps, void* stream);
-/* n_layers Llama decoder layers over one prompt x [S, H] in place, appending K/V to the paged cache
- * (LlamaDecoderLayer.forward, modeling_llama.py:623-684). */
+/* n_layers Llama decoder layers over the prompt rows x [S, H] in place, appending K/V to the paged cache
+ * (LlamaDecoderLayer.forward, modeling_llama.py:623-684).  n_seqs == 1, cu_seqlens == NULL: one prompt of S rows.
+ * Otherwise S is the total row count of n_seqs prompts packed back to back (cu_seqlens int32 [n_seqs+1] on the
+ * device, max_seqlen = longest prompt, start_pos [n_seqs], page_tables [n_seqs, page_table_stride]): every GEMM
+ * runs once over all S rows (batch 32 x 259 rows = the c3 workload), attention and the KV append per sequence. */
 int srgpt_llama_prefill_layers_bf16(void* x, const srgpt_llama_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
                                     void* ws_attn, void* ws_act, int S, int H, int n_heads, int n_kv_heads, int head_dim, int I,
                                     float eps, const void* cos_tab, const void* sin_tab, const int* start_pos,
-                                    const int* page_table, int page_size, void* stream);
+                                    const int* page_tables, int page_size, int n_seqs, const int* cu_seqlens, int max_seqlen,
+                                    int page_table_stride, void* stream);
 /* One whole decode step (5 kernels per layer + lm_head + argmax), h [H] in/out = residual stream of the new token. */
 int srgpt_llama_decode_step_bf16(void* h, const srgpt_llama_layer_weights* layers, int n_layers, void* q_buf, void* attn_buf,
                                  void* act_buf, int H, int n_heads, int n_kv_heads, int head_dim, int I, float eps,

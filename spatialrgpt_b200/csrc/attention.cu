@@ -65,7 +65,7 @@ __device__ __forceinline__ void load_tile(bf16 (*dst)[LD], const bf16* __restric
 template <int HD, int HDP, bool CAUSAL>
 __global__ void __launch_bounds__(NTHREADS)
 attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ out,
-                    int q_ld, int kv_ld, int o_ld, int seqlen, int group, float scale_log2) {
+                    int q_ld, int kv_ld, int o_ld, int seqlen_fixed, const int* __restrict__ cu_seqlens, int group, float scale_log2) {
   using S = Smem<HD, HDP>;
   constexpr int LD = S::LD;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -75,9 +75,16 @@ attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
   const int kvh = head / group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = qt * BM;
-  const bf16* qb = q + (size_t)b * seqlen * q_ld + head * HD;
-  const bf16* kb = k + (size_t)b * seqlen * kv_ld + kvh * HD;
-  const bf16* vb = v + (size_t)b * seqlen * kv_ld + kvh * HD;
+  // sequences are either equal-length (row base b * seqlen) or packed back to back with cu_seqlens[b] as row base
+  int row_base = b * seqlen_fixed, seqlen = seqlen_fixed;
+  if (cu_seqlens != nullptr) {
+    row_base = cu_seqlens[b];
+    seqlen = cu_seqlens[b + 1] - row_base;
+    if (q0 >= seqlen) return;  // grid.x covers the longest sequence
+  }
+  const bf16* qb = q + (size_t)row_base * q_ld + head * HD;
+  const bf16* kb = k + (size_t)row_base * kv_ld + kvh * HD;
+  const bf16* vb = v + (size_t)row_base * kv_ld + kvh * HD;
 
   // zero the padding columns [HD, LD) of every buffer once (never overwritten by the tile loads)
   if (HDP + 8 > HD) {
@@ -207,7 +214,7 @@ attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
   }
   const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
   const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
-  bf16* ob = out + (size_t)b * seqlen * o_ld + head * HD;
+  bf16* ob = out + (size_t)row_base * o_ld + head * HD;
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
 #pragma unroll
   for (int db = 0; db < HDP / 8; ++db) {
@@ -231,9 +238,21 @@ __device__ __forceinline__ void rope_pair(float x1, float x2, float c, float s, 
 __global__ void __launch_bounds__(128)
 rope_kv_append_kernel(bf16* __restrict__ qkv, int n_heads, int n_kv_heads, int hd, const bf16* __restrict__ cos_tab,
                       const bf16* __restrict__ sin_tab, const int* __restrict__ start_pos, bf16* __restrict__ kv_pages,
-                      const int* __restrict__ page_table, int page_size) {
+                      const int* __restrict__ page_table, int page_size, const int* __restrict__ cu_seqlens, int n_seqs,
+                      int pt_stride) {
   const int row = blockIdx.x;
-  const int pos = *start_pos + row;
+  int seq = 0, local = row;
+  if (cu_seqlens != nullptr) {  // packed sequences: largest s with cu_seqlens[s] <= row
+    int lo = 0, hi = n_seqs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (cu_seqlens[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    seq = lo;
+    local = row - cu_seqlens[seq];
+    page_table += (size_t)seq * pt_stride;
+  }
+  const int pos = start_pos[seq] + local;
   const int half = hd >> 1;
   const int ld = (n_heads + 2 * n_kv_heads) * hd;
   bf16* r = qkv + (size_t)row * ld;
@@ -401,7 +420,7 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
 
 template <int HD, int HDP, bool CAUSAL>
 static int launch_prefill(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch,
-                          int seqlen, int n_heads, int n_kv_heads, float scale, cudaStream_t st) {
+                          int seqlen, const int* cu_seqlens, int n_heads, int n_kv_heads, float scale, cudaStream_t st) {
   using S = Smem<HD, HDP>;
   static bool configured = false;
   if (!configured) {
@@ -411,7 +430,7 @@ static int launch_prefill(const void* q, const void* k, const void* v, void* out
   dim3 grid(ceil_div(seqlen, BM), n_heads, batch);
   attn_prefill_kernel<HD, HDP, CAUSAL><<<grid, NTHREADS, sizeof(S), st>>>(
       reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
-      reinterpret_cast<bf16*>(out), q_ld, kv_ld, o_ld, seqlen, n_heads / n_kv_heads, scale * 1.4426950408889634f);
+      reinterpret_cast<bf16*>(out), q_ld, kv_ld, o_ld, seqlen, cu_seqlens, n_heads / n_kv_heads, scale * 1.4426950408889634f);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }
@@ -423,40 +442,66 @@ using namespace srgpt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld,
-                                            int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
-                                            int causal, void* stream) {
+static int attention_prefill_any(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen,
+                                 const int* cu, int n_heads, int n_kv_heads, int head_dim, float scale, int causal, void* stream) {
   SRGPT_CHECK_ARG(q && k && v && out && batch > 0 && seqlen > 0 && n_heads > 0 && n_kv_heads > 0);
   SRGPT_CHECK_ARG((n_heads % n_kv_heads) == 0);
   SRGPT_CHECK_ARG((q_ld % 8) == 0 && (kv_ld % 8) == 0 && (o_ld % 2) == 0);
   SRGPT_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && (reinterpret_cast<uintptr_t>(out) & 3) == 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 72 && !causal)
-    return attn::launch_prefill<72, 80, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st);
+    return attn::launch_prefill<72, 80, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
   if (head_dim == 72 && causal)
-    return attn::launch_prefill<72, 80, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st);
+    return attn::launch_prefill<72, 80, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
   if (head_dim == 128 && causal)
-    return attn::launch_prefill<128, 128, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st);
+    return attn::launch_prefill<128, 128, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
   if (head_dim == 128 && !causal)
-    return attn::launch_prefill<128, 128, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st);
+    return attn::launch_prefill<128, 128, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
   if (head_dim == 64)
-    return causal ? attn::launch_prefill<64, 64, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st)
-                  : attn::launch_prefill<64, 64, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, n_heads, n_kv_heads, scale, st);
-  set_last_error("srgpt_attention_prefill_bf16: unsupported head_dim %d (supported: 64, 72, 128)", head_dim);
+    return causal ? attn::launch_prefill<64, 64, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st)
+                  : attn::launch_prefill<64, 64, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
+  set_last_error("srgpt_attention_prefill: unsupported head_dim %d (supported: 64, 72, 128)", head_dim);
   return SRGPT_ERR_UNSUPPORTED;
 }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_rope_kv_append_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
-                                         const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_table,
-                                         int page_size, void* stream) {
+extern "C" __attribute__((visibility("default"))) int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld,
+                                            int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
+                                            int causal, void* stream) {
+  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, nullptr, n_heads, n_kv_heads, head_dim, scale, causal, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_attention_prefill_varlen_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld,
+                                                   int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int n_heads, int n_kv_heads,
+                                                   int head_dim, float scale, int causal, void* stream) {
+  SRGPT_CHECK_ARG(cu_seqlens != nullptr);
+  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, n_seqs, max_seqlen, cu_seqlens, n_heads, n_kv_heads, head_dim, scale, causal, stream);
+}
+
+static int rope_kv_append_any(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab, const void* sin_tab,
+                              const int* start_pos, void* kv_pages, const int* page_table, int page_size, const int* cu, int n_seqs, int pt_stride,
+                              void* stream) {
   SRGPT_CHECK_ARG(qkv && cos_tab && sin_tab && start_pos && kv_pages && page_table);
   SRGPT_CHECK_ARG(rows > 0 && n_heads > 0 && n_kv_heads > 0 && head_dim > 0 && (head_dim % 16) == 0 && page_size > 0);
   SRGPT_CHECK_ARG(aligned16(qkv) && aligned16(kv_pages));
   attn::rope_kv_append_kernel<<<rows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<bf16*>(qkv), n_heads, n_kv_heads, head_dim, reinterpret_cast<const bf16*>(cos_tab),
-      reinterpret_cast<const bf16*>(sin_tab), start_pos, reinterpret_cast<bf16*>(kv_pages), page_table, page_size);
+      reinterpret_cast<const bf16*>(sin_tab), start_pos, reinterpret_cast<bf16*>(kv_pages), page_table, page_size, cu, n_seqs, pt_stride);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_rope_kv_append_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
+                                         const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_table,
+                                         int page_size, void* stream) {
+  return rope_kv_append_any(qkv, rows, n_heads, n_kv_heads, head_dim, cos_tab, sin_tab, start_pos, kv_pages, page_table, page_size, nullptr, 1, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_rope_kv_append_varlen_bf16(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab,
+                                                const void* sin_tab, const int* start_pos, void* kv_pages, const int* page_tables,
+                                                int page_table_stride, int page_size, int n_seqs, const int* cu_seqlens, void* stream) {
+  SRGPT_CHECK_ARG(cu_seqlens != nullptr && n_seqs > 0 && page_table_stride > 0);
+  return rope_kv_append_any(qkv, rows, n_heads, n_kv_heads, head_dim, cos_tab, sin_tab, start_pos, kv_pages, page_tables, page_size, cu_seqlens, n_seqs,
+                            page_table_stride, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf16(const void* q, void* out, const void* kv_pages, const int* page_table, int page_size,

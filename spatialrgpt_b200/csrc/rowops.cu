@@ -160,14 +160,18 @@ __global__ void splice_kernel(const bf16* s0, const bf16* s1, const bf16* s2, co
 // ---------------------------------------------------------------------------------------------
 // argmax over fp32 rows, first index on ties
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) argmax_f32_kernel(const float* __restrict__ x, int cols, long long* __restrict__ out) {
+__device__ __forceinline__ float argmax_load(const float* p) { return *p; }
+__device__ __forceinline__ float argmax_load(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ x, int ldx, int cols, long long* __restrict__ out) {
   __shared__ float sv[8];
   __shared__ int si[8];
-  const float* row = x + (size_t)blockIdx.x * cols;
+  const T* row = x + (size_t)blockIdx.x * ldx;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float v = row[c];
+    const float v = argmax_load(row + c);
     if (v > best || (v == best && c < bi)) { best = v; bi = c; }
   }
 #pragma unroll
@@ -260,7 +264,14 @@ extern "C" __attribute__((visibility("default"))) int srgpt_splice_rows_bf16(con
 
 extern "C" __attribute__((visibility("default"))) int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream) {
   SRGPT_CHECK_ARG(x && out && rows > 0 && cols > 0);
-  argmax_f32_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, out);
+  argmax_kernel<float><<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, cols, out);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream) {
+  SRGPT_CHECK_ARG(x && out && rows > 0 && cols > 0 && ldx >= cols);
+  argmax_kernel<bf16><<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, cols, out);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

@@ -81,6 +81,8 @@ class LlamaDecoder:
         self.cos, self.sin = build_rope_tables(dims, max_seq_len, dev)
         ppseq = (max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE
         self.cache = PagedKVCache(dims, kv_pages if kv_pages is not None else ppseq * max_seqs, max_seqs, ppseq, dev)
+        # the decode graph reads the page table of the sequence being decoded from this fixed buffer
+        self.active_pt = torch.zeros(ppseq + 1, dtype=torch.int32, device=dev)
         H, nh, hd, I = dims.hidden_size, dims.num_attention_heads, dims.head_dim, dims.intermediate_size
         # decode-step state (static addresses -> graph-capturable)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)       # position of the token being processed
@@ -97,6 +99,26 @@ class LlamaDecoder:
         self.kernels_per_decode_step = 5 * dims.num_hidden_layers + 2
 
     # ---------------------------------------------------------------------------------------------
+    def ensure_capacity(self, n_seqs: int, tokens_per_seq: int) -> None:
+        """Grow the paged cache so `n_seqs` sequences of `tokens_per_seq` tokens fit at once (batched prefill).
+        Re-allocation drops all cached sequences and the captured decode graph (page addresses change)."""
+        c = self.cache
+        need_pages = n_seqs * ((tokens_per_seq + PAGE_SIZE - 1) // PAGE_SIZE)
+        if n_seqs <= len(c.owned) and need_pages <= c.n_pages:
+            return
+        d = self.dims
+        per_page = 2 * PAGE_SIZE * d.num_key_value_heads * d.head_dim * 2 * d.num_hidden_layers
+        free_b, _ = torch.cuda.mem_get_info(self.device)
+        cur_b = c.pages.numel() * 2
+        if need_pages * per_page > free_b + cur_b - (2 << 30):
+            raise RuntimeError(f"KV cache for {n_seqs} x {tokens_per_seq} tokens needs {need_pages * per_page >> 20} MiB, not available")
+        self._graph = None
+        n_pages_old, n_seqs_old = c.n_pages, len(c.owned)
+        self.cache = None
+        del c
+        self.cache = PagedKVCache(d, max(need_pages, n_pages_old), max(n_seqs, n_seqs_old), (self.max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE, self.device)
+        self._layer_array = ops.make_llama_layer_array(self.w.layers, [self.cache.layer(l) for l in range(d.num_hidden_layers)])
+
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         """Embedding gather through the splice kernel (source 0 only)."""
         flat = ids.reshape(-1).to(device=self.device, dtype=torch.int32)
@@ -117,17 +139,48 @@ class LlamaDecoder:
             raise NotImplementedError("chunked prefill (prompt attention over cached pages) is a next-round item")
         return ops.llama_prefill_layers(x, self._layer_array, d.num_hidden_layers, d, self.cos, self.sin, sp, pt, PAGE_SIZE)
 
+    def prefill_packed(self, packed_embeds: torch.Tensor, seq_lens: List[int]) -> torch.Tensor:
+        """Prefill `len(seq_lens)` prompts packed back to back ([sum S_b, H]) into sequence slots 0..B-1 in ONE pass:
+        every GEMM runs over all rows, attention / RoPE / KV append per sequence (the unpadded varlen path of
+        modeling_llama.py:540-562).  The caller has reserved the pages.  Returns the final residual stream, packed."""
+        d = self.dims
+        B = len(seq_lens)
+        if packed_embeds.shape[0] != sum(seq_lens) or B < 1 or min(seq_lens) < 1:
+            raise RuntimeError("prefill_packed: rows do not match seq_lens")
+        if max(seq_lens) > self.max_seq_len:
+            raise RuntimeError(f"prompt of {max(seq_lens)} tokens exceeds max_seq_len {self.max_seq_len}")
+        cu = torch.tensor([0] + list(torch.tensor(seq_lens).cumsum(0).tolist()), dtype=torch.int32).to(self.device)
+        sp = torch.zeros(B, dtype=torch.int32, device=self.device)
+        x = packed_embeds.to(torch.bfloat16).contiguous().clone()
+        return ops.llama_prefill_layers(x, self._layer_array, d.num_hidden_layers, d, self.cos, self.sin, sp, self.cache.page_tables[:B],
+                                        PAGE_SIZE, cu_seqlens=cu, max_seqlen=max(seq_lens))
+
+    def first_tokens(self, hidden_packed: torch.Tensor, seq_lens: List[int], return_logits: bool = False):
+        """Greedy first token of every packed sequence: final norm + lm_head over the B last rows as one GEMM
+        (bf16 logits, modeling_llama.py:1044-1045), argmax with the lowest index on ties."""
+        last = (torch.tensor(seq_lens).cumsum(0) - 1).to(torch.int32).to(self.device)
+        rows = ops.splice_rows(hidden_packed, None, None, None, torch.zeros_like(last), last)
+        hn = ops.rmsnorm(rows, self.w.norm, self.dims.rms_norm_eps)
+        lg = ops.gemm(hn, self.w.lm_head, out=self._logits_buffer(hn.shape[0]))
+        ids = ops.argmax_bf16(lg)
+        return (ids, lg) if return_logits else ids
+
+    def _logits_buffer(self, rows: int) -> torch.Tensor:
+        """bf16 [rows, V] view with a 16-byte-aligned row stride (V = 128259 is odd; the GEMM stores 16-byte vectors)."""
+        V = self.dims.vocab_size
+        return torch.empty((rows, (V + 7) // 8 * 8), dtype=torch.bfloat16, device=self.device)[:, :V]
+
     def logits_all(self, hidden: torch.Tensor) -> torch.Tensor:
         """lm_head over every row -> fp32 logits [S, V] (LlamaForCausalLM.forward semantics, 1044-1045)."""
         hn = ops.rmsnorm(hidden, self.w.norm, self.dims.rms_norm_eps)
-        lg = ops.gemm(hn, self.w.lm_head, out_fp32=False)  # bf16 rounding first, then .float()
+        lg = ops.gemm(hn, self.w.lm_head, out=self._logits_buffer(hn.shape[0]))  # bf16 rounding first, then .float()
         return lg.float()
 
     # ---------------------------------------------------------------------------------------------
     def _decode_step_launch(self, seq: int, logits_out: Optional[torch.Tensor] = None) -> None:
         d, w = self.dims, self.w
         ops.llama_decode_step(self.h, self._layer_array, d.num_hidden_layers, self.q_buf, self.attn_buf, self.act_buf, d, self.cos,
-                              self.sin, self.pos, self.cache.page_tables[seq], PAGE_SIZE, w.norm, w.lm_head, w.embed, self.lm_ws,
+                              self.sin, self.pos, self.active_pt, PAGE_SIZE, w.norm, w.lm_head, w.embed, self.lm_ws,
                               self.out_ids, self.step, logits_out)
 
     def _ensure_graph(self, seq: int) -> None:
@@ -172,8 +225,13 @@ class LlamaDecoder:
         self.step.zero_()
         ops.lm_head_argmax(hidden[S - 1], w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
                            embed_table=w.embed, next_x=self.h, logits_out=None if logits is None else logits[0])
+        return self._decode_loop(seq, 1, max_new_tokens, eos, stopping_fn, use_graph, logits)
+
+    def _decode_loop(self, seq: int, n: int, max_new_tokens: int, eos, stopping_fn, use_graph: bool, logits):
+        """Greedy steps n..max_new_tokens-1 of sequence `seq`; pos / step / h / out_ids[:n] are already set."""
+        self.active_pt.copy_(self.cache.page_tables[seq])
         need_host_check = bool(eos) or stopping_fn is not None
-        n = 1
+        return_logits = logits is not None
         if use_graph and not return_logits:
             self._ensure_graph(seq)
         while n < max_new_tokens:
@@ -192,3 +250,48 @@ class LlamaDecoder:
         if return_logits:
             return out, logits[:n]
         return out
+
+    @torch.no_grad()
+    def generate_batch(self, packed_embeds: torch.Tensor, seq_lens: List[int], max_new_tokens: int, eos_token_ids=None,
+                       stopping_fn=None, use_graph: bool = True, return_logits: bool = False):
+        """Greedy decoding of B prompts: ONE packed prefill pass (tensor-core bound, all prompts share every GEMM), one
+        lm_head GEMM for the B first tokens, then each sequence is decoded from its own KV pages with the single-
+        sequence weight-streaming step.  Returns a list of LongTensor [n_b] (and a list of fp32 logits)."""
+        d, w = self.dims, self.w
+        B = len(seq_lens)
+        if max_new_tokens < 1:
+            return [torch.empty(0, dtype=torch.int64, device=self.device) for _ in range(B)]
+        if max_new_tokens > self.out_ids.numel():
+            raise RuntimeError(f"max_new_tokens {max_new_tokens} exceeds the decoder's cap {self.out_ids.numel()}")
+        if max(seq_lens) + max_new_tokens > self.max_seq_len:
+            raise RuntimeError(f"{max(seq_lens)} prompt + {max_new_tokens} new tokens exceed max_seq_len {self.max_seq_len}")
+        eos = set()
+        if eos_token_ids is not None:
+            eos = set(int(e) for e in (eos_token_ids if isinstance(eos_token_ids, (list, tuple, set)) else [eos_token_ids]))
+        for b in range(len(self.cache.owned)):
+            self.cache.release(b)
+        self.ensure_capacity(B, max(seq_lens) + max_new_tokens)
+        for b in range(B):
+            self.cache.reserve(b, seq_lens[b] + max_new_tokens)
+        hidden = self.prefill_packed(packed_embeds, seq_lens)
+        first, lg = self.first_tokens(hidden, seq_lens, return_logits=True)
+        outs, all_logits = [], []
+        if max_new_tokens == 1 and not return_logits:
+            return [first[b:b + 1] for b in range(B)]
+        zero = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for b in range(B):
+            logits = None
+            if return_logits:
+                logits = torch.empty((max_new_tokens, d.vocab_size), dtype=torch.float32, device=self.device)
+                logits[0].copy_(lg[b])
+            # decode state of sequence b: token 0 is known, the next step processes it at position S_b
+            self.out_ids[0:1].copy_(first[b:b + 1])
+            self.h.copy_(ops.splice_rows(w.embed, None, None, None, zero, first[b:b + 1].to(torch.int32))[0])
+            self.pos.fill_(seq_lens[b])
+            self.step.fill_(1)
+            r = self._decode_loop(b, 1, max_new_tokens, eos, stopping_fn, use_graph, logits)
+            if return_logits:
+                outs.append(r[0]); all_logits.append(r[1])
+            else:
+                outs.append(r)
+        return (outs, all_logits) if return_logits else outs

@@ -161,7 +161,8 @@ class LlavaLlamaModel:
         dflat, doff = cat_rows(depth_embeds)
         img_flat = image_features.reshape(n_img * n_tok, H)
 
-        new_embeds: List[torch.Tensor] = []
+        plan_sid: List[torch.Tensor] = []
+        plan_srow: List[torch.Tensor] = []
         new_labels: List[torch.Tensor] = []
         cur_image_idx = 0
         for b in range(B):
@@ -198,14 +199,21 @@ class LlavaLlamaModel:
                 cur_image_idx += 1
                 start = p + 1
             sid_parts.append(src_id[start:]); srow_parts.append(src_row[start:]); lab_parts.append(lab[start:])
-            sid, srow = torch.cat(sid_parts), torch.cat(srow_parts)
-            new_embeds.append(ops.splice_rows(self.weights.llama.embed, img_flat, mflat if mflat is not None else img_flat,
-                                              dflat if dflat is not None else img_flat, sid.to(dev), srow.to(dev)))
+            plan_sid.append(torch.cat(sid_parts)); plan_srow.append(torch.cat(srow_parts))
             new_labels.append(torch.cat(lab_parts))
 
+        # ONE gather kernel builds the embeddings of the whole batch, packed back to back
         max_model_len = getattr(cfg.llama, "tokenizer_model_max_length", None)
+        if max_model_len is not None:  # llava_arch.py:541-546 truncation
+            plan_sid = [x[:max_model_len] for x in plan_sid]
+            plan_srow = [x[:max_model_len] for x in plan_srow]
+        lens = [int(x.numel()) for x in plan_sid]
+        packed = ops.splice_rows(self.weights.llama.embed, img_flat, mflat if mflat is not None else img_flat,
+                                 dflat if dflat is not None else img_flat, torch.cat(plan_sid).to(dev), torch.cat(plan_srow).to(dev))
+        self._last_packed = (packed, lens)
+        new_embeds = list(torch.split(packed, lens, 0))
+
         if max_model_len is not None:
-            new_embeds = [x[:max_model_len] for x in new_embeds]
             new_labels = [x[:max_model_len] for x in new_labels]
         max_len = max(x.shape[0] for x in new_embeds)
         left = getattr(cfg.llama, "tokenizer_padding_side", "right") == "left"
@@ -240,14 +248,31 @@ class LlavaLlamaModel:
                     input_ids, position_ids, attention_mask, None, labels, images, masks, depths)
         B, S, H = inputs_embeds.shape
         lens = [S] * B if attention_mask is None else attention_mask.bool().sum(-1).tolist()
+        lens = [int(n) for n in lens]
         logits = torch.zeros((B, S, self.config.llama.vocab_size), dtype=torch.float32, device=self.device)
+        valid = [slice(0, n) for n in lens]
+        if attention_mask is not None:  # either padding side: the valid rows of a sequence are contiguous
+            am = attention_mask.bool()
+            for b in range(B):
+                idx = torch.nonzero(am[b]).flatten()
+                if idx.numel() != lens[b] or (lens[b] and int(idx[-1]) - int(idx[0]) + 1 != lens[b]):
+                    raise NotImplementedError("attention masks with holes are not supported")
+                valid[b] = slice(int(idx[0]), int(idx[0]) + lens[b]) if lens[b] else slice(0, 0)
+        llm = self.llm
+        for b in range(len(llm.cache.owned)):
+            llm.cache.release(b)
+        if B == 1:
+            hid = llm.prefill_hidden(inputs_embeds[0, valid[0]], 0, 0)
+        else:  # one packed pass over all rows of the batch
+            llm.ensure_capacity(B, max(lens))
+            for b in range(B):
+                llm.cache.reserve(b, lens[b])
+            hid = llm.prefill_packed(torch.cat([inputs_embeds[b, valid[b]] for b in range(B)], 0), lens)
+        lg = llm.logits_all(hid)
+        o = 0
         for b in range(B):
-            n = int(lens[b])
-            if attention_mask is not None and not bool(attention_mask[b, :n].all()):
-                raise NotImplementedError("left-padded batches in forward() are a next-round item")
-            self.llm.cache.release(0)
-            hid = self.llm.prefill_hidden(inputs_embeds[b, :n], 0, 0)
-            logits[b, :n] = self.llm.logits_all(hid)
+            logits[b, valid[b]] = lg[o:o + lens[b]]
+            o += lens[b]
         return CausalLMOutputWithPast(logits=logits)
 
     __call__ = forward
@@ -289,20 +314,35 @@ class LlavaLlamaModel:
         pad = pad_token_id if pad_token_id is not None else (self.config.llama.pad_token_id or 0)
 
         outs, all_logits = [], []
-        for b in range(B):
-            n = int(lens[b])
-            left = getattr(self.config.llama, "tokenizer_padding_side", "right") == "left"
-            emb = inputs_embeds[b, inputs_embeds.shape[1] - n:] if left else inputs_embeds[b, :n]
-            stop_fn = None
-            if stopping_criteria:
-                def stop_fn(ids, _sc=stopping_criteria):
-                    return any(bool(c(ids[None], None)) for c in _sc)
+        stop_fn = None
+        if stopping_criteria:
+            def stop_fn(ids, _sc=stopping_criteria):
+                return any(bool(c(ids[None], None)) for c in _sc)
+        lens = [int(n) for n in lens]
+        left = getattr(self.config.llama, "tokenizer_padding_side", "right") == "left"
+        if B == 1:
+            n = lens[0]
+            emb = inputs_embeds[0, inputs_embeds.shape[1] - n:] if left else inputs_embeds[0, :n]
             r = self.llm.generate_from_embeds(emb, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
                                               use_graph=use_graph, return_logits=return_logits)
             if return_logits:
                 r, lg = r
                 all_logits.append(lg)
             outs.append(r)
+        else:
+            # batch > 1: one packed prefill over all prompts (llava_arch.py:549-611 pads, modeling_llama.py:540-562 unpads
+            # again; here the rows were never padded), then per-sequence decode
+            if images is not None:
+                packed, _ = self._last_packed
+            else:
+                T = inputs_embeds.shape[1]
+                packed = torch.cat([inputs_embeds[b, T - lens[b]:] if left else inputs_embeds[b, :lens[b]] for b in range(B)], 0)
+            r = self.llm.generate_batch(packed, lens, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
+                                        use_graph=use_graph, return_logits=return_logits)
+            if return_logits:
+                outs, all_logits = r
+            else:
+                outs = r
         n_max = max(o.numel() for o in outs)
         seqs = torch.full((B, n_max), int(pad), dtype=torch.int64, device=self.device)
         for b, o in enumerate(outs):

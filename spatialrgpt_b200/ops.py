@@ -240,6 +240,39 @@ def attention_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: 
     return out
 
 
+def attention_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
+                             n_heads: int, n_kv_heads: int, head_dim: int, scale: float, causal: bool) -> torch.Tensor:
+    """Packed sequences: rows [cu_seqlens[b], cu_seqlens[b+1]) belong to sequence b (modeling_llama.py:540-562)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _need(t, BF16, f"attention_prefill_varlen.{nm}")
+    _need(cu_seqlens, torch.int32, "attention_prefill_varlen.cu_seqlens")
+    q_ld, k_ld, v_ld = _rowmajor2d(q, "q"), _rowmajor2d(k, "k"), _rowmajor2d(v, "v")
+    if k_ld != v_ld:
+        raise SrgptError("attention_prefill_varlen: k and v must share a row stride")
+    out = torch.empty((q.shape[0], n_heads * head_dim), dtype=BF16, device=q.device)
+    check(_lib.load().srgpt_attention_prefill_varlen_bf16(_p(q), _p(k), _p(v), _p(out), q_ld, k_ld, _rowmajor2d(out, "out"),
+                                                          cu_seqlens.numel() - 1, _p(cu_seqlens), max_seqlen, n_heads, n_kv_heads,
+                                                          head_dim, scale, 1 if causal else 0, _stream()),
+          "srgpt_attention_prefill_varlen_bf16")
+    return out
+
+
+def rope_kv_append_varlen(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
+                          start_pos: torch.Tensor, kv_pages: torch.Tensor, page_tables: torch.Tensor, page_size: int,
+                          cu_seqlens: torch.Tensor) -> None:
+    _need(qkv, BF16, "rope_kv_append_varlen.qkv")
+    if not qkv.is_contiguous() or qkv.shape[1] != (n_heads + 2 * n_kv_heads) * head_dim:
+        raise SrgptError("rope_kv_append_varlen: qkv must be contiguous [rows, (nh + 2 nkv) * hd]")
+    for t, nm in ((start_pos, "start_pos"), (page_tables, "page_tables"), (cu_seqlens, "cu_seqlens")):
+        _need(t, torch.int32, f"rope_kv_append_varlen.{nm}")
+    n_seqs = cu_seqlens.numel() - 1
+    if page_tables.dim() != 2 or page_tables.shape[0] < n_seqs or page_tables.stride(1) != 1 or start_pos.numel() < n_seqs:
+        raise SrgptError("rope_kv_append_varlen: page_tables [n_seqs, cap] / start_pos [n_seqs] expected")
+    check(_lib.load().srgpt_rope_kv_append_varlen_bf16(_p(qkv), qkv.shape[0], n_heads, n_kv_heads, head_dim, _p(cos_tab), _p(sin_tab),
+                                                       _p(start_pos), _p(kv_pages), _p(page_tables), page_tables.stride(0), page_size,
+                                                       n_seqs, _p(cu_seqlens), _stream()), "srgpt_rope_kv_append_varlen_bf16")
+
+
 def rope_kv_append(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, cos_tab: torch.Tensor,
                    sin_tab: torch.Tensor, start_pos: torch.Tensor, kv_pages: torch.Tensor, page_table: torch.Tensor,
                    page_size: int) -> None:
@@ -290,6 +323,15 @@ def argmax_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def argmax_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need(x, BF16, "argmax_bf16.x")
+    ldx = _rowmajor2d(x, "argmax_bf16.x")
+    rows, cols = x.shape
+    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    check(_lib.load().srgpt_argmax_bf16(_p(x), ldx, rows, cols, _p(out), _stream()), "srgpt_argmax_bf16")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ composite stacks
 def _count(n: int) -> None:
     global LAUNCHES
@@ -330,9 +372,19 @@ def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: in
     return x
 
 
-def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos, sin, start_pos, page_table, page_size: int) -> torch.Tensor:
-    """All decoder layers over one prompt x [S, H] in place (K/V appended to the paged cache)."""
+def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos, sin, start_pos, page_table, page_size: int,
+                         cu_seqlens: Optional[torch.Tensor] = None, max_seqlen: int = 0) -> torch.Tensor:
+    """All decoder layers over the prompt rows x [S, H] in place (K/V appended to the paged cache).  One prompt
+    (page_table [cap], start_pos [1]) or, with cu_seqlens [n_seqs+1], n_seqs prompts packed back to back
+    (page_table [n_seqs, cap], start_pos [n_seqs])."""
     _need(x, BF16, "llama_prefill_layers.x")
+    n_seqs, pt_stride = 1, 0
+    if cu_seqlens is not None:
+        _need(cu_seqlens, torch.int32, "llama_prefill_layers.cu_seqlens")
+        n_seqs = cu_seqlens.numel() - 1
+        if page_table.dim() != 2 or page_table.shape[0] < n_seqs or start_pos.numel() < n_seqs or page_table.stride(1) != 1:
+            raise SrgptError("llama_prefill_layers: packed prompts need page_table [n_seqs, cap] and start_pos [n_seqs]")
+        pt_stride = page_table.stride(0)
     S, H = x.shape
     nh, nkv, hd, I = dims.num_attention_heads, dims.num_key_value_heads, dims.head_dim, dims.intermediate_size
     dev = x.device
@@ -343,7 +395,8 @@ def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos,
     import ctypes
     check(_lib.load().srgpt_llama_prefill_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
                                                       _p(ws_attn), _p(ws_act), S, H, nh, nkv, hd, I, dims.rms_norm_eps, _p(cos), _p(sin),
-                                                      _p(start_pos), _p(page_table), page_size, _stream()), "srgpt_llama_prefill_layers_bf16")
+                                                      _p(start_pos), _p(page_table), page_size, n_seqs, _p(cu_seqlens), max_seqlen, pt_stride,
+                                                      _stream()), "srgpt_llama_prefill_layers_bf16")
     _count(8 * n_layers)
     return x
 

@@ -86,7 +86,14 @@ class RegionExtractor:
 
     def extract_region_features(self, features: torch.Tensor, masks, proj_w, proj_b, order: int):
         pooled = self.mask_pooling(features, masks, order=order, return_list=True)
-        return [None if p is None else ops.gemm(p.contiguous(), proj_w, bias=proj_b, epilogue=ops.EPI_BIAS) for p in pooled]
+        idx = [i for i, p in enumerate(pooled) if p is not None]
+        out: List[Optional[torch.Tensor]] = [None] * len(pooled)
+        if idx:  # one projector GEMM over the regions of the whole batch
+            rows = [pooled[i].shape[0] for i in idx]
+            proj = ops.gemm(torch.cat([pooled[i] for i in idx], 0), proj_w, bias=proj_b, epilogue=ops.EPI_BIAS)
+            for i, part in zip(idx, torch.split(proj, rows, 0)):
+                out[i] = part
+        return out
 
     def forward(self, image_features: torch.Tensor, depth_features: Optional[torch.Tensor], masks, hres_order: int = ops.ORDER_ROWMAJOR):
         """base_extractor.py:167-173.  ``image_features`` = hres (row-major by default, like the reference)."""

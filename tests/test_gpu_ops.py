@@ -291,6 +291,64 @@ def test_attention_prefill(ops, B, S, nh, nkv, hd, causal):
     assert_close(out, ref, rel_rms=1e-2, rel_max=8e-2, what=f"attention B{B} S{S} hd{hd} causal={causal}")
 
 
+@pytest.mark.parametrize("lens,nh,nkv,hd,causal", [
+    ([259, 1, 64, 130], 8, 2, 128, True), ([5, 300], 4, 4, 128, True), ([100, 7, 1024], 2, 2, 72, False), ([64], 2, 1, 64, True),
+])
+def test_attention_prefill_varlen(ops, lens, nh, nkv, hd, causal):
+    """Packed variable-length sequences (modeling_llama.py:540-562): every sequence equals its own dense attention."""
+    S = sum(lens)
+    qkv = rnd(S, (nh + 2 * nkv) * hd, seed=21)
+    qd, kd = nh * hd, nkv * hd
+    scale = hd ** -0.5
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32)
+    d = qkv.to(DEV)
+    out = ops.attention_prefill_varlen(d[:, :qd], d[:, qd:qd + kd], d[:, qd + kd:], cu.to(DEV), max(lens), nh, nkv, hd, scale, causal)
+    o = 0
+    for n in lens:
+        blk = qkv[o:o + n]
+        ref = _sdpa_ref(blk[None, :, :qd], blk[None, :, qd:qd + kd], blk[None, :, qd + kd:], nh, nkv, hd, scale, causal)[0]
+        assert_close(out[o:o + n], ref, rel_rms=1e-2, rel_max=8e-2, what=f"varlen attention len {n}")
+        # and bit-identical to the single-sequence entry point on the same rows
+        one = ops.attention_prefill(d[o:o + n, :qd], d[o:o + n, qd:qd + kd], d[o:o + n, qd + kd:], 1, n, nh, nkv, hd, scale, causal)
+        assert torch.equal(one, out[o:o + n])
+        o += n
+
+
+def test_rope_kv_append_varlen_equals_per_sequence(ops):
+    hd, page, nh, nkv = 128, 16, 4, 2
+    lens = [37, 1, 259, 16]
+    cos, sin = _rope_tables(hd, 500000.0, 512)
+    qkv = rnd(sum(lens), (nh + 2 * nkv) * hd, seed=22).to(DEV)
+    cap = 20
+    n_pages = len(lens) * cap
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(5)).to(torch.int32).view(len(lens), cap).to(DEV)
+    starts = torch.tensor([0, 3, 0, 32], dtype=torch.int32, device=DEV)  # non-zero start positions too
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    pages_a = torch.zeros(n_pages, 2, page, nkv, hd, dtype=BF, device=DEV)
+    pages_b = torch.zeros_like(pages_a)
+    a = qkv.clone()
+    ops.rope_kv_append_varlen(a, nh, nkv, hd, cos, sin, starts, pages_a, perm, page, cu)
+    b = qkv.clone()
+    o = 0
+    for i, n in enumerate(lens):
+        blk = b[o:o + n]
+        ops.rope_kv_append(blk, nh, nkv, hd, cos, sin, starts[i:i + 1], pages_b, perm[i], page)
+        o += n
+    assert torch.equal(a, b) and torch.equal(pages_a, pages_b)
+    assert float(pages_a.float().abs().sum()) > 0
+
+
+def test_argmax_bf16_first_index_on_ties(ops):
+    x = torch.zeros(3, 1000, dtype=BF)
+    x[0, 17] = x[0, 900] = 5.0
+    x[1, 999] = 1.0
+    x[2] = -1.0
+    wide = torch.zeros(3, 1024, dtype=BF)
+    wide[:, :1000] = x
+    wide[:, 1000:] = 9.0  # beyond `cols`: must be ignored (strided rows)
+    assert ops.argmax_bf16(wide.to(DEV)[:, :1000]).tolist() == [17, 999, 0]
+
+
 def _rope_tables(hd, theta, max_pos):
     from spatialrgpt_b200.config import LlamaDims
     from spatialrgpt_b200.llama_decoder import build_rope_tables

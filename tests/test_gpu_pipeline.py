@@ -153,6 +153,75 @@ def test_text_only_and_no_mask_image():
     assert_close(e[0], ref_e, **BF16_STAGE, what="splice without masks")
 
 
+def _batch_requests(oc, specs):
+    """specs: [(n_regions, t_text, seed)] -> padded ids [B, Tmax] + attention mask, image / depth batches, mask list."""
+    reqs = [O.synth_request(oc, n, t, seed=sd, kind="mask") for n, t, sd in specs]
+    T = max(r[0].shape[1] for r in reqs)
+    ids = torch.zeros(len(reqs), T, dtype=torch.long)
+    am = torch.zeros(len(reqs), T, dtype=torch.bool)
+    for b, r in enumerate(reqs):
+        n = r[0].shape[1]
+        ids[b, :n] = r[0][0]
+        am[b, :n] = True
+    return reqs, ids, am, torch.cat([r[1] for r in reqs]), torch.cat([r[2] for r in reqs]), [r[3][0] for r in reqs]
+
+
+def test_batched_generate_equals_per_request(golden_dir):
+    """B prompts of different lengths through ONE packed prefill (+ per-sequence decode) give exactly the tokens and
+    the logits (to bf16 GEMM-shape noise) of B separate generate() calls, and match the CPU oracle per request."""
+    name = "tiny_masks_gqa"
+    kw = CASES[name][0]
+    g = load_npz(os.path.join(golden_dir, name + ".npz"))
+    oc, sd, model = build_model(kw, int(g["weight_seed"]))
+    specs = [(2, 24, 1234), (1, 17, 77), (3, 31, 5)]
+    reqs, ids, am, images, depths, masks = _batch_requests(oc, specs)
+    n_new = 6
+    md = [m.to(DEV) for m in masks]
+    out, logits = model.generate(ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=md, attention_mask=am.to(DEV),
+                                 max_new_tokens=n_new, output_logits=True)
+    assert out.shape == (3, n_new)
+    out_graph = model.generate(ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=md, attention_mask=am.to(DEV),
+                               max_new_tokens=n_new)
+    for b, r in enumerate(reqs):
+        one, lg1 = model.generate(r[0].to(DEV), images=r[1].to(DEV), depths=r[2].to(DEV), masks=[r[3][0].to(DEV)],
+                                  max_new_tokens=n_new, output_logits=True)
+        sigma = float(lg1[0].std())
+        assert (logits[b] - lg1[0]).abs().max().item() <= 0.03 * sigma
+        # the oracle (fp32) for this request
+        enc = O.encode_multimodal(oc, sd, r[1], r[2], r[3])
+        emb = O.splice_embeddings(oc, sd["llm"]["model.embed_tokens.weight"].float(), r[0], enc["image_features"],
+                                  enc["mask_embeds"], enc["depth_embeds"])[0]
+        ref, rlg = O.greedy_generate(oc, sd["llm"], emb, n_new, return_logits=True)
+        assert (logits[b].cpu() - rlg).abs().max().item() <= 0.06 * float(rlg.std())
+        top2 = rlg.topk(2, -1).values
+        safe = int(((top2[:, 0] - top2[:, 1]) > 0.08 * float(rlg.std())).long().cumprod(0).sum())
+        assert out[b].tolist()[:safe] == ref.tolist()[:safe] and safe >= 1
+        assert out[b].tolist()[:safe] == one[0].tolist()[:safe] == out_graph[b].tolist()[:safe]
+    # prefill-only form (max_new_tokens=1, the c3 workload) returns the same first tokens
+    first = model.generate(ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=md, attention_mask=am.to(DEV), max_new_tokens=1)
+    assert first.shape == (3, 1) and first[:, 0].tolist() == out[:, 0].tolist()
+    # a single request afterwards still works (cache was re-grown, decode graph re-captured)
+    again = model.generate(reqs[0][0].to(DEV), images=reqs[0][1].to(DEV), depths=reqs[0][2].to(DEV), masks=[reqs[0][3][0].to(DEV)],
+                           max_new_tokens=n_new)
+    assert again[0].tolist() == out_graph[0].tolist()
+
+
+def test_batched_forward_logits(golden_dir):
+    name = "tiny_boxes"
+    kw = CASES[name][0]
+    g = load_npz(os.path.join(golden_dir, name + ".npz"))
+    oc, sd, model = build_model(kw, int(g["weight_seed"]))
+    reqs, ids, am, images, depths, masks = _batch_requests(oc, [(2, 24, 1234), (1, 19, 9)])
+    out = model.forward(input_ids=ids.to(DEV), images=images.to(DEV), masks=[m.to(DEV) for m in masks], depths=depths.to(DEV),
+                        attention_mask=am.to(DEV))
+    for b, r in enumerate(reqs):
+        one = model.forward(input_ids=r[0].to(DEV), images=r[1].to(DEV), masks=[r[3][0].to(DEV)], depths=r[2].to(DEV))
+        n = one.logits.shape[1]
+        sigma = float(one.logits.std())
+        assert (out.logits[b, :n] - one.logits[0]).abs().max().item() <= 0.03 * sigma
+        assert float(out.logits[b, n:].abs().max()) == 0.0 if out.logits.shape[1] > n else True
+
+
 def test_missing_cuda_inputs_fail_loudly():
     from spatialrgpt_b200 import SrgptError, ops
     with pytest.raises(SrgptError):
