@@ -108,7 +108,9 @@ int srgpt_reorder_rows_bf16(const void* x, void* y, int n_img, int side, int C, 
 int srgpt_depth_to_u8x3(const void* depth, int h, int w, void* out, int H, int W, void* workspace, void* stream);
 
 /* ---- attention (attention.cu) ------------------------------------------------------------------
- * Prefill attention, softmax in fp32, flash-style (no S x S matrix in HBM).
+ * Prefill attention, softmax in fp32, flash-style (no S x S matrix in HBM).  head_dim 72 / 128 run on the
+ * tcgen05 tensor cores (attention_tc.cu: TMA boxes out of the fused qkv buffer, S and P.V accumulators in TMEM,
+ * warp-specialised softmax); other head sizes use the mma.sync kernel.
  * Replaces SigLIP's eager attention (non-causal, head_dim 72) and flash_attn_func(causal=True) with
  * GQA (modeling_llama.py:564-566).  q/k/v/out rows are tokens; head h of a row starts at h*head_dim.
  * Sequences are `batch` equal-length segments of `seqlen` consecutive rows. */
@@ -116,11 +118,12 @@ int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, vo
                                  int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
                                  int causal, void* stream);
 /* Same, for `n_seqs` variable-length sequences packed back to back: sequence b owns rows
- * [cu_seqlens[b], cu_seqlens[b+1]) (device int32 [n_seqs+1]); max_seqlen bounds the grid.  This is the
- * varlen form of modeling_llama.py:540-562 (flash_attn_varlen_func over unpadded rows). */
+ * [cu_seqlens[b], cu_seqlens[b+1]) (device int32 [n_seqs+1]); max_seqlen bounds the grid, total_rows =
+ * cu_seqlens[n_seqs] bounds the TMA views (host value).  This is the varlen form of modeling_llama.py:540-562
+ * (flash_attn_varlen_func over unpadded rows). */
 int srgpt_attention_prefill_varlen_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld,
-                                        int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int n_heads,
-                                        int n_kv_heads, int head_dim, float scale, int causal, void* stream);
+                                        int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int total_rows,
+                                        int n_heads, int n_kv_heads, int head_dim, float scale, int causal, void* stream);
 /* RoPE + KV-cache append for `rows` new tokens of one sequence (modeling_llama.py:448-456):
  * rotates q and k in place inside the fused qkv buffer [rows, (nh + 2*nkv)*hd] using the bf16
  * cos/sin tables [max_pos, hd/2], and writes k, v into the paged cache.

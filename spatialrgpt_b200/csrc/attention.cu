@@ -442,13 +442,26 @@ using namespace srgpt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+namespace srgpt {
+namespace attn_tc {  // attention_tc.cu: tcgen05 / TMEM / TMA kernel (head_dim 72 and 128)
+int prefill(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen, const int* cu, long long total_rows,
+            int n_heads, int n_kv_heads, int head_dim, float scale, int causal, cudaStream_t st);
+}
+}  // namespace srgpt
+
 static int attention_prefill_any(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen,
-                                 const int* cu, int n_heads, int n_kv_heads, int head_dim, float scale, int causal, void* stream) {
+                                 const int* cu, long long total_rows, int n_heads, int n_kv_heads, int head_dim, float scale, int causal, void* stream) {
   SRGPT_CHECK_ARG(q && k && v && out && batch > 0 && seqlen > 0 && n_heads > 0 && n_kv_heads > 0);
   SRGPT_CHECK_ARG((n_heads % n_kv_heads) == 0);
   SRGPT_CHECK_ARG((q_ld % 8) == 0 && (kv_ld % 8) == 0 && (o_ld % 2) == 0);
   SRGPT_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && (reinterpret_cast<uintptr_t>(out) & 3) == 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // tensor-memory kernel first; the mma.sync kernel below covers the remaining head sizes (and SRGPT_ATTN_MMA_SYNC=1)
+  static const bool force_mma_sync = env_flag("SRGPT_ATTN_MMA_SYNC");
+  if (!force_mma_sync) {
+    const int rc = attn_tc::prefill(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, total_rows, n_heads, n_kv_heads, head_dim, scale, causal, st);
+    if (rc != SRGPT_ERR_UNSUPPORTED) return rc;
+  }
   if (head_dim == 72 && !causal)
     return attn::launch_prefill<72, 80, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, n_heads, n_kv_heads, scale, st);
   if (head_dim == 72 && causal)
@@ -467,14 +480,15 @@ static int attention_prefill_any(const void* q, const void* k, const void* v, vo
 extern "C" __attribute__((visibility("default"))) int srgpt_attention_prefill_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld,
                                             int batch, int seqlen, int n_heads, int n_kv_heads, int head_dim, float scale,
                                             int causal, void* stream) {
-  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, nullptr, n_heads, n_kv_heads, head_dim, scale, causal, stream);
+  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, nullptr, (long long)batch * seqlen, n_heads, n_kv_heads, head_dim, scale, causal,
+                               stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int srgpt_attention_prefill_varlen_bf16(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld,
-                                                   int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int n_heads, int n_kv_heads,
-                                                   int head_dim, float scale, int causal, void* stream) {
-  SRGPT_CHECK_ARG(cu_seqlens != nullptr);
-  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, n_seqs, max_seqlen, cu_seqlens, n_heads, n_kv_heads, head_dim, scale, causal, stream);
+                                                   int o_ld, int n_seqs, const int* cu_seqlens, int max_seqlen, int total_rows, int n_heads,
+                                                   int n_kv_heads, int head_dim, float scale, int causal, void* stream) {
+  SRGPT_CHECK_ARG(cu_seqlens != nullptr && total_rows >= max_seqlen);
+  return attention_prefill_any(q, k, v, out, q_ld, kv_ld, o_ld, n_seqs, max_seqlen, cu_seqlens, total_rows, n_heads, n_kv_heads, head_dim, scale, causal, stream);
 }
 
 static int rope_kv_append_any(void* qkv, int rows, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab, const void* sin_tab,

@@ -1,0 +1,466 @@
+// Prefill attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), warp-specialised, persistent.
+//
+// Replaces SigLIP's eager attention (HF SiglipAttention, head_dim 72, non-causal; call site
+// llava/model/multimodal_encoder/vision_encoder.py:119-130) and flash_attn_func / flash_attn_varlen_func
+// (modeling_llama.py:540-566; head_dim 128, causal, GQA) for the prompt rows.  The mma.sync kernel in attention.cu
+// (110 TFLOP/s) was 73 of the 120 ms of a 64-image tower pass; this is its tensor-memory successor.
+//
+// One CTA per SM loops over (q tile of 128 rows, head, sequence) work items:
+//   warp 0      TMA producer: Q tile once per item, K / V tiles through 2-stage rings.  Tiles come straight out of the
+//               fused qkv activation through 3-D tensor maps (channel, head, row): a head of 72 channels is a 64-channel
+//               128B-swizzled box + a 16-channel 32B-swizzled box whose channels 72..79 are out of bounds -> zero filled,
+//               so neither the GEMM output nor the weights need padding.
+//   warp 1      tcgen05.mma issuer.  S = Q K^T (both K-major) into one of two TMEM S buffers; O_j = P_j V_j with P (bf16,
+//               written by the softmax warps into a 128B-swizzled K-major tile) as A and the V tile [kv, channels] used
+//               AS LOADED as an MN-major B operand (no transpose anywhere).  S_{j+1} is issued before P_j V_j, so the
+//               tensor pipe works under the softmax of tile j.
+//   warps 2..9  softmax: thread pair (w, w+4) owns one q row, each thread half of the kv columns.  Online softmax in
+//               base 2 (ex2.approx on the SFU); every tile's O_j is a FRESH TMEM accumulator that the threads fold into
+//               registers (o = o * alpha + O_j), so TMEM is never rescaled and no correction pass exists.
+// Per 128x128 tile the SFU needs 1024 clk (16 ex2/clk/SM), the tensor pipe 640 clk, TMEM reads ~400 clk.
+// UMMA descriptor encodings (MN-major, 32B swizzle, OOB fill) were verified with tools/umma_probe.
+#include "common.cuh"
+#include "srgpt_b200.h"
+#include "tcgen05.cuh"
+
+namespace srgpt {
+namespace attn_tc {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int SM_WARPS = 8;
+constexpr int NTHREADS = 64 + 32 * SM_WARPS;
+constexpr int TMEM_COLS = 512;
+constexpr int O_COL = 256;  // S buffers at columns [0, 2*BN), O buffers at 256 and 384
+
+enum Bar { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 6, V_FULL = 8, V_EMPTY = 10, S_FULL = 12, S_EMPTY = 14, P_FULL = 16, P_EMPTY = 18,
+           O_FULL = 20, O_EMPTY = 22, NUM_BARS = 24 };
+
+template <int HD, int BN>
+struct Geo {
+  static_assert(HD == 72 || HD == 128, "head_dim 72 or 128");
+  static_assert(BN == 64 || BN == 128, "kv tile 64 or 128");
+  static constexpr int W1 = HD == 72 ? 16 : 64;            // channels of the second chunk (the first has 64)
+  static constexpr bool TAIL32 = W1 == 16;                 // second chunk is a 32B-swizzled box
+  static constexpr int ROWB1 = TAIL32 ? 32 : 128;          // bytes per row of chunk 1
+  static constexpr uint64_t F1 = TAIL32 ? UMMA_DESC_SW32 : UMMA_DESC_SW128;
+  static constexpr int Q_C0 = BM * 128, Q_BYTES = Q_C0 + BM * ROWB1;
+  static constexpr int KV_C0 = BN * 128, KV_BYTES = KV_C0 + BN * ROWB1;
+  static constexpr int P_BYTES = BM * BN * 2;
+  static constexpr int OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + 2 * KV_BYTES, OFF_P = OFF_V + 2 * KV_BYTES, OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_RED = OFF_BAR + NUM_BARS * 8 + 16;
+  static constexpr int SMEM_BYTES = OFF_RED + 3 * 2 * BM * 4 + 1024;  // + alignment slack
+  static constexpr int V_ADV1 = 16 * ROWB1;                // bytes per UMMA_K step (16 kv rows) of V chunk 1
+  static constexpr int NS = BN / 2;                        // S columns per softmax thread
+  static constexpr int OREG = HD == 72 ? 40 : 64;          // O columns per softmax thread
+};
+
+struct Maps {
+  CUtensorMap q0, q1, k0, k1, v0, v1;  // chunk 0 / chunk 1 boxes of the q, k, v views
+};
+
+struct Params {
+  const int* cu_seqlens;  // null: `batch` sequences of `seqlen` rows back to back
+  int seqlen, batch, n_heads, group, nqt;
+  float scale_log2;
+  bf16* out;
+  int o_ld;
+};
+
+struct Work {
+  int row_base, seqlen, q0, head, n_tiles;
+};
+
+// Work items of this CTA in order: w = blockIdx.x, + gridDim.x, ...; items whose q tile starts past the sequence end are skipped.
+template <int BN, bool CAUSAL>
+struct WorkIter {
+  const Params& p;
+  int w, n_work;
+  Work k;
+  __device__ WorkIter(const Params& p_, int n_work_) : p(p_), w((int)blockIdx.x - (int)gridDim.x), n_work(n_work_) { k.n_tiles = 0; }
+  __device__ bool next() {
+    while (true) {
+      w += gridDim.x;
+      if (w >= n_work) return false;
+      const int qt = w % p.nqt;
+      const int hb = w / p.nqt;
+      k.head = hb % p.n_heads;
+      const int b = hb / p.n_heads;
+      if (p.cu_seqlens != nullptr) {
+        k.row_base = p.cu_seqlens[b];
+        k.seqlen = p.cu_seqlens[b + 1] - k.row_base;
+      } else {
+        k.row_base = b * p.seqlen;
+        k.seqlen = p.seqlen;
+      }
+      k.q0 = qt * BM;
+      if (k.q0 >= k.seqlen) continue;
+      const int kv_end = CAUSAL ? min(k.seqlen, k.q0 + BM) : k.seqlen;
+      k.n_tiles = (kv_end + BN - 1) / BN;
+      return true;
+    }
+  }
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int HD, int BN, bool CAUSAL>
+__global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+  using G = Geo<HD, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_work = p.nqt * p.n_heads * p.batch;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + G::OFF_BAR;
+  auto bar = [&](int which) { return bar0 + which * 8; };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.q0); prefetch_tmap(&maps.q1); prefetch_tmap(&maps.k0);
+    prefetch_tmap(&maps.k1); prefetch_tmap(&maps.v0); prefetch_tmap(&maps.v1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(Q_FULL + i), 1);
+      mbar_init(bar(Q_EMPTY + i), 1);
+      mbar_init(bar(K_FULL + i), 1);
+      mbar_init(bar(K_EMPTY + i), 1);
+      mbar_init(bar(V_FULL + i), 1);
+      mbar_init(bar(V_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1);
+      mbar_init(bar(S_EMPTY + i), SM_WARPS);
+      mbar_init(bar(P_FULL + i), SM_WARPS);
+      mbar_init(bar(P_EMPTY + i), 1);
+      mbar_init(bar(O_FULL + i), 1);
+      mbar_init(bar(O_EMPTY + i), SM_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t t = 0, it = 0;
+      WorkIter<BN, CAUSAL> wi(p, n_work);
+      while (wi.next()) {
+        const Work& k = wi.k;
+        const int kvh = k.head / p.group;
+        const int qi = it & 1;
+        mbar_wait(bar(Q_EMPTY + qi), ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar(Q_FULL + qi), G::Q_BYTES);
+        tma_load_3d(sbase + qi * G::Q_BYTES, &maps.q0, bar(Q_FULL + qi), 0, k.head, k.row_base + k.q0);
+        tma_load_3d(sbase + qi * G::Q_BYTES + G::Q_C0, &maps.q1, bar(Q_FULL + qi), 64, k.head, k.row_base + k.q0);
+        for (int j = 0; j < k.n_tiles; ++j, ++t) {
+          const int i = t & 1;
+          const uint32_t ph = (t >> 1) & 1;
+          const int row = k.row_base + j * BN;
+          mbar_wait(bar(K_EMPTY + i), ph ^ 1);
+          mbar_expect_tx(bar(K_FULL + i), G::KV_BYTES);
+          tma_load_3d(sbase + G::OFF_K + i * G::KV_BYTES, &maps.k0, bar(K_FULL + i), 0, kvh, row);
+          tma_load_3d(sbase + G::OFF_K + i * G::KV_BYTES + G::KV_C0, &maps.k1, bar(K_FULL + i), 64, kvh, row);
+          mbar_wait(bar(V_EMPTY + i), ph ^ 1);
+          mbar_expect_tx(bar(V_FULL + i), G::KV_BYTES);
+          tma_load_3d(sbase + G::OFF_V + i * G::KV_BYTES, &maps.v0, bar(V_FULL + i), 0, kvh, row);
+          tma_load_3d(sbase + G::OFF_V + i * G::KV_BYTES + G::KV_C0, &maps.v1, bar(V_FULL + i), 64, kvh, row);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // Tile stream t = 0, 1, ... runs across work items.  Order: S_0, then for every tile t: S_{t+1} (possibly the first tile of
+    // the NEXT item, from the other Q buffer), P_t V_t - the tensor pipe always has the next S queued under the softmax of t.
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_v0 = umma_idesc_bf16(BM, 64, 0, 1);
+      constexpr uint32_t idesc_v1 = umma_idesc_bf16(BM, G::W1, 0, 1);
+      auto issue_s = [&](uint32_t tt, uint32_t item, bool first_of_item, bool last_of_item) {
+        const int i = tt & 1, qi = item & 1;
+        const uint32_t ph = (tt >> 1) & 1;
+        if (first_of_item) mbar_wait(bar(Q_FULL + qi), (item >> 1) & 1);
+        mbar_wait(bar(K_FULL + i), ph);
+        mbar_wait(bar(S_EMPTY + i), ph ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + i * BN;
+        const uint32_t qa = sbase + qi * G::Q_BYTES, ka = sbase + G::OFF_K + i * G::KV_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(d, umma_desc(UMMA_DESC_SW128, qa + k * 32), umma_desc(UMMA_DESC_SW128, ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < G::W1 / 16; ++k)
+          umma_f16(d, umma_desc(G::F1, qa + G::Q_C0 + k * 32), umma_desc(G::F1, ka + G::KV_C0 + k * 32), idesc_s, 1u);
+        umma_commit(bar(S_FULL + i));
+        umma_commit(bar(K_EMPTY + i));
+        if (last_of_item) umma_commit(bar(Q_EMPTY + qi));
+      };
+      auto issue_pv = [&](uint32_t tt) {
+        const int i = tt & 1;
+        const uint32_t ph = (tt >> 1) & 1;
+        mbar_wait(bar(P_FULL + i), ph);
+        mbar_wait(bar(V_FULL + i), ph);
+        mbar_wait(bar(O_EMPTY + i), ph ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + O_COL + i * 128;
+        const uint32_t pa = sbase + G::OFF_P + i * G::P_BYTES, va = sbase + G::OFF_V + i * G::KV_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          const uint64_t a = umma_desc(UMMA_DESC_SW128, pa + (ks >> 2) * (BM * 128) + (ks & 3) * 32);
+          umma_f16(d, a, umma_desc(UMMA_DESC_SW128, va + ks * 2048), idesc_v0, ks != 0 ? 1u : 0u);
+          umma_f16(d + 64, a, umma_desc(G::F1, va + G::KV_C0 + ks * G::V_ADV1), idesc_v1, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(O_FULL + i));
+        umma_commit(bar(P_EMPTY + i));
+        umma_commit(bar(V_EMPTY + i));
+      };
+      uint32_t t = 0, it = 0;
+      WorkIter<BN, CAUSAL> wi(p, n_work);
+      bool have = wi.next();
+      if (have) issue_s(0, 0, true, wi.k.n_tiles == 1);
+      while (have) {
+        const int n = wi.k.n_tiles;
+        for (int j = 0; j + 1 < n; ++j) {
+          issue_s(t + j + 1, it, false, j + 2 == n);
+          issue_pv(t + j);
+        }
+        t += n;
+        have = wi.next();  // first S of the next item goes in before the last P V of this one
+        if (have) issue_s(t, it + 1, true, wi.k.n_tiles == 1);
+        issue_pv(t - 1);
+        ++it;
+      }
+    }
+  } else {
+    // ===================== softmax warps (2..9) =====================
+    const int lg = warp & 3;            // TMEM lane group of this warp
+    const int half = (warp - 2) >> 2;   // which half of the kv columns / O columns this thread owns
+    const int r = lg * 32 + lane;       // q row inside the tile
+    const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+    const float sl = p.scale_log2;
+    const uint32_t red_max = sbase + G::OFF_RED;          // [2 tile parities][2 halves][128 rows] floats
+    const uint32_t red_l = red_max + 2 * 2 * BM * 4;      // [2 halves][128 rows]
+    const uint32_t p_row = sbase + G::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+
+    float o[G::OREG];
+#pragma unroll
+    for (int c = 0; c < G::OREG; ++c) o[c] = 0.f;
+
+    auto fold_o = [&](uint32_t tt, float alpha) {  // o = o * alpha + O_tt (this thread's columns)
+      const int i = tt & 1;
+      mbar_wait(bar(O_FULL + i), (tt >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t base = tmem_base + O_COL + i * 128 + lane_addr;
+      uint32_t v[G::OREG];
+      if (HD == 72) {
+        if (half == 0) {
+          tmem_ld_32x32b_x32(base, v);
+          tmem_ld_32x32b_x8(base + 64, v + 32);  // channels 64..71 (the 16-wide tail accumulator)
+        } else {
+          tmem_ld_32x32b_x32(base + 32, v);
+        }
+      } else {
+        tmem_ld_32x32b_x32(base + half * 64, v);
+        tmem_ld_32x32b_x32(base + half * 64 + 32, v + 32);
+      }
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(O_EMPTY + i));
+      const int n = (HD == 72 && half == 1) ? 32 : G::OREG;
+#pragma unroll
+      for (int c = 0; c < G::OREG; ++c)
+        if (c < n) o[c] = fmaf(o[c], alpha, __uint_as_float(v[c]));
+    };
+    auto finalize = [&](int row_base, int seqlen, int q0, int head, float l_run) {  // O / l -> global; then o = 0
+      st_shared_f32(red_l + (half * BM + r) * 4, l_run);
+      named_bar_sync(1 + lg, 64);
+      const float l_tot = l_run + ld_shared_f32(red_l + ((half ^ 1) * BM + r) * 4);
+      named_bar_sync(1 + lg, 64);  // both halves have read before the next item's finalize overwrites
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      if (q0 + r < seqlen) {
+        bf16* orow = p.out + (size_t)(row_base + q0 + r) * p.o_ld + head * HD;
+#pragma unroll
+        for (int c = 0; c < G::OREG; ++c) o[c] *= inv;
+        if (HD == 72) {
+          if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = pack8(o + c * 8);
+            *reinterpret_cast<uint4*>(orow + 64) = pack8(o + 32);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(orow + 32 + c * 8) = pack8(o + c * 8);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(orow + half * 64 + c * 8) = pack8(o + c * 8);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < G::OREG; ++c) o[c] = 0.f;
+    };
+
+    uint32_t t = 0;
+    bool pending = false;  // the previous item still has its last P V product to fold and its rows to store
+    int pv_row_base = 0, pv_seqlen = 0, pv_q0 = 0, pv_head = 0;
+    float pv_l = 0.f, pv_alpha = 0.f;
+    WorkIter<BN, CAUSAL> wi(p, n_work);
+    while (wi.next()) {
+      const Work k = wi.k;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      for (int j = 0; j < k.n_tiles; ++j, ++t) {
+        const int i = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        // ---- S tile -> registers
+        mbar_wait(bar(S_FULL + i), ph);
+        tcgen05_fence_after();
+        uint32_t sv[G::NS];
+#pragma unroll
+        for (int c = 0; c < G::NS; c += 32) tmem_ld_32x32b_x32(tmem_base + i * BN + half * G::NS + c + lane_addr, sv + c);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(S_EMPTY + i));
+        float s[G::NS];
+#pragma unroll
+        for (int c = 0; c < G::NS; ++c) s[c] = __uint_as_float(sv[c]);
+        // ---- masks: columns past the sequence end, and the causal diagonal tile
+        if (j * BN + BN > k.seqlen || (CAUSAL && j * BN + BN - 1 > k.q0)) {
+          const int kv0 = j * BN + half * G::NS, qi = k.q0 + r;
+#pragma unroll
+          for (int c = 0; c < G::NS; ++c) {
+            const int kv = kv0 + c;
+            if (kv >= k.seqlen || (CAUSAL && kv > qi)) s[c] = -INFINITY;
+          }
+        }
+        // ---- row max (two threads per row exchange through shared memory); 4 independent chains
+        float mx4[4] = {s[0], s[1], s[2], s[3]};
+#pragma unroll
+        for (int c = 4; c < G::NS; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const uint32_t rm = red_max + (t & 1) * (2 * BM * 4);
+        st_shared_f32(rm + (half * BM + r) * 4, mx);
+        named_bar_sync(1 + lg, 64);
+        mx = fmaxf(mx, ld_shared_f32(rm + ((half ^ 1) * BM + r) * 4));
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2_approx((m_run - m_use) * sl);  // m_run = -inf -> 0
+        m_run = m_new;
+        const float msl = m_use * sl;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < G::NS; ++c) {
+          s[c] = ex2_approx(fmaf(s[c], sl, -msl));
+          sum4[c & 3] += s[c];
+        }
+        l_run = fmaf(l_run, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        // ---- P (bf16) -> 128B-swizzled K-major tile: row r, 16-byte chunk c of k-block kb
+        mbar_wait(bar(P_EMPTY + i), ph ^ 1);
+#pragma unroll
+        for (int cc = 0; cc < G::NS / 8; ++cc) {
+          const int col = half * G::NS + cc * 8;
+          const int kb = col >> 6, cin = (col & 63) >> 3;
+          st_shared_v4(p_row + i * G::P_BYTES + kb * (BM * 128) + ((cin ^ (r & 7)) << 4), pack8(s + cc * 8));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL + i));
+        // ---- fold the previous tile's P V product while the tensor pipe works on this one
+        if (j > 0) {
+          fold_o(t - 1, alpha_prev);
+        } else if (pending) {  // ... which, on the first tile of an item, completes the PREVIOUS item
+          fold_o(t - 1, pv_alpha);
+          finalize(pv_row_base, pv_seqlen, pv_q0, pv_head, pv_l);
+          pending = false;
+        }
+        alpha_prev = alpha;
+      }
+      pending = true;
+      pv_row_base = k.row_base; pv_seqlen = k.seqlen; pv_q0 = k.q0; pv_head = k.head;
+      pv_l = l_run; pv_alpha = alpha_prev;
+    }
+    if (pending) {
+      fold_o(t - 1, pv_alpha);
+      finalize(pv_row_base, pv_seqlen, pv_q0, pv_head, pv_l);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int HD, int BN, bool CAUSAL>
+static int launch(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen, const int* cu,
+                  long long total_rows, int n_heads, int n_kv_heads, float scale, cudaStream_t st) {
+  using G = Geo<HD, BN>;
+  static bool configured = false;
+  if (!configured) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<HD, BN, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    configured = true;
+  }
+  Maps maps;
+  struct View { const void* ptr; int heads, ld, rows; CUtensorMap *m0, *m1; };
+  const View views[3] = {{q, n_heads, q_ld, BM, &maps.q0, &maps.q1}, {k, n_kv_heads, kv_ld, BN, &maps.k0, &maps.k1}, {v, n_kv_heads, kv_ld, BN, &maps.v0, &maps.v1}};
+  for (const View& vw : views) {
+    // (channel, head, row) view of a column slice of the fused qkv activation; channels >= HD are out of bounds -> 0
+    const cuuint64_t dims[3] = {(cuuint64_t)HD, (cuuint64_t)vw.heads, (cuuint64_t)total_rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)HD * 2, (cuuint64_t)vw.ld * 2};
+    const cuuint32_t box0[3] = {64, 1, (cuuint32_t)vw.rows};
+    const cuuint32_t box1[3] = {(cuuint32_t)G::W1, 1, (cuuint32_t)vw.rows};
+    int rc = encode_tmap_bf16(vw.m0, vw.ptr, 3, dims, strides, box0, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc == 0) rc = encode_tmap_bf16(vw.m1, vw.ptr, 3, dims, strides, box1, G::TAIL32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) {
+      set_last_error("attention (tcgen05): cuTensorMapEncodeTiled failed (%d) for ptr=%p heads=%d ld=%d rows=%lld", rc, vw.ptr, vw.heads, vw.ld, total_rows);
+      return SRGPT_ERR_CUDA;
+    }
+  }
+  Params p;
+  p.cu_seqlens = cu;
+  p.seqlen = seqlen;
+  p.batch = batch;
+  p.n_heads = n_heads;
+  p.group = n_heads / n_kv_heads;
+  p.nqt = ceil_div(seqlen, BM);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.o_ld = o_ld;
+  const long long n_work = (long long)p.nqt * n_heads * batch;
+  const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
+  attn_fwd_tc_kernel<HD, BN, CAUSAL><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(maps, p);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+// Entry used by attention.cu's dispatcher.  Returns SRGPT_ERR_UNSUPPORTED when the shape is not covered (the caller then
+// uses the mma.sync kernel).  seqlen = max sequence length when cu != null.
+int prefill(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen, const int* cu, long long total_rows,
+            int n_heads, int n_kv_heads, int head_dim, float scale, int causal, cudaStream_t st) {
+  if ((o_ld % 8) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || (q_ld % 8) != 0 || (kv_ld % 8) != 0) return SRGPT_ERR_UNSUPPORTED;
+  if (head_dim == 72 && !causal)
+    return launch<72, 128, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, total_rows, n_heads, n_kv_heads, scale, st);
+  if (head_dim == 128 && causal)
+    return launch<128, 64, true>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, total_rows, n_heads, n_kv_heads, scale, st);
+  if (head_dim == 128 && !causal)
+    return launch<128, 64, false>(q, k, v, out, q_ld, kv_ld, o_ld, batch, seqlen, cu, total_rows, n_heads, n_kv_heads, scale, st);
+  return SRGPT_ERR_UNSUPPORTED;
+}
+
+}  // namespace attn_tc
+}  // namespace srgpt

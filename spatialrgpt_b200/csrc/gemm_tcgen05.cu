@@ -172,7 +172,23 @@ struct Params {
   void* C;
   int epilogue;
   int out_fp32;
+  int gm;                  // rasterisation: m-units per group (see unit_to_tile)
 };
+
+// Tile order.  Units are walked group by group; a group is `gm` vertically adjacent m-units x ALL n-tiles, inside a group the
+// m-unit varies fastest.  The CTAs (unit = cid, cid + ncl, ...) therefore work on ~148 neighbouring m-tiles of one weight
+// tile, and a group's activation rows (gm * 128 * K * 2 bytes, sized to fit L2) are re-read from L2 - not HBM - for every
+// n-tile.  gm = all m-units is the plain "m fastest" order, right when the whole activation fits L2 (Llama prompts); for the
+// ViT tower (65536 x 4304 activations = 564 MB) it re-streamed A from HBM once per n-tile (fc2: 2.8 GB for a 0.56 GB problem).
+__device__ __forceinline__ void unit_to_tile(int unit, int tiles_mu, int tiles_n, int gm, int& mu, int& nt) {
+  const int per_group = gm * tiles_n;
+  const int g = unit / per_group;
+  const int rem = unit - g * per_group;
+  const int g0 = g * gm;
+  const int gsz = min(gm, tiles_mu - g0);
+  nt = rem / gsz;
+  mu = g0 + rem - nt * gsz;
+}
 
 template <int EPI>
 __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, const Params& p, int row, int col0) {
@@ -327,8 +343,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int unit = cid; unit < num_units; unit += ncl) {
-        const int m0 = ((unit % tiles_mu) * CL + crank) * BM;
-        const int n0 = (unit / tiles_mu) * BN;
+        int mu, nt;
+        unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
+        const int m0 = (mu * CL + crank) * BM;
+        const int n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -384,8 +402,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int chalf = (warp - 2) >> 2;  // 0: columns [0, BN/2), 1: columns [BN/2, BN)
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = cid; unit < num_units; unit += ncl) {
-      const int m0 = ((unit % tiles_mu) * CL + crank) * BM;
-      const int n0 = (unit / tiles_mu) * BN;
+      int mu, nt;
+      unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
+      const int m0 = (mu * CL + crank) * BM;
+      const int n0 = nt * BN;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
       const int row = m0 + lg * 32 + lane;
@@ -690,11 +710,22 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
   if (rc != SRGPT_OK) return rc;
   rc = make_tmap(&tb, W, p.N, p.K, ldw, bn / cl);  // each CTA of a cluster loads (and multicasts) its share of the B rows
   if (rc != SRGPT_OK) return rc;
-  const int units = ceil_div(ceil_div(p.M, BM), cl) * ceil_div(p.N, bn);
+  const int tiles_mu = ceil_div(ceil_div(p.M, BM), cl);
+  const int units = tiles_mu * ceil_div(p.N, bn);
+  // rasterisation group: the whole M when the activation fits L2, else as many m-units as keep a group's rows <= 40 MB
+  Params pg = p;
+  static const int gm_env = env_int("SRGPT_GEMM_GM");
+  const double a_bytes = 2.0 * p.M * p.K;
+  pg.gm = tiles_mu;
+  if (a_bytes > 80e6) {
+    const int g = (int)(40e6 / (2.0 * cl * BM * p.K));
+    pg.gm = g < 1 ? 1 : (g < tiles_mu ? g : tiles_mu);
+  }
+  if (gm_env > 0) pg.gm = gm_env < tiles_mu ? gm_env : tiles_mu;
   const int max_clusters = sm_count() / cl;
   const int grid = (units < max_clusters ? units : max_clusters) * cl;
-  if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, p, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, p, grid, stream);
-  return bn == 256 ? launch_cfg<EPI, 256, 1>(ta, tb, p, grid, stream) : launch_cfg<EPI, 128, 1>(ta, tb, p, grid, stream);
+  if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, pg, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, pg, grid, stream);
+  return bn == 256 ? launch_cfg<EPI, 256, 1>(ta, tb, pg, grid, stream) : launch_cfg<EPI, 128, 1>(ta, tb, pg, grid, stream);
 }
 
 }  // namespace gemm

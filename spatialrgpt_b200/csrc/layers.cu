@@ -55,7 +55,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_llama_prefill_layers
       SRGPT_TRY(srgpt_rope_kv_append_varlen_bf16(ws_qkv, S, n_heads, n_kv_heads, head_dim, cos_tab, sin_tab, start_pos, w.kv_pages, page_table, page_table_stride,
                                                  page_size, n_seqs, cu_seqlens, stream));
       SRGPT_TRY(srgpt_attention_prefill_varlen_bf16(ws_qkv, cptr(ws_qkv, (size_t)qd * 2), cptr(ws_qkv, (size_t)(qd + kd) * 2), ws_attn, nqkv, nqkv, qd, n_seqs,
-                                                    cu_seqlens, max_seqlen, n_heads, n_kv_heads, head_dim, scale, 1, stream));
+                                                    cu_seqlens, max_seqlen, S, n_heads, n_kv_heads, head_dim, scale, 1, stream));
     } else {
       SRGPT_TRY(srgpt_rope_kv_append_bf16(ws_qkv, S, n_heads, n_kv_heads, head_dim, cos_tab, sin_tab, start_pos, w.kv_pages, page_table, page_size, stream));
       SRGPT_TRY(srgpt_attention_prefill_bf16(ws_qkv, cptr(ws_qkv, (size_t)qd * 2), cptr(ws_qkv, (size_t)(qd + kd) * 2), ws_attn, nqkv, nqkv, qd, 1, S, n_heads,

@@ -251,7 +251,7 @@ def attention_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
         raise SrgptError("attention_prefill_varlen: k and v must share a row stride")
     out = torch.empty((q.shape[0], n_heads * head_dim), dtype=BF16, device=q.device)
     check(_lib.load().srgpt_attention_prefill_varlen_bf16(_p(q), _p(k), _p(v), _p(out), q_ld, k_ld, _rowmajor2d(out, "out"),
-                                                          cu_seqlens.numel() - 1, _p(cu_seqlens), max_seqlen, n_heads, n_kv_heads,
+                                                          cu_seqlens.numel() - 1, _p(cu_seqlens), max_seqlen, q.shape[0], n_heads, n_kv_heads,
                                                           head_dim, scale, 1 if causal else 0, _stream()),
           "srgpt_attention_prefill_varlen_bf16")
     return out

@@ -186,16 +186,21 @@ def test_batched_generate_equals_per_request(golden_dir):
         one, lg1 = model.generate(r[0].to(DEV), images=r[1].to(DEV), depths=r[2].to(DEV), masks=[r[3][0].to(DEV)],
                                   max_new_tokens=n_new, output_logits=True)
         sigma = float(lg1[0].std())
-        assert (logits[b] - lg1[0]).abs().max().item() <= 0.03 * sigma
+        same = 0
+        while same < n_new and int(out[b][same]) == int(one[0][same]):
+            same += 1
+        assert (logits[b][:min(same + 1, n_new)] - lg1[0][:min(same + 1, n_new)]).abs().max().item() <= 0.03 * sigma
         # the oracle (fp32) for this request
         enc = O.encode_multimodal(oc, sd, r[1], r[2], r[3])
         emb = O.splice_embeddings(oc, sd["llm"]["model.embed_tokens.weight"].float(), r[0], enc["image_features"],
                                   enc["mask_embeds"], enc["depth_embeds"])[0]
         ref, rlg = O.greedy_generate(oc, sd["llm"], emb, n_new, return_logits=True)
-        assert (logits[b].cpu() - rlg).abs().max().item() <= 0.06 * float(rlg.std())
         top2 = rlg.topk(2, -1).values
-        safe = int(((top2[:, 0] - top2[:, 1]) > 0.08 * float(rlg.std())).long().cumprod(0).sum())
+        safe = int(((top2[:, 0] - top2[:, 1]) > 0.08 * float(rlg.std())).long().cumprod(0).sum())  # prefix with a clear margin
         assert out[b].tolist()[:safe] == ref.tolist()[:safe] and safe >= 1
+        # logits of step i depend on tokens 0..i-1: comparable while the greedy prefixes agree
+        n_cmp = min(safe + 1, n_new)
+        assert (logits[b][:n_cmp].cpu() - rlg[:n_cmp]).abs().max().item() <= 0.06 * float(rlg.std())
         assert out[b].tolist()[:safe] == one[0].tolist()[:safe] == out_graph[b].tolist()[:safe]
     # prefill-only form (max_new_tokens=1, the c3 workload) returns the same first tokens
     first = model.generate(ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=md, attention_mask=am.to(DEV), max_new_tokens=1)

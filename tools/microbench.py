@@ -98,7 +98,9 @@ if "gemm" in which:
                            (2048, 1152, 1152, ops.EPI_BIAS_RESIDUAL), (8192, 4608, 1152, ops.EPI_BIAS_GELU_ERF),
                            (259, 6144, 4096, ops.EPI_NONE), (259, 28672, 4096, ops.EPI_SWIGLU), (259, 4096, 14336, ops.EPI_BIAS_RESIDUAL),
                            (8288, 6144, 4096, ops.EPI_NONE), (8288, 28672, 4096, ops.EPI_SWIGLU), (8288, 4096, 14336, ops.EPI_BIAS_RESIDUAL),
-                           (8192, 8192, 8192, ops.EPI_NONE)]:
+                           (8192, 8192, 8192, ops.EPI_NONE), (8288, 4096, 4096, ops.EPI_BIAS_RESIDUAL),
+                           (65536, 3456, 1152, ops.EPI_BIAS), (65536, 4304, 1152, ops.EPI_BIAS_GELU_TANH), (65536, 1152, 4304, ops.EPI_BIAS_RESIDUAL),
+                           (65536, 1152, 1152, ops.EPI_BIAS_RESIDUAL)]:
         a, w = rnd(M, K), rnd(N, K)
         bias = rnd(N) if epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU_TANH, ops.EPI_BIAS_GELU_ERF, ops.EPI_BIAS_RESIDUAL) else None
         n_out = N // 2 if epi == ops.EPI_SWIGLU else N
@@ -108,7 +110,7 @@ if "gemm" in which:
         emit(f"gemm {M}x{N}x{K} epi{epi}", ms, best, flops=2.0 * M * N * K, bytes_=(M * K + N * K + M * n_out) * 2)
 
 if "attn" in which:
-    for (B, S, nh, nkv, hd, causal) in [(2, 1024, 16, 16, 72, False), (1, 259, 32, 8, 128, True), (32, 259, 32, 8, 128, True)]:
+    for (B, S, nh, nkv, hd, causal) in [(2, 1024, 16, 16, 72, False), (64, 1024, 16, 16, 72, False), (1, 259, 32, 8, 128, True), (32, 259, 32, 8, 128, True)]:
         qkv = rnd(B * S, (nh + 2 * nkv) * hd)
         qd, kd = nh * hd, nkv * hd
         ms, best = timeit(lambda: ops.attention_prefill(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], B, S, nh, nkv, hd, hd ** -0.5, causal), flush=False)
