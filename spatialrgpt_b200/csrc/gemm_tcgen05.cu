@@ -92,6 +92,10 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensor
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y), "h"(cta_mask)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no barrier): turns the later TMA load into an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -173,6 +177,7 @@ struct Params {
   int epilogue;
   int out_fp32;
   int gm;                  // rasterisation: m-units per group (see unit_to_tile)
+  int l2_prefetch;         // k-blocks the producer prefetches into L2 ahead of its loads (0 = off)
 };
 
 // Tile order.  Units are walked group by group; a group is `gm` vertically adjacent m-units x ALL n-tiles, inside a group the
@@ -342,12 +347,34 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      // optional L2 prefetch cursor, p.l2_prefetch k-blocks ahead of the loads (runs on into the next tiles of this CTA).
+      // Idea: the ring holds only STAGES * 48 KB in flight, which bounds the ingest at ~60 B/clk/SM (ncu: tensor pipe 62 %
+      // active on the ViT GEMMs).  Measured: it makes things worse (see launch()), so it is off unless SRGPT_GEMM_L2PF is set.
+      int pf_unit = cid, pf_kb = 0, pf_m0 = 0, pf_n0 = 0;
+      bool pf_new = true;
+      auto pf_step = [&](bool issue) {
+        if (pf_unit >= num_units) return;
+        if (pf_new) {
+          int mu, nt;
+          unit_to_tile(pf_unit, tiles_mu, tiles_n, p.gm, mu, nt);
+          pf_m0 = (mu * CL + crank) * BM;
+          pf_n0 = nt * BN + (CL == 2 ? crank * (BN / 2) : 0);
+          pf_new = false;
+        }
+        if (issue) {
+          tma_prefetch_2d(&tmap_a, pf_kb * BK, pf_m0);
+          tma_prefetch_2d(&tmap_b, pf_kb * BK, pf_n0);
+        }
+        if (++pf_kb == num_kb) { pf_kb = 0; pf_unit += ncl; pf_new = true; }
+      };
+      for (int i = 0; i < p.l2_prefetch; ++i) pf_step(false);
       for (int unit = cid; unit < num_units; unit += ncl) {
         int mu, nt;
         unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
         const int m0 = (mu * CL + crank) * BM;
         const int n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (p.l2_prefetch > 0) pf_step(true);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, STAGE_BYTES);  // own A tile + the whole B tile (one half from each CTA when CL == 2)
@@ -431,6 +458,189 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair configuration (tcgen05 cta_group::2): the two CTAs of a cluster (one TPC) compute ONE 256 x 256 tile.  CTA r keeps
+// A rows [128 r, 128 r + 128) and HALF of the weight tile (rows [128 r, 128 r + 128) of the 256) in its own shared memory; the
+// leader issues M = 256 MMAs that read the A tile of each CTA and BOTH weight halves (the peer's through the pair's shared-
+// memory path), and every CTA ends up with its 128 x 256 accumulator in its own TMEM.  Per k-block a CTA now ingests
+// 16 + 16 KB instead of 16 + 32 KB for the same 128 x 256 x 64 MACs - the quantity that bounds the 1-CTA kernel (~60 B/clk/SM
+// of TMA ingest, tensor pipe 62-80 % active) - and the smaller stage allows 6 stages instead of 4.
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address
+//     mapped into the leader with mapa); the leader arms it with the bytes of both;
+//   * tcgen05.commit.cta_group::2 multicasts the "slot free" / "accumulator ready" arrivals to both CTAs;
+//   * the peer's epilogue warps release the accumulator on the leader's tmem_empty barrier (remote arrive).
+// ---------------------------------------------------------------------------------------------
+constexpr int PAIR_BN = 256;
+constexpr bool PAIR_DEFAULT = true;
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_B_HALF_BYTES = (PAIR_BN / 2) * BK * 2;                 // 16 KB
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_B_HALF_BYTES;       // 32 KB per CTA
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on this barrier offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)0x3)
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES, STAGE_BYTES = PAIR_STAGE_BYTES, TMEM_COLS = ACC_BUFS * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                            // [STAGES]  used in the leader only
+  uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  one per CTA (multicast commit)
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;          // [ACC_BUFS] one per CTA (multicast commit)
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_BUFS;  // [ACC_BUFS] used in the leader only: both CTAs' epilogue warps arrive
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_BUFS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int crank = (int)cluster_ctarank();
+  const int cid = (int)blockIdx.x / 2, ncl = (int)gridDim.x / 2;
+  const int tiles_mu = (tiles_m + 1) / 2;
+  const int num_units = tiles_mu * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < ACC_BUFS; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(tmem_base_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int unit = cid; unit < num_units; unit += ncl) {
+        int mu, nt;
+        unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
+        const int m0 = (mu * 2 + crank) * BM;
+        const int n0 = nt * BN + crank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (crank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), 2 * STAGE_BYTES);  // bytes of both CTAs
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d_pair(smem_u32(sa), &tmap_a, fb_leader, kb * BK, m0);
+          tma_load_2d_pair(smem_u32(sa + A_STAGE_BYTES), &tmap_b, fb_leader, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int unit = cid; unit < num_units; unit += ncl) {
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(smem_u32(&empty_bar[stage]));  // slot free in both CTAs once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(smem_u32(&tmem_full_bar[acc]));  // accumulators (one per CTA) complete
+        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9), both CTAs: rows of this CTA's 128 x 256 accumulator =====================
+    const int lg = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int unit = cid; unit < num_units; unit += ncl) {
+      int mu, nt;
+      unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
+      const int m0 = (mu * 2 + crank) * BM;
+      const int n0 = nt * BN;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + lg * 32 + lane;
+#pragma unroll 1
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
+        tmem_ld_wait();
+        if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -703,6 +913,48 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     if (ceil_div(p.N, 128) >= sm_count() - 4) return launch_tall<EPI, 128>(A, lda, W, ldw, p, stream);
     return launch_tall<EPI, 64>(A, lda, W, ldw, p, stream);
   }
+  // CTA-pair kernel (cta_group::2, 256 x 256 tiles per pair) for large problems
+  static const int pair_env = env_int("SRGPT_GEMM_PAIR");  // 1: on where eligible, -1: off, 0: default
+  // default: at least two waves of 256 x 256 pair tiles and >= 1024 rows (measured, profiles/r01_microbench_gemm_pair.txt:
+  // 8288 x 28672 x 4096 0.83 -> 0.90 of the cuBLAS peak, 8192^3 0.85 -> 0.92, ViT qkv 0.67 -> 0.70; M = 259 and the
+  // GELU-tanh epilogue (fc1: the epilogue, not the operand ingest, paces that kernel) are faster on the 1-CTA kernel)
+  const long long pair_units = (long long)ceil_div(ceil_div(p.M, BM), 2) * ceil_div(p.N, PAIR_BN);
+  const bool pair_default = PAIR_DEFAULT && p.M >= 1024 && pair_units >= 2 * (sm_count() / 2) && EPI != SRGPT_EPI_BIAS_GELU_TANH;
+  if (pair_env >= 0 && (pair_env > 0 || pair_default)) {
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+    if (rc != SRGPT_OK) return rc;
+    rc = make_tmap(&tb, W, p.N, p.K, ldw, PAIR_BN / 2);
+    if (rc != SRGPT_OK) return rc;
+    Params pg = p;
+    const int tiles_mu = ceil_div(ceil_div(p.M, BM), 2);
+    pg.gm = tiles_mu;
+    if (2.0 * p.M * p.K > 80e6) {
+      const int g = (int)(40e6 / (2.0 * 2 * BM * p.K));
+      pg.gm = g < 1 ? 1 : (g < tiles_mu ? g : tiles_mu);
+    }
+    pg.l2_prefetch = 0;
+    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    if (!configured[EPI]) {
+      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+      configured[EPI] = true;
+    }
+    const int max_clusters = sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((pair_units < max_clusters ? pair_units : max_clusters) * 2));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI>, ta, tb, pg));
+    return SRGPT_OK;
+  }
   int bn, cl;
   pick_cfg(p.M, p.N, &bn, &cl);
   CUtensorMap ta, tb;
@@ -722,6 +974,10 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     pg.gm = g < 1 ? 1 : (g < tiles_mu ? g : tiles_mu);
   }
   if (gm_env > 0) pg.gm = gm_env < tiles_mu ? gm_env : tiles_mu;
+  // MEASURED HARMFUL (profiles/r01_microbench_gemm_l2pf.txt: 8288x28672x4096 0.81 -> 0.67 of peak, ViT fc2 0.51 -> 0.29 with
+  // a distance of 8 or 16 k-blocks): the prefetch requests compete with the loads for the same L2 -> SM path.  Opt-in only.
+  static const int pf_env = env_int("SRGPT_GEMM_L2PF");  // > 0: distance in k-blocks
+  pg.l2_prefetch = pf_env > 0 ? pf_env : 0;
   const int max_clusters = sm_count() / cl;
   const int grid = (units < max_clusters ? units : max_clusters) * cl;
   if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, pg, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, pg, grid, stream);
@@ -756,6 +1012,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
   if (bias != nullptr) SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 
   gemm::Params p;
+  p.gm = 0; p.l2_prefetch = 0;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc;
   p.bias = reinterpret_cast<const bf16*>(bias);
   p.residual = reinterpret_cast<const bf16*>(residual);

@@ -75,7 +75,7 @@ if "gemv" in which:
         emit(name, ms, best, bytes_=N * K * 2, N=N, K=K)
 
 if "maskpool" in which:
-    for (n, side, C, M) in [(1, 128, 1152, 8), (1, 128, 1152, 16), (4, 128, 1152, 4), (1, 32, 1152, 8)]:
+    for (n, side, C, M) in [(1, 128, 1152, 8), (1, 128, 1152, 16), (4, 128, 1152, 4), (32, 128, 1152, 4), (1, 32, 1152, 8), (32, 32, 1152, 4)]:
         L = side * side
         x = rnd(n, L, C)
         masks = (torch.rand(n, M, 448, 448, device=dev) > 0.5).float()
@@ -89,9 +89,10 @@ if "maskpool" in which:
         emit(f"mask_pool n{n} L{L} C{C} M{M} (box masks)", ms, best, bytes_=algo)
         ms, best = timeit(lambda: ops.mask_weights(masks, side, ops.ORDER_NESTED if side % 4 == 0 else 0))
         emit(f"mask_weights n{n} M{M} 448->{side}", ms, best, bytes_=n * M * (448 * 448 * 4 + L * 2))
-    x = rnd(1, 128 * 128, 1152)
-    ms, best = timeit(lambda: ops.adaptive_avgpool(x, 128, 27, ops.ORDER_NESTED))
-    emit("adaptive_avgpool 128->27 C1152", ms, best, bytes_=128 * 128 * 1152 * 2 + 729 * 1152 * 2)
+    for n in (1, 32):
+        x = rnd(n, 128 * 128, 1152)
+        ms, best = timeit(lambda: ops.adaptive_avgpool(x, 128, 27, ops.ORDER_NESTED))
+        emit(f"adaptive_avgpool n{n} 128->27 C1152", ms, best, bytes_=n * (128 * 128 * 1152 * 2 + 729 * 1152 * 2))
 
 if "gemm" in which:
     for (M, N, K, epi) in [(2048, 3456, 1152, ops.EPI_BIAS), (2048, 4304, 1152, ops.EPI_BIAS_GELU_TANH), (2048, 1152, 4304, ops.EPI_BIAS_RESIDUAL),
