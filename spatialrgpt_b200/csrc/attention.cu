@@ -261,19 +261,26 @@ rope_kv_append_kernel(bf16* __restrict__ qkv, int n_heads, int n_kv_heads, int h
   const int page = page_table[pos / page_size], slot = pos % page_size;
   bf16* kdst = kv_pages + (((size_t)page * 2 + 0) * page_size + slot) * n_kv_heads * hd;
   bf16* vdst = kv_pages + (((size_t)page * 2 + 1) * page_size + slot) * n_kv_heads * hd;
-  const int nrot = (n_heads + n_kv_heads) * half;
-  for (int i = threadIdx.x; i < nrot; i += blockDim.x) {
-    const int h = i / half, d = i % half;
+  // 16-byte units: 8 channels of the first half of a head together with the matching 8 of the second half
+  const int upc = half >> 3;  // units per head
+  const int nunits = (n_heads + n_kv_heads) * upc;
+  for (int i = threadIdx.x; i < nunits; i += blockDim.x) {
+    const int h = i / upc, d = (i % upc) << 3;
     bf16* p = r + h * hd;
-    float o1, o2;
-    rope_pair(__bfloat162float(p[d]), __bfloat162float(p[d + half]), __bfloat162float(ct[d]), __bfloat162float(st[d]), o1, o2);
-    const bf16 b1 = __float2bfloat16_rn(o1), b2 = __float2bfloat16_rn(o2);
-    p[d] = b1;
-    p[d + half] = b2;
+    float x1[8], x2[8], c[8], sn[8], o1[8], o2[8];
+    unpack8(*reinterpret_cast<const uint4*>(p + d), x1);
+    unpack8(*reinterpret_cast<const uint4*>(p + d + half), x2);
+    unpack8(*reinterpret_cast<const uint4*>(ct + d), c);
+    unpack8(*reinterpret_cast<const uint4*>(st + d), sn);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) rope_pair(x1[t], x2[t], c[t], sn[t], o1[t], o2[t]);
+    const uint4 b1 = pack8(o1), b2 = pack8(o2);
+    *reinterpret_cast<uint4*>(p + d) = b1;
+    *reinterpret_cast<uint4*>(p + d + half) = b2;
     if (h >= n_heads) {
       const int kh = h - n_heads;
-      kdst[kh * hd + d] = b1;
-      kdst[kh * hd + d + half] = b2;
+      *reinterpret_cast<uint4*>(kdst + kh * hd + d) = b1;
+      *reinterpret_cast<uint4*>(kdst + kh * hd + d + half) = b2;
     }
   }
   const bf16* vsrc = r + (n_heads + n_kv_heads) * hd;

@@ -89,6 +89,63 @@ layernorm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w
   }
 }
 
+// LayerNorm for short rows (cols <= 1280, e.g. the 1152 channels of SigLIP): one WARP per row, rows strided over a fixed
+// grid.  The CTA-per-row kernel above moved a 64-image tower's 65536 x 1152 activations at 0.34 of the HBM peak (137 us per
+// call, 53 calls per request batch): a 2.3 KB row per 128-thread CTA leaves too few bytes in flight and pays two block
+// reductions.  Here a lane holds up to 5 16-byte chunks, reductions are warp shuffles, 64 warps per SM stream rows.
+constexpr int LNW_WARPS = 8;
+__global__ void __launch_bounds__(LNW_WARPS * 32)
+layernorm_warp_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ weight, const bf16* __restrict__ bias,
+                      bf16* __restrict__ y, int ldy, int rows, int cols, float eps, int act) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nchunk = cols >> 3;
+  const float inv_cols = 1.f / (float)cols;
+  for (int row = blockIdx.x * LNW_WARPS + warp; row < rows; row += gridDim.x * LNW_WARPS) {
+    float v[LN_MAXV][8];
+    float sum = 0.f;
+    const bf16* xr = x + (size_t)row * ldx;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        unpack8(ld_stream16(xr + (c << 3)), v[i]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sum += v[i][t];
+      }
+    }
+    const float mean = warp_sum(sum) * inv_cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      if (lane + i * 32 < nchunk) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float d = v[i][t] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_cols + eps);
+    bf16* yr = y + (size_t)row * ldy;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        float w[8], b[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(weight + (c << 3)), w);
+        unpack8(*reinterpret_cast<const uint4*>(bias + (c << 3)), b);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float r = (v[i][t] - mean) * rstd * w[t] + b[t];
+          if (act == 1) r = gelu_erf(bf16_round(r));
+          o[t] = r;
+        }
+        *reinterpret_cast<uint4*>(yr + (c << 3)) = pack8(o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RMSNorm (Llama): y = weight * bf16(x * rsqrt(mean(x^2) + eps))
 // ---------------------------------------------------------------------------------------------
@@ -202,6 +259,15 @@ extern "C" __attribute__((visibility("default"))) int srgpt_layernorm_bf16(const
   SRGPT_CHECK_ARG((ldx % 8) == 0 && (ldy % 8) == 0 && ldx >= cols && ldy >= cols);
   SRGPT_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(bias) && aligned16(y));
   SRGPT_CHECK_ARG(act == 0 || act == 1);
+  if (cols <= 32 * LN_MAXV * 8 && rows >= 4 * LNW_WARPS) {  // short rows: one warp per row
+    const int ctas = ceil_div(rows, LNW_WARPS);
+    const int grid = ctas < sm_count() * 8 ? ctas : sm_count() * 8;
+    layernorm_warp_kernel<<<grid, LNW_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),
+        reinterpret_cast<bf16*>(y), ldy, rows, cols, eps, act);
+    SRGPT_CHECK_LAUNCH();
+    return SRGPT_OK;
+  }
   DownsampleGather g{0, 0, 0, 0};
   layernorm_kernel<false><<<rows, LN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(weight), reinterpret_cast<const bf16*>(bias),

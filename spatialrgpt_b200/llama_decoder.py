@@ -62,6 +62,22 @@ class PagedKVCache:
             own.extend(new)
             self.page_tables[seq, start:start + add] = torch.tensor(new, dtype=torch.int32)
 
+    def reserve_many(self, n_tokens: List[int]) -> None:
+        """reserve() for sequences 0..len-1 with ONE host->device copy of the page tables (a 32-request batch otherwise issues
+        32 tiny copies between the encoders and the prefill)."""
+        host = torch.zeros((len(n_tokens), self.page_tables.shape[1]), dtype=torch.int32)
+        for seq, n in enumerate(n_tokens):
+            need = (n + PAGE_SIZE - 1) // PAGE_SIZE
+            if need > self.max_pages_per_seq:
+                raise RuntimeError(f"sequence needs {need} KV pages > capacity {self.max_pages_per_seq}")
+            own = self.owned[seq]
+            if need > len(own):
+                if need - len(own) > len(self.free):
+                    raise RuntimeError("KV cache exhausted")
+                own.extend(self.free.pop() for _ in range(need - len(own)))
+            host[seq, :len(own)] = torch.tensor(own, dtype=torch.int32)
+        self.page_tables[:len(n_tokens)].copy_(host, non_blocking=True)
+
     def release(self, seq: int) -> None:
         self.free.extend(reversed(self.owned[seq]))
         self.owned[seq] = []
@@ -271,8 +287,7 @@ class LlamaDecoder:
         for b in range(len(self.cache.owned)):
             self.cache.release(b)
         self.ensure_capacity(B, max(seq_lens) + max_new_tokens)
-        for b in range(B):
-            self.cache.reserve(b, seq_lens[b] + max_new_tokens)
+        self.cache.reserve_many([n + max_new_tokens for n in seq_lens])
         hidden = self.prefill_packed(packed_embeds, seq_lens)
         first, lg = self.first_tokens(hidden, seq_lens, return_logits=True)
         outs, all_logits = [], []
