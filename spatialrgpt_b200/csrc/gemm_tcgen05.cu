@@ -295,8 +295,8 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
 // pulled from L2 per CTA and k-block drop from 16+BN/8 KB... (A + B) to A + B/2 — the quantity that bounds this kernel.
 // A stage may be refilled only after BOTH CTAs' MMAs have read it, hence the multicast tcgen05.commit on the
 // empty barriers (count CL).
-template <int EPI, int BN, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, int BN, int CL, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
@@ -332,7 +332,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < ACC_BUFS; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[a]), EW);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -426,7 +426,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // With short K (SigLIP: 18 k-blocks) the epilogue of a tile costs as many issue slots as its main loop, and one
     // warp per scheduler cannot hide the TMEM / global latencies -> two warps per lane group, half the columns each.
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
-    const int chalf = (warp - 2) >> 2;  // 0: columns [0, BN/2), 1: columns [BN/2, BN)
+    // EW / 4 warps share a lane group; each owns a contiguous share of the tile's 32-column chunks
+    constexpr int CPW = (BN / 32) / (EW / 4);
+    const int cpart = (warp - 2) >> 2;
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = cid; unit < num_units; unit += ncl) {
       int mu, nt;
@@ -437,7 +439,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_after();
       const int row = m0 + lg * 32 + lane;
 #pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      for (int c = cpart * CPW; c < (cpart + 1) * CPW; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -517,8 +519,8 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
                : "memory");
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES, STAGE_BYTES = PAIR_STAGE_BYTES, TMEM_COLS = ACC_BUFS * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -549,7 +551,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < ACC_BUFS; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * NUM_EPI_WARPS);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * EW);
     }
     fence_barrier_init();
   }
@@ -609,7 +611,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue warps (2..9), both CTAs: rows of this CTA's 128 x 256 accumulator =====================
     const int lg = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    constexpr int CPW = (BN / 32) / (EW / 4);
+    const int cpart = (warp - 2) >> 2;
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = cid; unit < num_units; unit += ncl) {
       int mu, nt;
@@ -620,7 +623,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tcgen05_fence_after();
       const int row = m0 + lg * 32 + lane;
 #pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      for (int c = cpart * CPW; c < (cpart + 1) * CPW; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
@@ -828,17 +831,41 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, 
   return SRGPT_OK;
 }
 
+// Epilogue warps: 8 by default (two per TMEM lane group).  A 16-warp epilogue (four per lane group, SRGPT_GEMM_EW=16; the
+// erf-GELU epilogue's 116 registers do not fit the 96-register budget of an 18-warp CTA and stays at 8) was built to shorten
+// the per-tile latency chain of the short-K ViT GEMMs and MEASURED (profiles/r01_microbench_gemm_ew.txt): out_proj +
+// residual 0.33 -> 0.37 of peak, but qkv 0.70 -> 0.62 and fc1 0.62 -> 0.56, Llama shapes unchanged -> not the default.
+static int env_int(const char* name);
+
+template <int EPI>
+struct EpiWarps {
+  static constexpr int N = EPI == SRGPT_EPI_BIAS_GELU_ERF ? 8 : 16;
+};
+static int epi_warps_env() {
+  static const int v = env_int("SRGPT_GEMM_EW");  // 16 selects the 16-warp epilogue where it exists
+  return v;
+}
+
+template <int EPI, int BN, int CL, int EW>
+static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream);
+
 template <int EPI, int BN, int CL>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+  if (EpiWarps<EPI>::N == 16 && epi_warps_env() == 16) return launch_cfg_ew<EPI, BN, CL, 16>(ta, tb, p, grid, stream);
+  return launch_cfg_ew<EPI, BN, CL, 8>(ta, tb, p, grid, stream);
+}
+
+template <int EPI, int BN, int CL, int EW>
+static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI, BN, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(64 + 32 * EW);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -848,7 +875,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, BN, CL>, ta, tb, p));
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, BN, CL, EW>, ta, tb, p));
   return SRGPT_OK;
 }
 
@@ -934,15 +961,17 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
       pg.gm = g < 1 ? 1 : (g < tiles_mu ? g : tiles_mu);
     }
     pg.l2_prefetch = 0;
-    static bool configured[8] = {false, false, false, false, false, false, false, false};
-    if (!configured[EPI]) {
-      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-      configured[EPI] = true;
+    const bool ew16 = EpiWarps<EPI>::N == 16 && epi_warps_env() == 16;
+    static bool configured = false;
+    if (!configured) {
+      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, EpiWarps<EPI>::N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+      configured = true;
     }
     const int max_clusters = sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((pair_units < max_clusters ? pair_units : max_clusters) * 2));
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(64 + 32 * (ew16 ? 16 : 8));
     cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -952,7 +981,8 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI>, ta, tb, pg));
+    if (ew16) SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, EpiWarps<EPI>::N>, ta, tb, pg));
+    else SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, 8>, ta, tb, pg));
     return SRGPT_OK;
   }
   int bn, cl;

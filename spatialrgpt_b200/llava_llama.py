@@ -98,6 +98,30 @@ class LlavaLlamaModel:
         """llava_arch.py:307-310 (tower -> projector, no regions)."""
         return self.mm_projector(self.vision_tower(images))
 
+    def _start_host_copies(self, tensors):
+        """Device tensors -> pinned host copies on a side stream (None entries pass through).  Returns (host tensors, event):
+        the caller synchronises the event, not the compute stream."""
+        out, any_dev = [], False
+        side = getattr(self, "_side_stream", None)
+        for t in tensors:
+            if t is None or not t.is_cuda:
+                out.append(None if t is None else t.detach())
+                continue
+            if side is None:
+                side = self._side_stream = torch.cuda.Stream(device=self.device)
+            if not any_dev:
+                side.wait_stream(torch.cuda.current_stream())
+                any_dev = True
+            with torch.cuda.stream(side):
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t.detach(), non_blocking=True)
+            out.append(h)
+        if not any_dev:
+            return out, None
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return out, ev
+
     def _tokens_per_image(self) -> int:
         """Rows one <image> slot expands to: the projector's 2x2 down-sampling of the 27x27 refined map (regions on) or of the
         tower grid (base_projector.py:32-52)."""
@@ -143,13 +167,18 @@ class LlavaLlamaModel:
             return input_ids, position_ids, attention_mask, past_key_values, None, labels  # llava_arch.py:355-385
         cfg = self.config
         dev = self.device
-        # The splice plan needs only host-side facts (token ids, images / regions per request), so it is built BEFORE the
-        # encoders are launched: the id copy below is the only device->host read, and with it up front the host never waits
-        # on the tower and the GPU never waits on this Python loop (it cost ~15 % of a 32-request batch when it came after).
-        ids_cpu = input_ids.detach().to("cpu", torch.int64)
+        # The splice plan needs only host-side facts (token ids, images / regions per request).  Order of events: (1) the ids
+        # (and masks / labels) start their device->host copy on a side stream, (2) the encoders are launched, (3) the host
+        # builds the plan while the GPU runs the tower, (4) plan upload + one gather kernel.  The host never waits on the tower
+        # and the GPU never waits on the Python loop below (it cost ~15 % of a 32-request batch when it came in between).
+        host_copies, copy_done = self._start_host_copies([input_ids, attention_mask, labels])
+        encoded = self._encode_multimodal(images, masks, depths)
+        if copy_done is not None:
+            copy_done.synchronize()
+        ids_cpu = host_copies[0].to(torch.int64)
         B, T = ids_cpu.shape
-        am_cpu = torch.ones((B, T), dtype=torch.bool) if attention_mask is None else attention_mask.detach().to("cpu").bool()
-        lab_cpu = torch.full((B, T), IGNORE_INDEX, dtype=torch.int64) if labels is None else labels.detach().to("cpu", torch.int64)
+        am_cpu = torch.ones((B, T), dtype=torch.bool) if attention_mask is None else host_copies[1].bool()
+        lab_cpu = torch.full((B, T), IGNORE_INDEX, dtype=torch.int64) if labels is None else host_copies[2].to(torch.int64)
         if isinstance(images, (list, tuple)):
             n_img = sum(im.shape[0] if im.dim() == 4 else 1 for im in images)
         else:
@@ -213,8 +242,8 @@ class LlavaLlamaModel:
         lens = [int(x.numel()) for x in plan_sid]
         sid_dev, srow_dev = torch.cat(plan_sid).to(dev, non_blocking=True), torch.cat(plan_srow).to(dev, non_blocking=True)
 
-        # ---- encoders (GPU), then ONE gather kernel builds the embeddings of the whole batch
-        image_features, mask_embeds, depth_embeds = self._encode_multimodal(images, masks, depths)
+        # ---- ONE gather kernel builds the embeddings of the whole batch from the encoder outputs
+        image_features, mask_embeds, depth_embeds = encoded
         if tuple(image_features.shape[:2]) != (n_img, n_tok):
             raise RuntimeError(f"splice plan expected {(n_img, n_tok)} image tokens, encoders produced {tuple(image_features.shape[:2])}")
         H = image_features.shape[2]

@@ -98,7 +98,8 @@ def test_gemm_cluster_multicast_path():
         "print('CLUSTER_OK')\n")
     # 2-CTA shared weight tile; 4-CTA shared activation tile (M <= 384); grouped tile rasterisation (3 m-units per group)
     # ... and the CTA-pair kernel (tcgen05 cta_group::2, one 256 x 256 tile per 2-CTA cluster) forced on for every shape
-    for knob, val in (("SRGPT_GEMM_CL", "2"), ("SRGPT_GEMM_TALL", "1"), ("SRGPT_GEMM_GM", "3"), ("SRGPT_GEMM_PAIR", "1")):
+    for knob, val in (("SRGPT_GEMM_CL", "2"), ("SRGPT_GEMM_TALL", "1"), ("SRGPT_GEMM_GM", "3"), ("SRGPT_GEMM_PAIR", "1"),
+                      ("SRGPT_GEMM_EW", "16")):
         env = dict(os.environ, **{knob: val})
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

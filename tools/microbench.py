@@ -101,7 +101,8 @@ if "gemm" in which:
                            (8288, 6144, 4096, ops.EPI_NONE), (8288, 28672, 4096, ops.EPI_SWIGLU), (8288, 4096, 14336, ops.EPI_BIAS_RESIDUAL),
                            (8192, 8192, 8192, ops.EPI_NONE), (8288, 4096, 4096, ops.EPI_BIAS_RESIDUAL),
                            (65536, 3456, 1152, ops.EPI_BIAS), (65536, 4304, 1152, ops.EPI_BIAS_GELU_TANH), (65536, 1152, 4304, ops.EPI_BIAS_RESIDUAL),
-                           (65536, 1152, 1152, ops.EPI_BIAS_RESIDUAL)]:
+                           (65536, 1152, 1152, ops.EPI_BIAS_RESIDUAL), (65536, 1152, 1152, ops.EPI_NONE), (65536, 1152, 1152, ops.EPI_BIAS),
+                           (65536, 1280, 1152, ops.EPI_NONE), (65536, 4304, 1152, ops.EPI_BIAS)]:
         a, w = rnd(M, K), rnd(N, K)
         bias = rnd(N) if epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU_TANH, ops.EPI_BIAS_GELU_ERF, ops.EPI_BIAS_RESIDUAL) else None
         n_out = N // 2 if epi == ops.EPI_SWIGLU else N
