@@ -215,30 +215,6 @@ def run_ours(args):
     ms_ttft, _ = timed(step_ttft, args.steps)
     ttft_ms = ms_ttft / args.steps
 
-    # ---- config c3: batch of 32 images x 4 regions, prefill only (generate(max_new_tokens=1)): every GEMM of the tower and
-    #      of the Llama prefill runs over the whole batch (64 x 1024 ViT rows, 32 x 259 prompt rows) -> tensor-core bound
-    c3 = None
-    if not args.no_c3:
-        b_ids, b_img, b_dep, b_msk = make_batch(cfg, C3_BATCH, C3_REGIONS, 4321 + rank)
-        b_ids, b_img, b_dep = b_ids.to(dev), b_img.to(dev), b_dep.to(dev)
-        b_msk = [m.to(dev) for m in b_msk]
-
-        def step_c3():
-            return model.generate(b_ids, images=b_img, depths=b_dep, masks=b_msk, do_sample=False, max_new_tokens=1)
-        for _ in range(2):
-            step_c3()
-        l0 = ops.LAUNCHES
-        ms_c3, n_c3 = timed(step_c3, args.steps)
-        c3_launches = (ops.LAUNCHES - l0) // args.steps
-        c3_ms = ms_c3 / args.steps
-        c3_flops = C3_BATCH * nums["flops_ttft"]
-        c3 = {"workload": f"c3: {C3_BATCH} images x {C3_REGIONS} mask regions, depth ON, 64-token prompts, prefill + first token, per GPU",
-              "ms_per_batch": round(c3_ms, 2), "algorithmic_tflop": round(c3_flops / 1e12, 2),
-              "tflops_per_gpu": round(c3_flops / c3_ms / 1e9, 1), "peak_tflops": tensor_peak,
-              "frac_tensor": round(c3_flops / c3_ms / 1e9 / tensor_peak, 4), "requests_per_s": round(C3_BATCH * world / (c3_ms / 1e3), 1),
-              "gpu_launches_per_batch": int(c3_launches)}
-        del b_ids, b_img, b_dep, b_msk
-
     # ---- per-kernel roofline of the dominant kernel, timed live with CUDA events: the gate/up GEMV
     roof = None
     if rank == 0:
@@ -272,6 +248,30 @@ def run_ours(args):
                 "traffic": ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": nums["gateup_bytes"], "avg_launch_ms": round(avg_ms, 5),
                 "decode_step": {"ms": round(step_ms, 4), "algorithmic_GBps": round(step_bytes / step_ms / 1e6, 1),
                                 "frac_hbm": round(step_bytes / step_ms / 1e6 / hbm_peak, 4), "kernels": llm.kernels_per_decode_step}}
+
+    # ---- config c3: batch of 32 images x 4 regions, prefill only (generate(max_new_tokens=1)): every GEMM of the tower and
+    #      of the Llama prefill runs over the whole batch (64 x 1024 ViT rows, 32 x 259 prompt rows) -> tensor-core bound
+    c3 = None
+    if not args.no_c3:
+        b_ids, b_img, b_dep, b_msk = make_batch(cfg, C3_BATCH, C3_REGIONS, 4321 + rank)
+        b_ids, b_img, b_dep = b_ids.to(dev), b_img.to(dev), b_dep.to(dev)
+        b_msk = [m.to(dev) for m in b_msk]
+
+        def step_c3():
+            return model.generate(b_ids, images=b_img, depths=b_dep, masks=b_msk, do_sample=False, max_new_tokens=1)
+        for _ in range(2):
+            step_c3()
+        l0 = ops.LAUNCHES
+        ms_c3, n_c3 = timed(step_c3, args.steps)
+        c3_launches = (ops.LAUNCHES - l0) // args.steps
+        c3_ms = ms_c3 / args.steps
+        c3_flops = C3_BATCH * nums["flops_ttft"]
+        c3 = {"workload": f"c3: {C3_BATCH} images x {C3_REGIONS} mask regions, depth ON, 64-token prompts, prefill + first token, per GPU",
+              "ms_per_batch": round(c3_ms, 2), "algorithmic_tflop": round(c3_flops / 1e12, 2),
+              "tflops_per_gpu": round(c3_flops / c3_ms / 1e9, 1), "peak_tflops": tensor_peak,
+              "frac_tensor": round(c3_flops / c3_ms / 1e9 / tensor_peak, 4), "requests_per_s": round(C3_BATCH * world / (c3_ms / 1e3), 1),
+              "gpu_launches_per_batch": int(c3_launches)}
+        del b_ids, b_img, b_dep, b_msk
 
     if rank != 0:
         if world > 1:
