@@ -178,6 +178,7 @@ struct Params {
   int out_fp32;
   int gm;                  // rasterisation: m-units per group (see unit_to_tile)
   int l2_prefetch;         // k-blocks the producer prefetches into L2 ahead of its loads (0 = off)
+  int res_prefetch;        // 1: residual rows are requested before the accumulator wait
 };
 
 // Tile order.  Units are walked group by group; a group is `gm` vertically adjacent m-units x ALL n-tiles, inside a group the
@@ -196,7 +197,7 @@ __device__ __forceinline__ void unit_to_tile(int unit, int tiles_mu, int tiles_n
 }
 
 template <int EPI>
-__device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, const Params& p, int row, int col0) {
+__device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, const Params& p, int row, int col0, const uint4* pre_res = nullptr) {
   // v[j] is the fp32 accumulator of column col0 + j.  Rounding points mirror the reference's
   // sequence of bf16 torch ops (linear -> activation -> residual add), see DESIGN.md.
   if (EPI == SRGPT_EPI_NONE) return;
@@ -229,7 +230,8 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         if (col0 + j + 8 <= p.N) {
-          uint4 b = *reinterpret_cast<const uint4*>(rp + j);
+          // the residual chunk was requested before the accumulator wait when the whole 32-column chunk is inside N
+          uint4 b = (pre_res != nullptr && p.res_prefetch && col0 + 32 <= p.N) ? pre_res[j >> 3] : *reinterpret_cast<const uint4*>(rp + j);
           float f[8];
           unpack8(b, f);
 #pragma unroll
@@ -245,7 +247,7 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
 
 // one thread's 32 consecutive accumulator columns of one output row: fused epilogue + 16-byte stores
 template <int EPI>
-__device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, int row, int col0) {
+__device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, int row, int col0, const uint4* pre_res = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -267,7 +269,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
         if ((col0 >> 1) + j < ncols_out) cp[j] = __float2bfloat16_rn(o[j]);
     }
   } else {
-    apply_epilogue<EPI>(v, p, row, col0);
+    apply_epilogue<EPI>(v, p, row, col0, pre_res);
     if (p.out_fp32) {
       float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
       if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
@@ -286,6 +288,25 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
       }
+    }
+  }
+}
+
+// Residual rows of one thread's chunks (CPW chunks of 32 columns), requested BEFORE the wait on the accumulator: the addresses
+// depend only on the tile index, so the global-load latency (the longest link of the epilogue chain of the short-K ViT
+// GEMMs: out_proj ran at 0.38 of peak with the residual against 0.58 without) hides behind the tile's main loop.
+template <int EPI, int CPW>
+__device__ __forceinline__ void prefetch_residual(uint4 (&pre)[CPW][4], const Params& p, int row, int n0, int c_first) {
+  if (EPI != SRGPT_EPI_BIAS_RESIDUAL) return;
+  if (p.residual == nullptr || row >= p.M || !p.res_prefetch) return;
+  const int rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
+#pragma unroll
+  for (int ci = 0; ci < CPW; ++ci) {
+    const int col0 = n0 + (c_first + ci) * 32;
+    if (col0 + 32 <= p.N) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)rrow * p.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[ci][j] = rp[j];
     }
   }
 }
@@ -435,17 +456,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
       const int m0 = (mu * CL + crank) * BM;
       const int n0 = nt * BN;
+      const int row = m0 + lg * 32 + lane;
+      uint4 pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1][4];
+      if (EPI == SRGPT_EPI_BIAS_RESIDUAL) prefetch_residual<EPI, (EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1)>(pre, p, row, n0, cpart * CPW);
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + lg * 32 + lane;
-#pragma unroll 1
-      for (int c = cpart * CPW; c < (cpart + 1) * CPW; ++c) {
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c = cpart * CPW + ci;
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
         tmem_ld_wait();
-        if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+        if (row < p.M) store_chunk<EPI>(r, p, row, col0, EPI == SRGPT_EPI_BIAS_RESIDUAL ? pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? ci : 0] : nullptr);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -619,17 +643,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       unit_to_tile(unit, tiles_mu, tiles_n, p.gm, mu, nt);
       const int m0 = (mu * 2 + crank) * BM;
       const int n0 = nt * BN;
+      const int row = m0 + lg * 32 + lane;
+      uint4 pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1][4];
+      if (EPI == SRGPT_EPI_BIAS_RESIDUAL) prefetch_residual<EPI, (EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1)>(pre, p, row, n0, cpart * CPW);
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + lg * 32 + lane;
-#pragma unroll 1
-      for (int c = cpart * CPW; c < (cpart + 1) * CPW; ++c) {
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c = cpart * CPW + ci;
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
         tmem_ld_wait();
-        if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+        if (row < p.M) store_chunk<EPI>(r, p, row, col0, EPI == SRGPT_EPI_BIAS_RESIDUAL ? pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? ci : 0] : nullptr);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1043,6 +1070,8 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
 
   gemm::Params p;
   p.gm = 0; p.l2_prefetch = 0;
+  static const bool no_respf = getenv("SRGPT_GEMM_NO_RESPF") != nullptr && getenv("SRGPT_GEMM_NO_RESPF")[0] == '1';
+  p.res_prefetch = no_respf ? 0 : 1;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc;
   p.bias = reinterpret_cast<const bf16*>(bias);
   p.residual = reinterpret_cast<const bf16*>(residual);
