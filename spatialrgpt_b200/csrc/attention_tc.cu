@@ -17,13 +17,16 @@
 //   warps 2..9  softmax: thread pair (w, w+4) owns one q row, each thread half of the kv columns.  Online softmax in
 //               base 2 (ex2.approx on the SFU); every tile's O_j is a FRESH TMEM accumulator that the threads fold into
 //               registers (o = o * alpha + O_j), so TMEM is never rescaled and no correction pass exists.
-// Measured (B200, 64 images x 16 heads x 1024 tokens, head_dim 72): 0.955 ms = 324 TFLOP/s vs 1.55 ms for the mma.sync kernel;
+// Measured (B200, 64 images x 16 heads x 1024 tokens, head_dim 72): 0.826 ms = 374 TFLOP/s vs 1.55 ms for the mma.sync kernel
+// (0.955 ms before the third K stage);
 // ncu: ~1500 clk per 128x128 tile, XU (ex2) pipe 34 %, tensor pipe 21 %, issue slots 36 % - a latency chain per tile
 // (TMEM load -> max -> exchange -> 64 ex2 -> pack -> st.shared -> fence -> arrive) on 2 warps per scheduler.  A variant
 // with FOUR threads per row (16 softmax warps, 96 registers, two-pass S reads) measured 1.03 ms at head_dim 72 and
 // 0.168 vs 0.196 ms at head_dim 128 / 32 prompts; the two-thread version is kept.  Next: ex2 emulation on the FMA pipe
 // for a share of the columns and packed f32x2 arithmetic.
 // UMMA descriptor encodings (MN-major, 32B swizzle, OOB fill) were verified with tools/umma_probe.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "srgpt_b200.h"
 #include "tcgen05.cuh"
@@ -39,8 +42,9 @@ constexpr int NTHREADS = 64 + 32 * SM_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr int O_COL = 256;  // S buffers at columns [0, 2*BN), O buffers at 256 and 384
 
-enum Bar { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 6, V_FULL = 8, V_EMPTY = 10, S_FULL = 12, S_EMPTY = 14, P_FULL = 16, P_EMPTY = 18,
-           O_FULL = 20, O_EMPTY = 22, NUM_BARS = 24 };
+constexpr int KST = 3;  // K ring depth (measured: 0.955 ms -> 0.826 ms against two stages; shared memory has no room for a third V stage)
+enum Bar { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 7, V_FULL = 10, V_EMPTY = 12, S_FULL = 14, S_EMPTY = 16, P_FULL = 18, P_EMPTY = 20,
+           O_FULL = 22, O_EMPTY = 24, NUM_BARS = 26 };
 
 template <int HD, int BN>
 struct Geo {
@@ -53,7 +57,7 @@ struct Geo {
   static constexpr int Q_C0 = BM * 128, Q_BYTES = Q_C0 + BM * ROWB1;
   static constexpr int KV_C0 = BN * 128, KV_BYTES = KV_C0 + BN * ROWB1;
   static constexpr int P_BYTES = BM * BN * 2;
-  static constexpr int OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + 2 * KV_BYTES, OFF_P = OFF_V + 2 * KV_BYTES, OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KST * KV_BYTES, OFF_P = OFF_V + 2 * KV_BYTES, OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int OFF_RED = OFF_BAR + NUM_BARS * 8 + 16;
   static constexpr int SMEM_BYTES = OFF_RED + 3 * 2 * BM * 4 + 1024;  // + alignment slack
   static constexpr int V_ADV1 = 16 * ROWB1;                // bytes per UMMA_K step (16 kv rows) of V chunk 1
@@ -71,6 +75,7 @@ struct Params {
   float scale_log2;
   bf16* out;
   int o_ld;
+  int s_ahead;  // tiles the S = Q K^T stream may run ahead of P V (1 or 2)
 };
 
 struct Work {
@@ -138,8 +143,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(Q_FULL + i), 1);
       mbar_init(bar(Q_EMPTY + i), 1);
-      mbar_init(bar(K_FULL + i), 1);
-      mbar_init(bar(K_EMPTY + i), 1);
       mbar_init(bar(V_FULL + i), 1);
       mbar_init(bar(V_EMPTY + i), 1);
       mbar_init(bar(S_FULL + i), 1);
@@ -148,6 +151,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
       mbar_init(bar(P_EMPTY + i), 1);
       mbar_init(bar(O_FULL + i), 1);
       mbar_init(bar(O_EMPTY + i), SM_WARPS);
+    }
+    for (int i = 0; i < KST; ++i) {
+      mbar_init(bar(K_FULL + i), 1);
+      mbar_init(bar(K_EMPTY + i), 1);
     }
     fence_barrier_init();
   }
@@ -174,10 +181,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
           const int i = t & 1;
           const uint32_t ph = (t >> 1) & 1;
           const int row = k.row_base + j * BN;
-          mbar_wait(bar(K_EMPTY + i), ph ^ 1);
-          mbar_expect_tx(bar(K_FULL + i), G::KV_BYTES);
-          tma_load_3d(sbase + G::OFF_K + i * G::KV_BYTES, &maps.k0, bar(K_FULL + i), 0, kvh, row);
-          tma_load_3d(sbase + G::OFF_K + i * G::KV_BYTES + G::KV_C0, &maps.k1, bar(K_FULL + i), 64, kvh, row);
+          const int ik = t % KST;
+          const uint32_t phk = (t / KST) & 1;
+          mbar_wait(bar(K_EMPTY + ik), phk ^ 1);
+          mbar_expect_tx(bar(K_FULL + ik), G::KV_BYTES);
+          tma_load_3d(sbase + G::OFF_K + ik * G::KV_BYTES, &maps.k0, bar(K_FULL + ik), 0, kvh, row);
+          tma_load_3d(sbase + G::OFF_K + ik * G::KV_BYTES + G::KV_C0, &maps.k1, bar(K_FULL + ik), 64, kvh, row);
           mbar_wait(bar(V_EMPTY + i), ph ^ 1);
           mbar_expect_tx(bar(V_FULL + i), G::KV_BYTES);
           tma_load_3d(sbase + G::OFF_V + i * G::KV_BYTES, &maps.v0, bar(V_FULL + i), 0, kvh, row);
@@ -197,12 +206,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
       auto issue_s = [&](uint32_t tt, uint32_t item, bool first_of_item, bool last_of_item) {
         const int i = tt & 1, qi = item & 1;
         const uint32_t ph = (tt >> 1) & 1;
+        const int ik = tt % KST;
         if (first_of_item) mbar_wait(bar(Q_FULL + qi), (item >> 1) & 1);
-        mbar_wait(bar(K_FULL + i), ph);
+        mbar_wait(bar(K_FULL + ik), (tt / KST) & 1);
         mbar_wait(bar(S_EMPTY + i), ph ^ 1);
         tcgen05_fence_after();
         const uint32_t d = tmem_base + i * BN;
-        const uint32_t qa = sbase + qi * G::Q_BYTES, ka = sbase + G::OFF_K + i * G::KV_BYTES;
+        const uint32_t qa = sbase + qi * G::Q_BYTES, ka = sbase + G::OFF_K + ik * G::KV_BYTES;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(d, umma_desc(UMMA_DESC_SW128, qa + k * 32), umma_desc(UMMA_DESC_SW128, ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
         for (int k = 0; k < G::W1 / 16; ++k)
           umma_f16(d, umma_desc(G::F1, qa + G::Q_C0 + k * 32), umma_desc(G::F1, ka + G::KV_C0 + k * 32), idesc_s, 1u);
         umma_commit(bar(S_FULL + i));
-        umma_commit(bar(K_EMPTY + i));
+        umma_commit(bar(K_EMPTY + ik));
         if (last_of_item) umma_commit(bar(Q_EMPTY + qi));
       };
       auto issue_pv = [&](uint32_t tt) {
@@ -232,21 +242,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
         umma_commit(bar(P_EMPTY + i));
         umma_commit(bar(V_EMPTY + i));
       };
-      uint32_t t = 0, it = 0;
-      WorkIter<BN, CAUSAL> wi(p, n_work);
-      bool have = wi.next();
-      if (have) issue_s(0, 0, true, wi.k.n_tiles == 1);
-      while (have) {
-        const int n = wi.k.n_tiles;
-        for (int j = 0; j + 1 < n; ++j) {
-          issue_s(t + j + 1, it, false, j + 2 == n);
-          issue_pv(t + j);
+      // two cursors over the same tile stream: S = Q K^T is issued p.s_ahead tiles ahead of P V.  Measured in one run
+      // (64 images, head_dim 72): one tile ahead 0.826 ms, two tiles ahead (S_{t+2} queued as soon as the softmax warps
+      // have pulled S_t out of TMEM) 1.19 ms -> one is the default (SRGPT_ATTN_S_AHEAD=2 selects the other).  The K ring has
+      // three stages: with two, 0.955 ms.
+      WorkIter<BN, CAUSAL> ws(p, n_work), wp(p, n_work);
+      uint32_t ts = 0, its = 0;   // S cursor: global tile index, item index
+      int js = 0;                 // tile inside the S cursor's item
+      bool s_have = ws.next();
+      uint32_t tp = 0;            // P V cursor
+      bool p_have = wp.next();
+      int jp = 0;
+      while (p_have) {
+        while (s_have && ts <= tp + p.s_ahead) {  // s_ahead = 2: tiles tp+1 and tp+2 are in the two S buffers while P_tp V_tp is issued
+          issue_s(ts, its, js == 0, js + 1 == ws.k.n_tiles);
+          ++ts;
+          if (++js == ws.k.n_tiles) {
+            js = 0;
+            ++its;
+            s_have = ws.next();
+          }
         }
-        t += n;
-        have = wi.next();  // first S of the next item goes in before the last P V of this one
-        if (have) issue_s(t, it + 1, true, wi.k.n_tiles == 1);
-        issue_pv(t - 1);
-        ++it;
+        issue_pv(tp);
+        ++tp;
+        if (++jp == wp.k.n_tiles) {
+          jp = 0;
+          p_have = wp.next();
+        }
       }
     }
   } else {
@@ -446,6 +468,8 @@ static int launch(const void* q, const void* k, const void* v, void* out, int q_
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out);
   p.o_ld = o_ld;
+  static const int s_ahead_env = getenv("SRGPT_ATTN_S_AHEAD") ? atoi(getenv("SRGPT_ATTN_S_AHEAD")) : 0;
+  p.s_ahead = (s_ahead_env == 1 || s_ahead_env == 2) ? s_ahead_env : 1;
   const long long n_work = (long long)p.nqt * n_heads * batch;
   const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
   attn_fwd_tc_kernel<HD, BN, CAUSAL><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(maps, p);
