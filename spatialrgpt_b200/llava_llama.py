@@ -18,6 +18,7 @@ from .llama_decoder import LlamaDecoder
 from .multimodal_encoder import VisionTower
 from .multimodal_projector import MultimodalProjector
 from .region_extractor import RegionExtractor
+from .splice_plan import build_splice_plan
 from .weights import ModelWeights
 
 
@@ -186,61 +187,15 @@ class LlavaLlamaModel:
         n_tok = self._tokens_per_image()
         region_on = cfg.enable_region and self.region_extractor is not None
         depth_on = region_on and cfg.enable_depth and depths is not None
-        mask_list = list(masks) if masks is not None else [None] * n_img
-        counts = [0 if m is None else int(m.shape[0]) for m in mask_list] + [0] * max(0, n_img - len(mask_list))
-        has_embeds = [m is not None for m in mask_list] + [False] * max(0, n_img - len(mask_list))
-        moff = [0]
-        for c in counts[:n_img]:
-            moff.append(moff[-1] + c)
-        doff = moff  # depth embeds mirror the mask embeds (base_extractor.py:167-173)
-
-        plan_sid: List[torch.Tensor] = []
-        plan_srow: List[torch.Tensor] = []
-        new_labels: List[torch.Tensor] = []
-        cur_image_idx = 0
-        for b in range(B):
-            ids = ids_cpu[b][am_cpu[b]]
-            lab = lab_cpu[b][am_cpu[b]]
-            n = ids.shape[0]
-            src_id = torch.zeros(n, dtype=torch.int32)
-            src_row = ids.clamp(min=0).to(torch.int32)  # image slots -> token 0 (llava_arch.py:436), replaced below
-            img_pos = torch.where(ids == IMAGE_TOKEN_INDEX)[0].tolist()
-            if img_pos:
-                first_img = cur_image_idx
-                if region_on and has_embeds[first_img]:
-                    pos = torch.where(ids == cfg.llm_mask_token_id)[0]
-                    k = min(pos.numel(), moff[first_img + 1] - moff[first_img])
-                    if pos.numel() > k:
-                        print("Error: fewer mask embeds than <mask> tokens")  # llava_arch.py:476-477 (prints, no raise)
-                    src_id[pos[:k]] = 2
-                    src_row[pos[:k]] = torch.arange(moff[first_img], moff[first_img] + k, dtype=torch.int32)
-                elif cfg.enable_region and int((ids == cfg.llm_mask_token_id).sum()) > 0:
-                    print("Error: mask embed is None, but the num of <mask> is not 0!!!")
-                if depth_on and has_embeds[first_img]:
-                    pos = torch.where(ids == cfg.llm_depth_token_id)[0]
-                    k = min(pos.numel(), doff[first_img + 1] - doff[first_img])
-                    src_id[pos[:k]] = 3
-                    src_row[pos[:k]] = torch.arange(doff[first_img], doff[first_img] + k, dtype=torch.int32)
-            # expand every <image> slot into that image's n_tok feature rows
-            sid_parts, srow_parts, lab_parts = [], [], []
-            start = 0
-            for p in img_pos:
-                sid_parts.append(src_id[start:p]); srow_parts.append(src_row[start:p]); lab_parts.append(lab[start:p])
-                sid_parts.append(torch.full((n_tok,), 1, dtype=torch.int32))
-                srow_parts.append(torch.arange(cur_image_idx * n_tok, (cur_image_idx + 1) * n_tok, dtype=torch.int32))
-                lab_parts.append(torch.full((n_tok,), IGNORE_INDEX, dtype=torch.int64))
-                cur_image_idx += 1
-                start = p + 1
-            sid_parts.append(src_id[start:]); srow_parts.append(src_row[start:]); lab_parts.append(lab[start:])
-            plan_sid.append(torch.cat(sid_parts)); plan_srow.append(torch.cat(srow_parts))
-            new_labels.append(torch.cat(lab_parts))
-
-        max_model_len = getattr(cfg.llama, "tokenizer_model_max_length", None)
-        if max_model_len is not None:  # llava_arch.py:541-546 truncation
-            plan_sid = [x[:max_model_len] for x in plan_sid]
-            plan_srow = [x[:max_model_len] for x in plan_srow]
-        lens = [int(x.numel()) for x in plan_sid]
-        sid_dev, srow_dev = torch.cat(plan_sid).to(dev, non_blocking=True), torch.cat(plan_srow).to(dev, non_blocking=True)
+        mask_list = (list(masks) if masks is not None else []) + [None] * n_img
+        plan = build_splice_plan(ids_cpu, None if attention_mask is None else am_cpu, None if labels is None else lab_cpu, n_tok,
+                                 [0 if m is None else int(m.shape[0]) for m in mask_list[:n_img]], [m is not None for m in mask_list[:n_img]],
+                                 cfg.llm_mask_token_id, cfg.llm_depth_token_id, region_on, depth_on,
+                                 getattr(cfg.llama, "tokenizer_model_max_length", None))
+        for w in plan.warnings:
+            print(w)
+        lens, new_labels = plan.lens, plan.labels
+        sid_dev, srow_dev = plan.src_id.to(dev, non_blocking=True), plan.src_row.to(dev, non_blocking=True)
 
         # ---- ONE gather kernel builds the embeddings of the whole batch from the encoder outputs
         image_features, mask_embeds, depth_embeds = encoded
@@ -262,8 +217,6 @@ class LlavaLlamaModel:
             return None, None, attention_mask, past_key_values, None, None
         new_embeds = list(torch.split(packed, lens, 0))
 
-        if max_model_len is not None:
-            new_labels = [x[:max_model_len] for x in new_labels]
         max_len = max(x.shape[0] for x in new_embeds)
         left = getattr(cfg.llama, "tokenizer_padding_side", "right") == "left"
         out = torch.zeros((B, max_len, H), dtype=torch.bfloat16, device=dev)
