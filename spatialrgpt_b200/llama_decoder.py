@@ -42,7 +42,7 @@ class PagedKVCache:
         self.max_pages_per_seq = max_pages_per_seq
         self.pages = torch.zeros((dims.num_hidden_layers, n_pages, 2, PAGE_SIZE, dims.num_key_value_heads, dims.head_dim),
                                  dtype=torch.bfloat16, device=device)
-        # +1 column: the decode attention kernel speculatively reads the page id of row pos+1 (masked afterwards)
+        # +1 spare column (a measured-and-dropped decode-attention variant read the page id of row pos+1; kept so tables stay 16-byte padded)
         self.page_tables = torch.zeros((max_seqs, max_pages_per_seq + 1), dtype=torch.int32, device=device)
         self.free: List[int] = list(range(n_pages - 1, -1, -1))
         self.owned: List[List[int]] = [[] for _ in range(max_seqs)]
