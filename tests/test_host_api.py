@@ -137,3 +137,21 @@ def test_read_checkpoint_roundtrip(tmp_path):
     assert torch.equal(got["llm"]["lm_head.weight"][: oc.vocab], sd["llm"]["lm_head.weight"])
     with pytest.raises(NotImplementedError):
         builder.load_pretrained_model(root, "x", load_4bit=True)
+
+
+def test_bench_algorithmic_numbers_match_the_survey():
+    """bench.py's FLOP / byte model of config c2 equals SURVEY.md §8(d): 5.58 TFLOP per request to the first token,
+    15.01 GB streamed per decoded token, 131072 B of KV per cached token, 234.9 MB for the gate/up GEMV."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from spatialrgpt_b200 import baseline_config
+    n = bench.algorithmic_numbers(baseline_config("c2"))
+    assert n["S"] == 259
+    assert abs(n["flops_ttft"] / 1e12 - 5.58) < 0.01
+    assert abs(n["w_stream"] / 1e9 - 15.01) < 0.01
+    assert n["kv_per_tok"] == 131072 and n["gateup_bytes"] == 2 * 14336 * 4096 * 2
+    hbm, tensor, src = bench.load_peaks()
+    assert hbm > 1000 and tensor > 100 and isinstance(src, str)
