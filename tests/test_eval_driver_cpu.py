@@ -1,0 +1,102 @@
+"""The SpatialRGPT-Bench driver (spatialrgpt_b200/eval_spatial.py, mirror of llava/eval/eval_spatial.py) on the CPU with a stub
+model: chunking, region construction (run-length masks, box fallback, clamping, padding), prompt assembly, JSONL records."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from spatialrgpt_b200 import eval_spatial as E
+from spatialrgpt_b200.constants import IMAGE_TOKEN_INDEX
+from tests.golden.make_host_golden import ToyTokenizer
+
+
+def test_chunking_matches_the_reference_rule():
+    items = list(range(10))
+    assert [list(c) for c in E.split_list(items, 3)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]  # ceil(10/3) = 4 per chunk
+    assert list(E.get_chunk(items, 4, 3)) == [9] and list(E.get_chunk(items, 1, 0)) == items
+    assert sum(len(c) for c in E.split_list(items, 8)) == 10
+
+
+def test_rle_roundtrip_and_column_major_order():
+    rng = np.random.RandomState(0)
+    for h, w in [(5, 7), (64, 48), (1, 9), (33, 1)]:
+        m = (rng.rand(h, w) > 0.6).astype(np.uint8)
+        flat = m.T.reshape(-1)  # column-major
+        counts, cur, run = [], 0, 0
+        for v in flat:
+            if v == cur:
+                run += 1
+            else:
+                counts.append(run); cur ^= 1; run = 1
+        counts.append(run)
+        assert np.array_equal(E.rle_decode({"size": [h, w], "counts": counts}), m)
+        s = E.rle_encode_counts(counts)
+        assert all(48 <= ord(ch) < 48 + 64 for ch in s)
+        assert np.array_equal(E.rle_decode({"size": [h, w], "counts": s}), m)
+        assert np.array_equal(E.rle_decode({"size": [h, w], "counts": s.encode()}), m)
+    # a hand-checked case: 2x3 mask, column-major runs 1 zero, 2 ones, 3 zeros -> [[0,1,0],[1,0,0]]
+    assert E.rle_decode({"size": [2, 3], "counts": [1, 2, 3]}).tolist() == [[0, 1, 0], [1, 0, 0]]
+    with pytest.raises(ValueError):
+        E.rle_decode({"size": [2, 3], "counts": [1, 2]})
+    # long runs need several characters and the delta coding of the compressed form
+    counts = [0, 1000, 70000, 3, 5, 1200]
+    assert E._rle_counts_from_string(E.rle_encode_counts(counts)) == counts
+
+
+def test_regions_boxes_clamp_pad_and_fallback():
+    info = {"height": 20, "width": 30, "file_path": "x.jpg"}
+    line = {"image_info": info, "bbox": [[-5.0, 2.0, 10.0, 50.0], [3.2, 4.9, 8.1, 9.0]], "rle": [{"size": [20, 30], "counts": "garbage!"}]}
+    boxes = E.regions_for_line(json.loads(json.dumps(line)), use_mask=False, pad=False)
+    assert boxes[0].shape == (20, 30) and int(boxes[0].sum()) == 10 * 18 and int(boxes[1].sum()) == 5 * 5  # clamped; int() truncation
+    fallback = E.regions_for_line(json.loads(json.dumps(line)), use_mask=True, pad=False)  # undecodable rle -> boxes, like the reference
+    assert all(np.array_equal(a, b) for a, b in zip(boxes, fallback))
+    padded = E.regions_for_line(json.loads(json.dumps(line)), use_mask=False, pad=True)
+    assert padded[0].shape == (30, 30) and int(padded[0].sum()) == int(boxes[0].sum()) and padded[0][:5].sum() == 0
+    good = dict(line, rle=[{"size": [20, 30], "counts": [40, 20, 540]}])
+    m = E.regions_for_line(good, use_mask=True, pad=False)
+    assert int(m[0].sum()) == 20 and m[0][0, 2] == 1  # the run starts at column 2, row 0
+
+
+class _StubModel:
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.config = SimpleNamespace(image_aspect_ratio="resize")
+        self.calls = []
+
+    def generate(self, input_ids, images=None, depths=None, masks=None, **kw):
+        self.calls.append(dict(ids=input_ids.clone(), images=images, depths=depths, masks=masks, kw=kw))
+        return torch.tensor([[5, 6, 7]])
+
+
+def test_driver_writes_the_reference_records(tmp_path):
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+    proc = SiglipImageProcessor(size={"height": 28, "width": 28})
+    tok = ToyTokenizer()
+    tok.batch_decode = lambda ids, skip_special_tokens=True: ["  the answer is 2 m</s>"]
+    model = _StubModel()
+    Image.fromarray(np.random.RandomState(1).randint(0, 255, (20, 30, 3), dtype=np.uint8)).save(tmp_path / "a.jpg")
+    ann = [{"id": i, "image_info": {"file_path": "a.jpg", "height": 20, "width": 30}, "text_q": "how far?", "qa_info": {"type": "dist"},
+            "bbox": [[1, 1, 10, 10], [5, 5, 25, 18]],
+            "conversations": [{"from": "human", "value": "<image>\nDistance between <mask> and <mask>?"}, {"from": "gpt", "value": "2 m"},
+                              {"from": "human", "value": "And is <mask> closer?"}, {"from": "gpt", "value": "yes"}]} for i in range(3)]
+    (tmp_path / "ann.json").write_text(json.dumps(ann))
+    args = SimpleNamespace(model_path="ckpt/SpatialRGPT-VILA1.5-8B", model_base=None, image_folder=str(tmp_path), annotation_file=str(tmp_path / "ann.json"),
+                           answers_file=str(tmp_path / "out" / "answers.jsonl"), conv_mode="llava_v1", num_chunks=2, chunk_idx=0, temperature=0.0,
+                           top_p=None, num_beams=1, use_mask=False)
+    n = E.eval_model(args, depth_predictor=None, loader=lambda p, name, base: (tok, model, proc, 4096))
+    recs = [json.loads(l) for l in open(args.answers_file)]
+    assert n == len(recs) == 4  # chunk 0 of 2 holds ceil(3/2) = 2 annotations x 2 question turns
+    assert recs[0] == {"question_id": 0, "image": "a.jpg", "question": "how far?", "pred": "the answer is 2 m", "gt": "2 m",
+                       "model_id": "SpatialRGPT-VILA1.5-8B", "qa_info": {"type": "dist"}}
+    assert recs[1]["gt"] == "yes" and recs[2]["question_id"] == 1
+    c0, c1 = model.calls[0], model.calls[1]
+    assert c0["images"].shape == (1, 3, 28, 28) and c0["images"].dtype == torch.bfloat16 and c0["depths"] is None
+    assert c0["masks"][0].shape == (2, 28, 28) and c0["kw"]["do_sample"] is False and c0["kw"]["max_new_tokens"] == 128
+    assert int((c0["ids"] == IMAGE_TOKEN_INDEX).sum()) == 1
+    assert c1["ids"].shape[1] > c0["ids"].shape[1]  # the second turn carries the first question and an empty answer slot
+    assert E.question_with_depth_tokens("a <mask> b <mask>") == "a <mask> <depth> b <mask> <depth>"
+    assert E.stop_string("llava_v1") == "</s>" and E.clean_output(" x </s>", "</s>") == "x"
