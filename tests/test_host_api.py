@@ -155,3 +155,16 @@ def test_bench_algorithmic_numbers_match_the_survey():
     assert n["kv_per_tok"] == 131072 and n["gateup_bytes"] == 2 * 14336 * 4096 * 2
     hbm, tensor, src = bench.load_peaks()
     assert hbm > 1000 and tensor > 100 and isinstance(src, str)
+
+
+def test_ab_tool_parsing_and_summary():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("ab_tool", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ab.py"))
+    ab = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ab)
+    assert ab.parse_variant("B:SRGPT_X=2,Y=z") == ("B", {"SRGPT_X": "2", "Y": "z"}) and ab.parse_variant("A:") == ("A", {})
+    out = 'noise\n{"kernel": "k1", "ms_median": 1.5}\n{"other": 1}\n{"kernel": "k2", "ms_median": 0.5, "x": 1}\n{broken'
+    assert ab.collect(out) == {"k1": 1.5, "k2": 0.5}
+    rows = ab.summarise({"A": {"k1": [1.0, 3.0, 2.0]}, "B": {"k1": [1.0, 1.0, 4.0]}})
+    assert rows[0][0] == "k1" and rows[0][1] == {"A": 2.0, "B": 1.0} and rows[0][2]["B"] == 0.5
