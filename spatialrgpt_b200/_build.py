@@ -45,10 +45,25 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
+    """Builds under an inter-process file lock: N eval workers started at once (scripts/srgpt_bench.sh) must not compile into
+    the same object directory / link the same .so concurrently; the losers of the race find a fresh library and return."""
     if not force and not is_stale():
         return LIB_PATH
-    nvcc = _nvcc()
+    import fcntl
+
     os.makedirs(BUILD_DIR, exist_ok=True)
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
@@ -60,7 +75,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
     cmd = [nvcc, "-shared", "--cudart", "shared", "-o", tmp, *objs,
            "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)

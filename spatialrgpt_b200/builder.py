@@ -118,6 +118,16 @@ def read_checkpoint(model_path: str, load_tokenizer: bool = True):
         mm_projector_type=mp_cfg.get("mm_projector_type", "mlp_downsample"),
         region_extractor_type=re_cfg.get("region_extractor_type", "regiongpt"))
 
+    # HF generate() stops on generation_config.eos_token_id (llava_llama.py:212 -> GenerationMixin), which for Llama-3 chat
+    # checkpoints is a LIST that includes <|eot_id|>; config.json alone only names <|end_of_text|>
+    gen_cfg_path = os.path.join(paths["llm"], "generation_config.json")
+    if os.path.exists(gen_cfg_path):
+        gen_cfg = _read_json(gen_cfg_path)
+        if gen_cfg.get("eos_token_id") is not None:
+            cfg.llama.eos_token_id = gen_cfg["eos_token_id"]
+        if gen_cfg.get("pad_token_id") is not None and cfg.llama.pad_token_id is None:
+            cfg.llama.pad_token_id = gen_cfg["pad_token_id"]
+
     sd = {"llm": load_state_dict(paths["llm"]), "vision_tower": load_state_dict(paths["vision_tower"]),
           "mm_projector": load_state_dict(paths["mm_projector"])}
     if enable_region:

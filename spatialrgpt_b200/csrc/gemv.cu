@@ -349,6 +349,7 @@ lm_head_finalize_kernel(const float* __restrict__ part_val, const int* __restric
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w)
       if (better(sv[w], si[w], best, bi)) { best = sv[w]; bi = si[w]; }
+    if (bi == 0x7fffffff) bi = 0;  // all-NaN logits: never feed the sentinel to the embedding gather of the next step
     s_tok = bi;
     out_ids[*step] = (long long)bi;
   }

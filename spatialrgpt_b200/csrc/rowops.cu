@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ x, in
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w)
       if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-    out[blockIdx.x] = bi;
+    out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;  // a row of NaNs compares false everywhere: report index 0, never the sentinel
   }
 }
 

@@ -181,6 +181,41 @@ def depth_image(raw_rgb: np.ndarray, depth_predictor: Callable[[np.ndarray], tor
     return Image.fromarray(u8.cpu().numpy())
 
 
+def get_depth_predictor(spec: Optional[str] = None) -> Optional[Callable[[np.ndarray], torch.Tensor]]:
+    """The depth network is external to the hot path (eval_spatial.py:29-58 loads DepthAnything from $DEPTH_ANYTHING_PATH).
+    ``spec`` = "package.module:factory" names a zero-argument factory returning ``predictor(rgb uint8 [H, W, 3]) -> depth
+    [h', w']``; without a spec, $DEPTH_ANYTHING_PATH is used the way the reference uses it (its ``depth_anything`` package,
+    ``checkpoints/depth_anything_vitl14.pth`` and the 518-px / multiple-of-14 transform).  Returns None when neither is given."""
+    import importlib
+    import sys
+
+    if spec:
+        mod, _, fn = spec.partition(":")
+        return getattr(importlib.import_module(mod), fn or "get_depth_predictor")()
+    root = os.environ.get("DEPTH_ANYTHING_PATH")
+    if not root:
+        return None
+    import cv2
+    sys.path.append(root)
+    from depth_anything.dpt import DepthAnything
+    from depth_anything.util.transform import NormalizeImage, PrepareForNet, Resize
+    net = DepthAnything({"encoder": "vitl", "features": 256, "out_channels": [256, 512, 1024, 1024], "localhub": False})
+    net.load_state_dict(torch.load(os.path.join(root, "checkpoints", "depth_anything_vitl14.pth"), map_location="cpu"))
+    net = net.cuda().eval()
+    steps = [Resize(width=518, height=518, resize_target=False, keep_aspect_ratio=True, ensure_multiple_of=14,
+                    resize_method="lower_bound", image_interpolation_method=cv2.INTER_CUBIC),
+             NormalizeImage(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]), PrepareForNet()]
+
+    @torch.no_grad()
+    def predict(rgb: np.ndarray) -> torch.Tensor:
+        sample = {"image": rgb / 255.0}
+        for t in steps:
+            sample = t(sample)
+        return net(torch.from_numpy(sample["image"]).unsqueeze(0).cuda())[0]
+
+    return predict
+
+
 def answer_questions(line: Dict[str, Any], model, tokenizer, image_processor, image, depth, masks: Optional[torch.Tensor], conv_mode: str,
                      model_name: str, image_file: str, max_new_tokens: int = 128, temperature: float = 0.0, top_p=None,
                      num_beams: int = 1) -> List[Dict[str, Any]]:
@@ -193,7 +228,10 @@ def answer_questions(line: Dict[str, Any], model, tokenizer, image_processor, im
     conversations = line["conversations"]
     records = []
     for i in range(len(conversations) // 2):
-        conv.append_message(conv.roles[0], question_with_depth_tokens(conversations[i * 2]["value"]))
+        # <depth> follows <mask> only when a depth image feeds the depth branch: without one the rows would keep the raw
+        # token-table embedding of <depth>, which the model was never trained on
+        q = conversations[i * 2]["value"]
+        conv.append_message(conv.roles[0], question_with_depth_tokens(q) if depth is not None else q)
         conv.append_message(conv.roles[1], None)
         input_ids = tokenizer_image_token(conv.get_prompt(), tokenizer, IMAGE_TOKEN_INDEX, return_tensors="pt").unsqueeze(0).to(dev)
         output_ids = model.generate(input_ids, images=images_tensor, depths=depths_tensor,
@@ -215,6 +253,15 @@ def eval_model(args, depth_predictor: Optional[Callable[[np.ndarray], torch.Tens
     model_path = os.path.expanduser(args.model_path)
     model_name = get_model_name_from_path(model_path)
     tokenizer, model, image_processor, _ = loader(model_path, model_name, getattr(args, "model_base", None))
+    if depth_predictor is None:
+        depth_predictor = get_depth_predictor(getattr(args, "depth_predictor", None))
+    if depth_predictor is None and getattr(model.config, "enable_depth", False):
+        # the reference ALWAYS runs DepthAnything (eval_spatial.py:113); answers without it are not comparable
+        if not getattr(args, "allow_no_depth", False):
+            raise RuntimeError("this checkpoint has enable_depth=True but no depth network was given: pass --depth-predictor "
+                               "module:factory, set DEPTH_ANYTHING_PATH, or accept degraded answers with --allow-no-depth")
+        print("WARNING: no depth network: the depth branch gets no input and <depth> tokens are not inserted; answers are NOT "
+              "comparable with the reference's", flush=True)
     with open(args.annotation_file) as f:
         questions = get_chunk(json.load(f), args.num_chunks, args.chunk_idx)
     answers_file = os.path.expanduser(args.answers_file)
@@ -252,6 +299,9 @@ def build_arg_parser() -> argparse.ArgumentParser:
     p.add_argument("--top_p", type=float, default=None)
     p.add_argument("--num_beams", type=int, default=1)
     p.add_argument("--use-mask", type=lambda s: str(s).lower() not in ("0", "false", "no"), default=True)
+    p.add_argument("--depth-predictor", type=str, default=None,
+                   help="module:factory of the external depth network (default: DepthAnything from $DEPTH_ANYTHING_PATH, like the reference)")
+    p.add_argument("--allow-no-depth", action="store_true", help="run an enable_depth checkpoint without a depth network (degraded answers)")
     return p
 
 

@@ -138,6 +138,10 @@ class LlamaDecoder:
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         """Embedding gather through the splice kernel (source 0 only)."""
         flat = ids.reshape(-1).to(device=self.device, dtype=torch.int32)
+        if flat.numel():  # nn.Embedding raises on an out-of-range id; the gather kernel itself has no bounds check
+            lo, hi = int(flat.min()), int(flat.max())
+            if lo < 0 or hi >= self.w.embed.shape[0]:
+                raise IndexError(f"token id {lo if lo < 0 else hi} is outside the token table [0, {self.w.embed.shape[0]})")
         return ops.splice_rows(self.w.embed, None, None, None, torch.zeros_like(flat), flat)
 
     def prefill_hidden(self, inputs_embeds: torch.Tensor, seq: int = 0, start_pos: int = 0) -> torch.Tensor:
@@ -232,7 +236,8 @@ class LlamaDecoder:
         eos = set()
         if eos_token_ids is not None:
             eos = set(int(e) for e in (eos_token_ids if isinstance(eos_token_ids, (list, tuple, set)) else [eos_token_ids]))
-        self.cache.release(seq)
+        for b in range(len(self.cache.owned)):  # a previous batched generate leaves pages owned by sequences 1..B-1
+            self.cache.release(b)
         self.cache.reserve(seq, S + max_new_tokens)
         hidden = self.prefill_hidden(inputs_embeds, seq, 0)
         logits = torch.empty((max_new_tokens, d.vocab_size), dtype=torch.float32, device=self.device) if return_logits else None

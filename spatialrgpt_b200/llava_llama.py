@@ -191,7 +191,7 @@ class LlavaLlamaModel:
         plan = build_splice_plan(ids_cpu, None if attention_mask is None else am_cpu, None if labels is None else lab_cpu, n_tok,
                                  [0 if m is None else int(m.shape[0]) for m in mask_list[:n_img]], [m is not None for m in mask_list[:n_img]],
                                  cfg.llm_mask_token_id, cfg.llm_depth_token_id, region_on, depth_on,
-                                 getattr(cfg.llama, "tokenizer_model_max_length", None))
+                                 getattr(cfg.llama, "tokenizer_model_max_length", None), vocab_size=self.weights.llama.embed.shape[0])
         for w in plan.warnings:
             print(w)
         lens, new_labels = plan.lens, plan.labels

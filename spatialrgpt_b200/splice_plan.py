@@ -32,11 +32,18 @@ class SplicePlan:
 
 def build_splice_plan(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], labels: Optional[torch.Tensor], n_tok: int,
                       region_counts: Sequence[int], region_present: Sequence[bool], mask_token_id: int, depth_token_id: int,
-                      region_on: bool, depth_on: bool, max_len: Optional[int] = None) -> SplicePlan:
+                      region_on: bool, depth_on: bool, max_len: Optional[int] = None, vocab_size: Optional[int] = None) -> SplicePlan:
     """input_ids [B, T] (CPU int64, IMAGE_TOKEN_INDEX marks image slots); region_counts[i] / region_present[i]: number of
     regions of image i and whether its mask list entry was given (None entries write no region rows, base_extractor.py:47-49)."""
     ids_cpu = input_ids.to(torch.int64)
     B, T = ids_cpu.shape
+    if vocab_size is not None:
+        # the reference's nn.Embedding raises on an out-of-range id (llava_arch.py:436-437); the gather kernel has no bounds check,
+        # so the plan is the place to refuse (only IMAGE_TOKEN_INDEX may be negative)
+        bad = ((ids_cpu < 0) & (ids_cpu != IMAGE_TOKEN_INDEX)) | (ids_cpu >= vocab_size)
+        if bool(bad.any()):
+            b, t = [int(v) for v in torch.nonzero(bad)[0]]
+            raise IndexError(f"input_ids[{b}, {t}] = {int(ids_cpu[b, t])} is outside the token table [0, {vocab_size})")
     am = torch.ones((B, T), dtype=torch.bool) if attention_mask is None else attention_mask.bool()
     lab_all = torch.full((B, T), IGNORE_INDEX, dtype=torch.int64) if labels is None else labels.to(torch.int64)
     offs = [0]

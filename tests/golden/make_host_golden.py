@@ -41,6 +41,49 @@ CONVERSATIONS = [
 PROMPTS = ["<image>\nWhat is <mask> <depth>?", "no image here", "a <image> b <image> c", "<image>"]
 
 
+def preproc_inputs():
+    """Seeded synthetic PIL images / uint8 region masks shared by the generator and tests/test_host_api.py."""
+    import numpy as np
+    from PIL import Image
+
+    rng = np.random.RandomState(7)
+    # smooth-ish content (random low-res noise upsampled) so that bicubic resampling is exercised away from saturation
+    imgs = []
+    for (h, w) in ((40, 70), (64, 64), (90, 33)):
+        low = rng.randint(0, 255, (h // 4 + 1, w // 4 + 1, 3), dtype=np.uint8)
+        imgs.append(Image.fromarray(low).resize((w, h), Image.BILINEAR))
+    masks = []
+    for (h, w) in ((40, 70), (40, 70), (90, 33)):
+        m = np.zeros((h, w), dtype=np.uint8)
+        y0, x0 = rng.randint(0, h // 2), rng.randint(0, w // 2)
+        m[y0:y0 + h // 3 + 1, x0:x0 + w // 3 + 1] = 1
+        m[rng.rand(h, w) > 0.97] ^= 1
+        masks.append(m)
+    return imgs, masks
+
+
+def make_preproc_golden(RM):
+    """process_images / process_regions of the REFERENCE (llava/mm_utils.py:421-542) with the SigLIP processor, both aspect modes."""
+    import numpy as np
+    from types import SimpleNamespace
+    from transformers import SiglipImageProcessor
+
+    imgs, masks = preproc_inputs()
+    out = {}
+    for mode in ("resize", "pad"):
+        proc = SiglipImageProcessor(size={"height": 56, "width": 56})
+        # transformers 4.37.2 (the reference's pin): the SigLIP processor has NO crop_size attribute, which is how
+        # mm_utils.py:434-441 tells it from CLIP; 5.5.0 adds crop_size=None -> restore the pinned behaviour for the reference run
+        if getattr(proc, "crop_size", None) is None and "crop_size" in vars(proc):
+            delattr(proc, "crop_size")
+        cfg = SimpleNamespace(image_aspect_ratio=mode, image_processor=proc)
+        out[f"images_{mode}"] = RM.process_images(imgs, proc, cfg).numpy()
+        out[f"regions_{mode}_a"] = RM.process_regions(masks[:2], proc, cfg).numpy()
+        out[f"regions_{mode}_b"] = RM.process_regions(masks[2:], proc, cfg).numpy()
+    np.savez_compressed(os.path.join(HERE, "host_preproc.npz"), **out)
+    print("wrote host_preproc.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main():
     ref_shim.install()
     from llava import conversation as RC
@@ -48,8 +91,6 @@ def main():
 
     out = {"prompts": {}, "tokenize": [], "stopping": []}
     for name, tmpl in RC.conv_templates.items():
-        if name in ("default", "v0"):  # few-shot template: only system/separators are mirrored (see conversation.py)
-            continue
         rows = []
         for conv_msgs in CONVERSATIONS:
             c = tmpl.copy()
@@ -71,6 +112,7 @@ def main():
         out["stopping"].append(bool(crit(torch.tensor([base[:n]]), None)))
     out["stopping_ids"] = base
     out["model_names"] = {p: RM.get_model_name_from_path(p) for p in ["a/b/SpatialRGPT-VILA1.5-8B", "x/run1/checkpoint-500/", "solo"]}
+    make_preproc_golden(RM)
     with open(os.path.join(HERE, "host_api.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote host_api.json:", {k: len(v) for k, v in out.items()})

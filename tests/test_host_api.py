@@ -86,6 +86,26 @@ def test_process_images_and_regions_shapes():
     assert 0.9 < float(reg[1].mean()) <= 1.01  # resampled floats, not rescaled by 1/255 (mm_utils.py:479-482)
 
 
+@pytest.mark.parametrize("mode", ["resize", "pad"])
+def test_process_images_and_regions_match_reference(mode):
+    """a1: process_images / process_regions against outputs of the REFERENCE's llava/mm_utils.py:421-542 on the same seeded
+    inputs (tests/golden/host_preproc.npz, written by make_host_golden.py).  Same PIL / cv2 / HF processor underneath -> exact."""
+    from types import SimpleNamespace
+    from transformers import SiglipImageProcessor
+
+    from tests.golden.make_host_golden import preproc_inputs
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "host_preproc.npz"))
+    imgs, masks = preproc_inputs()
+    proc = SiglipImageProcessor(size={"height": 56, "width": 56})
+    cfg = SimpleNamespace(image_aspect_ratio=mode, image_processor=proc)
+    px = M.process_images(imgs, proc, cfg)
+    assert px.dtype == torch.float32 and np.array_equal(px.numpy(), gold[f"images_{mode}"])
+    for tag, sl in (("a", slice(0, 2)), ("b", slice(2, 3))):
+        reg = M.process_regions(masks[sl], proc, cfg)
+        assert reg.dtype == torch.float32 and np.array_equal(reg.numpy(), gold[f"regions_{mode}_{tag}"])
+
+
 def test_read_checkpoint_roundtrip(tmp_path):
     """A synthetic checkpoint written in the reference's four-directory layout parses back (CPU only)."""
     from safetensors.torch import save_file
