@@ -33,6 +33,14 @@ constexpr int ACC_BUFS = 2;
 constexpr int NUM_EPI_WARPS = 8;           // two warps per TMEM lane group, each owns half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int MAX_STAGES = 6;
+// Staged epilogue: every epilogue warp owns STG_BUFS buffers of one 32-row x 32-column bf16 chunk (64-byte rows laid out in the
+// TMA SWIZZLE_64B pattern so the row-per-thread 16-byte writes are bank-conflict free); a chunk leaves through ONE TMA store
+// (cp.async.bulk.tensor ... global.shared::cta, SASS UTMASTG) instead of 32 lanes x 4 scattered 16-byte STG (each a separate
+// half-sector L2 write) - the row-per-thread stores were what paced the short-K SigLIP GEMMs (DESIGN.md "GEMM").
+constexpr int STG_CHUNK_BYTES = 32 * 32 * 2;
+constexpr int STG_BUFS = 2;
+constexpr int STG_BYTES = NUM_EPI_WARPS * STG_BUFS * STG_CHUNK_BYTES;  // 32 KB
+constexpr int BAR_BYTES = 512;
 
 // Tile configuration.  BN = 128: 32 KB / stage, 6 stages, 256 TMEM columns.  BN = 256: 48 KB / stage, 4 stages,
 // all 512 TMEM columns — 1.33x the FLOPs per byte pulled from L2, which is what bounds 128x128 tiles
@@ -44,7 +52,7 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = BN_ * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int TMEM_COLS = ACC_BUFS * BN_;  // 256 / 512 (power of two >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + BAR_BYTES;
 };
 
 
@@ -67,6 +75,18 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensor
 // L2 prefetch of one box (no shared-memory destination, no barrier): turns the later TMA load into an L2 hit
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y) : "memory");
+}
+// TMA store of one box from shared memory (bulk async-group completion); rows / columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src),
+               "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source (the buffers may then be rewritten)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -114,6 +134,8 @@ struct Params {
   int gm;                  // rasterisation: m-units per group (see unit_to_tile)
   int l2_prefetch;         // k-blocks the producer prefetches into L2 ahead of its loads (0 = off)
   int res_prefetch;        // 1: residual rows are requested before the accumulator wait
+  int staged;              // 1: bf16 output leaves through shared memory + TMA stores (tmap_c valid)
+  int res_tma;             // 1 (pair kernel only): the residual tile is TMA-loaded into the staging buffers (tmap_r valid)
 };
 
 // Tile order.  Units are walked group by group; a group is `gm` vertically adjacent m-units x ALL n-tiles, inside a group the
@@ -131,7 +153,7 @@ __device__ __forceinline__ void unit_to_tile(int unit, int tiles_mu, int tiles_n
   mu = g0 + rem - nt * gsz;
 }
 
-template <int EPI>
+template <int EPI, bool RES_STAGED = false>
 __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, const Params& p, int row, int col0, const uint4* pre_res = nullptr) {
   // v[j] is the fp32 accumulator of column col0 + j.  Rounding points mirror the reference's
   // sequence of bf16 torch ops (linear -> activation -> residual add), see DESIGN.md.
@@ -159,7 +181,16 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(bf16_round(v[j]));
   } else if (EPI == SRGPT_EPI_BIAS_RESIDUAL) {
-    if (p.residual != nullptr) {
+    if (RES_STAGED) {
+      // all 32 columns come from the TMA-loaded residual tile (columns beyond N were zero-filled and are clipped by the store)
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+        unpack8(pre_res[j >> 3], f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[j + t] = bf16_round(v[j + t]) + f[t];
+      }
+    } else if (p.residual != nullptr) {
       const int rrow = p.res_row_mod > 0 ? row % p.res_row_mod : row;
       const bf16* rp = p.residual + (size_t)rrow * p.ldr + col0;
 #pragma unroll
@@ -227,6 +258,37 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
   }
 }
 
+// Staged variant (bf16 output, every epilogue except SwiGLU): the warp's 32 rows x 32 columns go to its staging buffer in the
+// SWIZZLE_64B layout (16-byte chunk j of row r at r*64 + ((j ^ ((r >> 1) & 3)) << 4)) and leave with one TMA store, which also
+// clips rows >= M and columns >= N.  `buf` is free again once at most BUFS-1 younger stores of this lane are still reading.
+template <int EPI, int BUFS, bool RES_STAGED>
+__device__ __forceinline__ void store_chunk_staged(const uint32_t* r, const Params& p, const CUtensorMap* tmap_c, uint8_t* buf, int lane, int row,
+                                                   int row0, int col0, const uint4* pre_res) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  uint8_t* rp = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  if (RES_STAGED) {
+    uint4 res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rp + ((j ^ sw) << 4));
+    apply_epilogue<EPI, true>(v, p, row, col0, res);
+  } else {
+    if (row < p.M) apply_epilogue<EPI, false>(v, p, row, col0, pre_res);
+    if (lane == 0) bulk_wait_group_read<BUFS - 1>();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(rp + ((j ^ sw) << 4)) = pack8(v + 8 * j);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmap_c, smem_u32(buf), col0, row0);
+    bulk_commit_group();
+  }
+}
+
 // Residual rows of one thread's chunks (CPW chunks of 32 columns), requested BEFORE the wait on the accumulator: the addresses
 // depend only on the tile index, so the global-load latency (the longest link of the epilogue chain of the short-K ViT
 // GEMMs: out_proj ran at 0.38 of peak with the residual against 0.58 without) hides behind the tile's main loop.
@@ -253,7 +315,8 @@ __device__ __forceinline__ void prefetch_residual(uint4 (&pre)[CPW][4], const Pa
 // empty barriers (count CL).
 template <int EPI, int BN, int CL, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const Params p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int STAGE_BYTES = C::STAGE_BYTES;
@@ -261,7 +324,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned stage buffers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;  // epilogue staging (STG_BYTES), 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;     // [ACC_BUFS]
@@ -282,6 +346,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.staged) prefetch_tmap(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), CL);  // one tcgen05.commit per CTA sharing the B tile
@@ -384,7 +449,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lg = warp & 3;  // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
     // EW / 4 warps share a lane group; each owns a contiguous share of the tile's 32-column chunks
     constexpr int CPW = (BN / 32) / (EW / 4);
+    constexpr bool CAN_STAGE = EW == NUM_EPI_WARPS && EPI != SRGPT_EPI_SWIGLU;  // staging is sized for 8 epilogue warps
     const int cpart = (warp - 2) >> 2;
+    const bool staged = CAN_STAGE && p.staged != 0;
+    uint8_t* stg = stg_base + (warp - 2) * (STG_BUFS * STG_CHUNK_BYTES);
+    uint32_t sbuf = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = cid; unit < num_units; unit += ncl) {
       int mu, nt;
@@ -404,13 +473,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
         tmem_ld_wait();
-        if (row < p.M) store_chunk<EPI>(r, p, row, col0, EPI == SRGPT_EPI_BIAS_RESIDUAL ? pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? ci : 0] : nullptr);
+        const uint4* pr = EPI == SRGPT_EPI_BIAS_RESIDUAL ? pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? ci : 0] : nullptr;
+        if (CAN_STAGE && staged) {
+          store_chunk_staged<EPI, STG_BUFS, false>(r, p, &tmap_c, stg + sbuf * STG_CHUNK_BYTES, lane, row, m0 + lg * 32, col0, pr);
+          sbuf ^= 1;
+        } else if (row < p.M) {
+          store_chunk<EPI>(r, p, row, col0, pr);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
+    if (CAN_STAGE && staged && lane == 0) bulk_wait_group_read<0>();  // shared memory stays valid until every store has read it
   }
 
   tcgen05_fence_before();
@@ -436,10 +512,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // ---------------------------------------------------------------------------------------------
 constexpr int PAIR_BN = 256;
 constexpr bool PAIR_DEFAULT = true;
-constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_B_HALF_BYTES = (PAIR_BN / 2) * BK * 2;                 // 16 KB
 constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_B_HALF_BYTES;       // 32 KB per CTA
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+// RES_TMA (residual epilogue): the tile's residual rows are TMA-LOADED into the staging buffers while the tile's main loop runs
+// (one 32 x 32 box per chunk, 4 buffers per warp = all of a warp's chunks), the epilogue adds in place and the same buffer leaves
+// through the TMA store.  That needs 64 KB of staging, paid for with one pipeline stage (5 instead of 6).
+template <bool RES_TMA>
+struct PairCfg {
+  static constexpr int STAGES = RES_TMA ? 5 : 6;
+  static constexpr int BUFS = RES_TMA ? 4 : STG_BUFS;
+  static constexpr int STG = NUM_EPI_WARPS * BUFS * STG_CHUNK_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + STG + 1024 + BAR_BYTES;
+};
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -478,13 +562,17 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
                : "memory");
 }
 
-template <int EPI, int EW>
+template <int EPI, int EW, bool RES_TMA>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES, STAGE_BYTES = PAIR_STAGE_BYTES, TMEM_COLS = ACC_BUFS * BN;
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const Params p) {
+  using PC = PairCfg<RES_TMA>;
+  constexpr int BN = PAIR_BN, STAGES = PC::STAGES, STAGE_BYTES = PAIR_STAGE_BYTES, TMEM_COLS = ACC_BUFS * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + PC::STG);
+  uint64_t* res_bar = bars + 32;  // [NUM_EPI_WARPS * 4] (RES_TMA): one per warp and chunk, at byte 256 of the barrier block
   uint64_t* full_bar = bars;                            // [STAGES]  used in the leader only
   uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  one per CTA (multicast commit)
   uint64_t* tmem_full_bar = bars + 2 * STAGES;          // [ACC_BUFS] one per CTA (multicast commit)
@@ -512,6 +600,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * EW);
     }
+    if (RES_TMA)
+      for (int i = 0; i < NUM_EPI_WARPS * 4; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    if (p.staged) prefetch_tmap(&tmap_c);
+    if (RES_TMA) prefetch_tmap(&tmap_r);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(smem_u32(tmem_base_slot), TMEM_COLS);
@@ -571,7 +663,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue warps (2..9), both CTAs: rows of this CTA's 128 x 256 accumulator =====================
     const int lg = warp & 3;
     constexpr int CPW = (BN / 32) / (EW / 4);
+    constexpr bool CAN_STAGE = EW == NUM_EPI_WARPS && EPI != SRGPT_EPI_SWIGLU;
+    constexpr bool RES_STAGED = RES_TMA && EPI == SRGPT_EPI_BIAS_RESIDUAL && CAN_STAGE && CPW == 4;
     const int cpart = (warp - 2) >> 2;
+    const bool staged = CAN_STAGE && p.staged != 0;
+    uint8_t* stg = stg_base + (warp - 2) * (PC::BUFS * STG_CHUNK_BYTES);
+    uint64_t* my_res_bar = res_bar + (warp - 2) * 4;
+    uint32_t sbuf = 0, res_phase = 0;  // res_phase: one parity bit per chunk barrier
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = cid; unit < num_units; unit += ncl) {
       int mu, nt;
@@ -579,8 +677,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m0 = (mu * 2 + crank) * BM;
       const int n0 = nt * BN;
       const int row = m0 + lg * 32 + lane;
-      uint4 pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1][4];
-      if (EPI == SRGPT_EPI_BIAS_RESIDUAL) prefetch_residual<EPI, (EPI == SRGPT_EPI_BIAS_RESIDUAL ? CPW : 1)>(pre, p, row, n0, cpart * CPW);
+      uint4 pre[(EPI == SRGPT_EPI_BIAS_RESIDUAL && !RES_STAGED) ? CPW : 1][4];
+      if (RES_STAGED) {
+        // the residual boxes of this warp's chunks land in its 4 staging buffers while the main loop of the tile runs
+        if (lane == 0) {
+          bulk_wait_group_read<0>();  // the previous tile's stores have finished reading the buffers
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci) {
+            const int col0 = n0 + (cpart * CPW + ci) * 32;
+            if (col0 < p.N) {
+              const uint32_t rb = smem_u32(&my_res_bar[ci]);
+              mbar_expect_tx(rb, STG_CHUNK_BYTES);  // out-of-bounds rows / columns are zero-filled and still counted
+              tma_load_2d(smem_u32(stg + ci * STG_CHUNK_BYTES), &tmap_r, rb, col0, m0 + lg * 32);
+            }
+          }
+        }
+        __syncwarp();
+      } else if (EPI == SRGPT_EPI_BIAS_RESIDUAL) {
+        prefetch_residual<EPI, (EPI == SRGPT_EPI_BIAS_RESIDUAL && !RES_STAGED) ? CPW : 1>(pre, p, row, n0, cpart * CPW);
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
 #pragma unroll
@@ -591,13 +706,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
         tmem_ld_wait();
-        if (row < p.M) store_chunk<EPI>(r, p, row, col0, EPI == SRGPT_EPI_BIAS_RESIDUAL ? pre[EPI == SRGPT_EPI_BIAS_RESIDUAL ? ci : 0] : nullptr);
+        if (RES_STAGED) {
+          mbar_wait(smem_u32(&my_res_bar[ci]), (res_phase >> ci) & 1u);
+          res_phase ^= 1u << ci;
+          store_chunk_staged<EPI, PC::BUFS, true>(r, p, &tmap_c, stg + ci * STG_CHUNK_BYTES, lane, row, m0 + lg * 32, col0, nullptr);
+        } else {
+          const uint4* pr = (EPI == SRGPT_EPI_BIAS_RESIDUAL && !RES_STAGED) ? pre[(EPI == SRGPT_EPI_BIAS_RESIDUAL && !RES_STAGED) ? ci : 0] : nullptr;
+          if (CAN_STAGE && staged) {
+            store_chunk_staged<EPI, STG_BUFS, false>(r, p, &tmap_c, stg + sbuf * STG_CHUNK_BYTES, lane, row, m0 + lg * 32, col0, pr);
+            sbuf ^= 1;
+          } else if (row < p.M) {
+            store_chunk<EPI>(r, p, row, col0, pr);
+          }
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
       if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
     }
+    if (CAN_STAGE && (staged || RES_STAGED) && lane == 0) bulk_wait_group_read<0>();
   }
 
   tcgen05_fence_before();
@@ -793,6 +921,26 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, 
   return SRGPT_OK;
 }
 
+// [rows, cols] row-major bf16 output / residual matrix -> box {32 columns, 32 rows}, 64B swizzle (the staged epilogue's chunk)
+static int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+    return SRGPT_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (output) failed: CUresult %d (rows=%d cols=%d ld=%d ptr=%p)", (int)r, rows, cols, ld, ptr);
+    return SRGPT_ERR_CUDA;
+  }
+  return SRGPT_OK;
+}
+
 // Epilogue warps: 8 by default (two per TMEM lane group).  A 16-warp epilogue (four per lane group, SRGPT_GEMM_EW=16; the
 // erf-GELU epilogue's 116 registers do not fit the 96-register budget of an 18-warp CTA and stays at 8) was built to shorten
 // the per-tile latency chain of the short-K ViT GEMMs and MEASURED (profiles/r01_microbench_gemm_ew.txt): out_proj +
@@ -809,16 +957,20 @@ static int epi_warps_env() {
 }
 
 template <int EPI, int BN, int CL, int EW>
-static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream);
+static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p, int grid, cudaStream_t stream);
 
 template <int EPI, int BN, int CL>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
-  if (EpiWarps<EPI>::N == 16 && epi_warps_env() == 16) return launch_cfg_ew<EPI, BN, CL, 16>(ta, tb, p, grid, stream);
-  return launch_cfg_ew<EPI, BN, CL, 8>(ta, tb, p, grid, stream);
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p, int grid, cudaStream_t stream) {
+  if (EpiWarps<EPI>::N == 16 && epi_warps_env() == 16) {
+    Params q = p;
+    q.staged = 0;  // the staging buffers are sized for 8 epilogue warps
+    return launch_cfg_ew<EPI, BN, CL, 16>(ta, tb, tc, q, grid, stream);
+  }
+  return launch_cfg_ew<EPI, BN, CL, 8>(ta, tb, tc, p, grid, stream);
 }
 
 template <int EPI, int BN, int CL, int EW>
-static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -837,7 +989,7 @@ static int launch_cfg_ew(const CUtensorMap& ta, const CUtensorMap& tb, const Par
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, BN, CL, EW>, ta, tb, p));
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<EPI, BN, CL, EW>, ta, tb, tc, p));
   return SRGPT_OK;
 }
 
@@ -902,20 +1054,37 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     if (ceil_div(p.N, 128) >= sm_count() - 4) return launch_tall<EPI, 128>(A, lda, W, ldw, p, stream);
     return launch_tall<EPI, 64>(A, lda, W, ldw, p, stream);
   }
+  // staged epilogue (shared memory + TMA stores): every bf16 output except SwiGLU; SRGPT_GEMM_DIRECT_EPI=1 restores the
+  // row-per-thread global stores (A/B knob).  The residual tile is TMA-loaded too in the pair kernel unless its rows are
+  // broadcast (res_row_mod, the position-embedding add of the patch GEMM) or SRGPT_GEMM_NO_RESTMA=1.
+  static const int direct_epi = env_int("SRGPT_GEMM_DIRECT_EPI"), no_restma = env_int("SRGPT_GEMM_NO_RESTMA");
+  Params ps = p;
+  ps.staged = (!direct_epi && !p.out_fp32 && EPI != SRGPT_EPI_SWIGLU) ? 1 : 0;
+  ps.res_tma = 0;
+  CUtensorMap tc, tr;
+  if (ps.staged) {
+    int rc = make_tmap_out(&tc, p.C, p.M, p.N, p.ldc);
+    if (rc != SRGPT_OK) return rc;
+  } else {
+    tc = CUtensorMap{};
+  }
+  tr = tc;
   // CTA-pair kernel (cta_group::2, 256 x 256 tiles per pair) for large problems
   static const int pair_env = env_int("SRGPT_GEMM_PAIR");  // 1: on where eligible, -1: off, 0: default
   // default: at least two waves of 256 x 256 pair tiles and >= 1024 rows (measured, profiles/r01_microbench_gemm_pair.txt:
-  // 8288 x 28672 x 4096 0.83 -> 0.90 of the cuBLAS peak, 8192^3 0.85 -> 0.92, ViT qkv 0.67 -> 0.70; M = 259 and the
-  // GELU-tanh epilogue (fc1: the epilogue, not the operand ingest, paces that kernel) are faster on the 1-CTA kernel)
+  // 8288 x 28672 x 4096 0.83 -> 0.90 of the cuBLAS peak, 8192^3 0.85 -> 0.92, ViT qkv 0.67 -> 0.70; M = 259 is faster on
+  // the 1-CTA kernel).  SRGPT_GEMM_PAIR_GELU=-1 keeps the GELU-tanh epilogue (SigLIP fc1) off the pair kernel as in round 1.
+  static const int pair_gelu = env_int("SRGPT_GEMM_PAIR_GELU");
   const long long pair_units = (long long)ceil_div(ceil_div(p.M, BM), 2) * ceil_div(p.N, PAIR_BN);
-  const bool pair_default = PAIR_DEFAULT && p.M >= 1024 && pair_units >= 2 * (sm_count() / 2) && EPI != SRGPT_EPI_BIAS_GELU_TANH;
+  const bool pair_default = PAIR_DEFAULT && p.M >= 1024 && pair_units >= 2 * (sm_count() / 2) &&
+                            (EPI != SRGPT_EPI_BIAS_GELU_TANH || pair_gelu >= 0);
   if (pair_env >= 0 && (pair_env > 0 || pair_default)) {
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
     if (rc != SRGPT_OK) return rc;
     rc = make_tmap(&tb, W, p.N, p.K, ldw, PAIR_BN / 2);
     if (rc != SRGPT_OK) return rc;
-    Params pg = p;
+    Params pg = ps;
     const int tiles_mu = ceil_div(ceil_div(p.M, BM), 2);
     pg.gm = tiles_mu;
     if (2.0 * p.M * p.K > 80e6) {
@@ -924,17 +1093,28 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     }
     pg.l2_prefetch = 0;
     const bool ew16 = EpiWarps<EPI>::N == 16 && epi_warps_env() == 16;
+    if (ew16) pg.staged = 0;
+    constexpr bool HAS_RES = EPI == SRGPT_EPI_BIAS_RESIDUAL;
+    const bool res_tma = HAS_RES && pg.staged && !no_restma && p.residual != nullptr && p.res_row_mod == 0;
+    if (res_tma) {
+      rc = make_tmap_out(&tr, p.residual, p.M, p.N, p.ldr);
+      if (rc != SRGPT_OK) return rc;
+      pg.res_tma = 1;
+    }
     static bool configured = false;
     if (!configured) {
-      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, EpiWarps<EPI>::N>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<false>::SMEM_BYTES));
+      SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, EpiWarps<EPI>::N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            PairCfg<false>::SMEM_BYTES));
+      if (HAS_RES)
+        SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<EPI, 8, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<HAS_RES>::SMEM_BYTES));
       configured = true;
     }
     const int max_clusters = sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((pair_units < max_clusters ? pair_units : max_clusters) * 2));
     cfg.blockDim = dim3(64 + 32 * (ew16 ? 16 : 8));
-    cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+    cfg.dynamicSmemBytes = res_tma ? PairCfg<HAS_RES>::SMEM_BYTES : PairCfg<false>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -943,8 +1123,9 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (ew16) SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, EpiWarps<EPI>::N>, ta, tb, pg));
-    else SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, 8>, ta, tb, pg));
+    if (ew16) SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, EpiWarps<EPI>::N, false>, ta, tb, tc, tr, pg));
+    else if (res_tma) SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, 8, HAS_RES>, ta, tb, tc, tr, pg));
+    else SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI, 8, false>, ta, tb, tc, tr, pg));
     return SRGPT_OK;
   }
   int bn, cl;
@@ -957,7 +1138,7 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
   const int tiles_mu = ceil_div(ceil_div(p.M, BM), cl);
   const int units = tiles_mu * ceil_div(p.N, bn);
   // rasterisation group: the whole M when the activation fits L2, else as many m-units as keep a group's rows <= 40 MB
-  Params pg = p;
+  Params pg = ps;
   static const int gm_env = env_int("SRGPT_GEMM_GM");
   const double a_bytes = 2.0 * p.M * p.K;
   pg.gm = tiles_mu;
@@ -972,8 +1153,8 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
   pg.l2_prefetch = pf_env > 0 ? pf_env : 0;
   const int max_clusters = sm_count() / cl;
   const int grid = (units < max_clusters ? units : max_clusters) * cl;
-  if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, pg, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, pg, grid, stream);
-  return bn == 256 ? launch_cfg<EPI, 256, 1>(ta, tb, pg, grid, stream) : launch_cfg<EPI, 128, 1>(ta, tb, pg, grid, stream);
+  if (cl == 2) return bn == 256 ? launch_cfg<EPI, 256, 2>(ta, tb, tc, pg, grid, stream) : launch_cfg<EPI, 128, 2>(ta, tb, tc, pg, grid, stream);
+  return bn == 256 ? launch_cfg<EPI, 256, 1>(ta, tb, tc, pg, grid, stream) : launch_cfg<EPI, 128, 1>(ta, tb, tc, pg, grid, stream);
 }
 
 }  // namespace gemm
@@ -1004,7 +1185,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
   if (bias != nullptr) SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0);
 
   gemm::Params p;
-  p.gm = 0; p.l2_prefetch = 0;
+  p.gm = 0; p.l2_prefetch = 0; p.staged = 0; p.res_tma = 0;
   static const bool no_respf = getenv("SRGPT_GEMM_NO_RESPF") != nullptr && getenv("SRGPT_GEMM_NO_RESPF")[0] == '1';
   p.res_prefetch = no_respf ? 0 : 1;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc;

@@ -22,7 +22,8 @@ __device__ __forceinline__ int feat_row(int y, int x, int side, int order) {
 
 // ATen area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=false)
 __device__ __forceinline__ float src_index(float rscale, int dst) {
-  const float s = rscale * ((float)dst + 0.5f) - 0.5f;
+  // one fused multiply-add, as both ATen builds contract it (gcc -ffp-contract=fast on the host, nvcc -fmad on the device)
+  const float s = __fmaf_rn(rscale, (float)dst + 0.5f, -0.5f);
   return s < 0.f ? 0.f : s;
 }
 
@@ -277,6 +278,23 @@ __global__ void reorder_rows_kernel(const bf16* __restrict__ x, bf16* __restrict
 // ---------------------------------------------------------------------------------------------
 // depth map: resize + min/max (pass 1), normalise to u8 x3 (pass 2)
 // ---------------------------------------------------------------------------------------------
+// Bilinear tap with the EXACT fp32 operation order of ATen's upsample_bilinear2d as compiled (the reference runs it in
+// get_depth_map, llava/eval/eval_spatial.py:100): val = fma(w_y0, fma(w_x0, v00, w_x1 * v01), w_y1 * fma(w_x0, v10, w_x1 * v11)).
+// The uint8 truncation right after makes a 1-ulp difference visible, so the association matters here (it does not for the
+// mask weights, which are rounded to bf16); pinned bit-exactly against torch in tests/test_gpu_ops.py::test_depth_to_u8x3.
+__device__ __forceinline__ float bilinear_tap_aten(const float* __restrict__ img, int IH, int IW, float rs_y, float rs_x, int oy, int ox) {
+  const float sy = src_index(rs_y, oy), sx = src_index(rs_x, ox);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < IH - 1 ? 1 : 0), x1 = x0 + (x0 < IW - 1 ? 1 : 0);
+  const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float v00 = img[(size_t)y0 * IW + x0], v01 = img[(size_t)y0 * IW + x1];
+  const float v10 = img[(size_t)y1 * IW + x0], v11 = img[(size_t)y1 * IW + x1];
+  const float r0 = __fmaf_rn(lx0, v00, __fmul_rn(lx1, v01));
+  const float r1 = __fmaf_rn(lx0, v10, __fmul_rn(lx1, v11));
+  return __fmaf_rn(ly0, r0, __fmul_rn(ly1, r1));
+}
+
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);
   return i >= 0 ? i : i ^ 0x7fffffff;
@@ -292,7 +310,7 @@ depth_resize_kernel(const float* __restrict__ d, int h, int w, float* __restrict
   __shared__ float smin[8], smax[8];
   float lo = INFINITY, hi = -INFINITY;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
-    const float v = bilinear_tap(d, h, w, rs_y, rs_x, p / W, p % W);
+    const float v = bilinear_tap_aten(d, h, w, rs_y, rs_x, p / W, p % W);
     tmp[p] = v;
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);

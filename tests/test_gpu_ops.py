@@ -275,8 +275,11 @@ def test_depth_to_u8x3(ops, h, w, H, W):
     ref = O.depth_to_u8x3(d, H, W)
     out = ops.depth_to_u8x3(d.to(DEV), H, W).cpu()
     assert out.shape == ref.shape and out.dtype == torch.uint8
-    diff = (out.int() - ref.int()).abs()
-    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3  # fp32 association at a truncation boundary
+    assert torch.equal(out, ref), "byte work is bit-exact: the kernel mirrors ATen's fp32 operation order (region.cu bilinear_tap_aten)"
+    # the reference interpolates on the GPU (eval_spatial.py:96-100) and normalises in numpy: the same bytes
+    dev_interp = torch.nn.functional.interpolate(d.to(DEV)[None], (H, W), mode="bilinear", align_corners=False)[0, 0].cpu().numpy()
+    n = (dev_interp - dev_interp.min()) / (dev_interp.max() - dev_interp.min()) * 255.0
+    assert torch.equal(out[..., 0], torch.from_numpy(n.astype("uint8")))
     assert int(out.min()) == 0 and int(out.max()) == 255
 
 

@@ -173,7 +173,8 @@ def test_bench_algorithmic_numbers_match_the_survey():
     assert abs(n["flops_ttft"] / 1e12 - 5.58) < 0.01
     assert abs(n["w_stream"] / 1e9 - 15.01) < 0.01
     assert n["kv_per_tok"] == 131072 and n["gateup_bytes"] == 2 * 14336 * 4096 * 2
-    hbm, tensor, src = bench.load_peaks()
+    hbm, tensor, src, tensor_sustained = bench.load_peaks()
+    assert 0 < tensor_sustained <= tensor
     assert hbm > 1000 and tensor > 100 and isinstance(src, str)
 
 
