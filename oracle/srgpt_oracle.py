@@ -314,9 +314,21 @@ def downsample_block(x: torch.Tensor) -> torch.Tensor:
 
 
 def mm_projector_forward(cfg: OracleConfig, w: Dict[str, torch.Tensor], lres: torch.Tensor,
-                         dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    """``mlp_downsample`` (base_projector.py:73-80): DownSample -> LN(4C) -> Linear -> GELU(erf) -> Linear."""
+                         dtype: torch.dtype = torch.float32, ptype: str = "mlp_downsample") -> torch.Tensor:
+    """``MultimodalProjector.forward`` (base_projector.py:69-94).  ``mlp_downsample`` (:73-80): DownSample -> LN(4C) -> Linear ->
+    GELU(erf) -> Linear; ``identity`` (:69-70); ``linear`` (:71-72); ``mlpNx_gelu`` (:81-88): Linear, then N-1 x (GELU, Linear)."""
     W = lambda k: w[k].to(dtype)  # noqa: E731
+    if ptype == "identity":
+        return lres.to(dtype)
+    if ptype == "linear":
+        return F.linear(lres.to(dtype), W("layers.weight"), W("layers.bias"))
+    if ptype != "mlp_downsample":
+        import re
+        depth = int(re.match(r"^mlp(\d+)x_gelu$", ptype).group(1))
+        x = F.linear(lres.to(dtype), W("layers.0.weight"), W("layers.0.bias"))
+        for i in range(1, depth):
+            x = F.linear(F.gelu(x), W(f"layers.{2 * i}.weight"), W(f"layers.{2 * i}.bias"))
+        return x
     x = downsample_block(lres.to(dtype))
     x = F.layer_norm(x, (x.shape[-1],), W("layers.1.weight"), W("layers.1.bias"), 1e-5)
     x = F.linear(x, W("layers.2.weight"), W("layers.2.bias"))

@@ -340,6 +340,17 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
     vpre[u] = make_uint4(0, 0, 0, 0);
     if (j < pos_early) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, kpre[u], vpre[u]);
   }
+  // immutable rows beyond the register window (prompts longer than DEC_PRE * 32 = 256 tokens): requested into L2 now, so the
+  // loop after the wait pays an L2 hit instead of an HBM round trip (one 128-byte line per 8 lanes of a half-warp)
+  if (prefetch && (hl & 7) == 0) {
+    for (int j = DEC_PRE * DEC_HW + hw; j < pos_early; j += DEC_HW) {
+      const int pg = j / page_size;
+      const int page = __ldg(page_table + pg);
+      const bf16* kp = kv_pages + (((size_t)page * 2 + 0) * page_size + (j - pg * page_size)) * row_stride + kvh * 128 + hl * 8;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kp));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + (size_t)page_size * row_stride));
+    }
+  }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   trace_mark(trace, 1);

@@ -53,6 +53,7 @@ struct Params {
   int* part_idx;
   unsigned long long* trace;  // optional timeline record (srgpt_trace_begin)
   int spre;                   // number of extra 4-chunk batches per row staged in shared memory before the wait (0..SPRE_MAX)
+  int l2pf;                   // 1: the rest of the warp's two rows is requested into L2 (bulk prefetch) before the dependency wait
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -196,6 +197,23 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
       ++n_spre;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // ---- third level, no registers and no shared memory: everything of the two rows that the levels above did not request goes
+  //      to L2 with one bulk prefetch per row (cp.async.bulk.prefetch.L2, SASS UBLKPF).  A kernel whose CTAs are resident while
+  //      its producer still runs (o_proj under the decode attention, gate/up under o_proj's tail, every kernel across the
+  //      ~1 us dependency release) then keeps HBM streaming through what used to be idle gaps and later reads L2 hits.
+  if (p.l2pf && active && lane < 2) {
+    const int c_req = first_full ? (32 * NPRE + 128 * n_spre) : 0;  // chunks per row already requested above
+    if (c_req < nchunk) {
+      const char* rowp = reinterpret_cast<const char*>(lane == 0 ? p0 : p1) + (size_t)c_req * 16;
+      uint32_t bytes = (uint32_t)(nchunk - c_req) * 16u;
+      while (bytes > 0) {  // pieces of <= 16 KB
+        const uint32_t n = bytes > 16384u ? 16384u : bytes;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rowp), "r"(n) : "memory");
+        rowp += n;
+        bytes -= n;
+      }
+    }
   }
   // norm weights are static too: fetch them before the wait when a thread owns at most 2 chunks of x
   uint4 nw_pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
@@ -404,6 +422,11 @@ static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
   Params q = p;
   q.trace = trace_next_slot();
   q.spre = spre_default();
+  static const int l2pf = [] {
+    const char* v = getenv("SRGPT_GEMV_L2PF");
+    return (v != nullptr && v[0] != 0) ? atoi(v) : 1;
+  }();
+  q.l2pf = l2pf;
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, PRE>, q));
   return SRGPT_OK;
 }

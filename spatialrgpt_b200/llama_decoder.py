@@ -255,18 +255,60 @@ class LlamaDecoder:
         return_logits = logits is not None
         if use_graph and not return_logits:
             self._ensure_graph(seq)
-        while n < max_new_tokens:
-            if need_host_check:
-                ids = self.out_ids[:n]
-                last = int(ids[-1])  # device->host sync, like HF's per-token eos check
-                if last in eos or (stopping_fn is not None and stopping_fn(ids)):
-                    break
+        def launch_step(k: int) -> None:
             if use_graph and not return_logits:
                 self._graph.replay()
                 ops.LAUNCHES += self.kernels_per_decode_step
             else:
-                self._decode_step_launch(seq, None if logits is None else logits[n])
-            n += 1
+                self._decode_step_launch(seq, None if logits is None else logits[k])
+
+        if not need_host_check:
+            while n < max_new_tokens:
+                launch_step(n)
+                n += 1
+        else:
+            # EOS / stopping criteria (the mode eval_spatial.py:223-237 runs) WITHOUT a host round trip per token: the step that
+            # produces token n is enqueued BEFORE token n-1 is inspected, token ids reach the host through a side stream into
+            # pinned memory, and the host inspects token n-1 while the GPU computes token n.  On a stop the one speculative
+            # step is discarded (it only touched this sequence's own KV slot and the step counters, which the next request
+            # resets).  HF inspects after every token too (a blocking .item()); the result is identical.
+            if getattr(self, "_host_ids", None) is None:
+                self._host_ids = torch.empty(self.out_ids.numel(), dtype=torch.int64, pin_memory=True)
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            host, side = self._host_ids, self._copy_stream
+            done = {}
+
+            def fetch(lo: int, hi: int) -> None:  # tokens [lo, hi) -> host, ordered after the work enqueued so far
+                e = torch.cuda.Event()
+                e.record()
+                side.wait_event(e)
+                with torch.cuda.stream(side):
+                    host[lo:hi].copy_(self.out_ids[lo:hi], non_blocking=True)
+                    d = torch.cuda.Event()
+                    d.record(side)
+                for k in range(lo, hi):
+                    done[k] = d
+
+            fetch(0, n)
+            checked = 0
+            while True:
+                launched = n < max_new_tokens
+                if launched:
+                    launch_step(n)
+                    fetch(n, n + 1)
+                else:
+                    break  # the token budget is spent: the last token is returned whatever it is (HF semantics)
+                stop_len = None
+                for k in range(checked, n):
+                    done.pop(k).synchronize()
+                    if int(host[k]) in eos or (stopping_fn is not None and stopping_fn(host[:k + 1])):
+                        stop_len = k + 1
+                        break
+                checked = n
+                if stop_len is not None:
+                    n = stop_len
+                    break
+                n += 1
         out = self.out_ids[:n].clone()
         if return_logits:
             return out, logits[:n]

@@ -128,7 +128,7 @@ class LlavaLlamaModel:
         tower grid (base_projector.py:32-52)."""
         from .region_extractor import ADA_POOL
         side = ADA_POOL if (self.config.enable_region and self.region_extractor is not None) else self.config.vision.grid
-        return ((side + 1) // 2) ** 2
+        return self.mm_projector.tokens_out(side)
 
     def _encode_multimodal(self, images, masks, depths):
         """llava_arch.py:387-411.  Returns (image_features [N,196,H], mask_embeds, depth_embeds)."""

@@ -75,12 +75,15 @@ class RegionW:
 
 @dataclass
 class ProjectorW:
-    ln_w: torch.Tensor  # [4C]
-    ln_b: torch.Tensor
-    fc1_w: torch.Tensor  # [H, 4C]
-    fc1_b: torch.Tensor
-    fc2_w: torch.Tensor  # [H, H]
-    fc2_b: torch.Tensor
+    """``mlp_downsample``: LayerNorm(4C) + two linears.  The other reference types (base_projector.py:69-72,81-91) keep their
+    linears in ``linears`` [(weight [out, in], bias)] - one for ``linear``, N for ``mlpNx_gelu``, none for ``identity``."""
+    ln_w: Optional[torch.Tensor] = None  # [4C]
+    ln_b: Optional[torch.Tensor] = None
+    fc1_w: Optional[torch.Tensor] = None  # [H, 4C]
+    fc1_b: Optional[torch.Tensor] = None
+    fc2_w: Optional[torch.Tensor] = None  # [H, H]
+    fc2_b: Optional[torch.Tensor] = None
+    linears: List = field(default_factory=list)
 
 
 @dataclass
@@ -178,9 +181,22 @@ def from_state_dicts(cfg: LlavaConfig, sd: Dict[str, Dict[str, torch.Tensor]], d
             depth_w=g(r, "depth_projector.weight").contiguous(), depth_b=g(r, "depth_projector.bias"))
 
     m = sd["mm_projector"]
-    projector = ProjectorW(ln_w=g(m, "layers.1.weight"), ln_b=g(m, "layers.1.bias"),
-                           fc1_w=g(m, "layers.2.weight").contiguous(), fc1_b=g(m, "layers.2.bias"),
-                           fc2_w=g(m, "layers.4.weight").contiguous(), fc2_b=g(m, "layers.4.bias"))
+    ptype = cfg.mm_projector_type
+    if ptype == "mlp_downsample":
+        projector = ProjectorW(ln_w=g(m, "layers.1.weight"), ln_b=g(m, "layers.1.bias"),
+                               fc1_w=g(m, "layers.2.weight").contiguous(), fc1_b=g(m, "layers.2.bias"),
+                               fc2_w=g(m, "layers.4.weight").contiguous(), fc2_b=g(m, "layers.4.bias"))
+    elif ptype == "identity":
+        projector = ProjectorW()
+    elif ptype == "linear":  # nn.Linear stored as `layers` itself (base_projector.py:71-72)
+        projector = ProjectorW(linears=[(g(m, "layers.weight").contiguous(), g(m, "layers.bias"))])
+    else:
+        import re as _re
+        mt = _re.match(r"^mlp(\d+)x_gelu$", ptype or "")
+        if not mt:
+            raise ValueError(f"Unknown projector type: {ptype}")  # base_projector.py:91
+        # nn.Sequential(Linear, GELU, Linear, ...): linears sit at the even indices (base_projector.py:83-88)
+        projector = ProjectorW(linears=[(g(m, f"layers.{2 * i}.weight").contiguous(), g(m, f"layers.{2 * i}.bias")) for i in range(int(mt.group(1)))])
 
     l, lc = sd["llm"], cfg.llama
     llama = LlamaW(embed=g(l, "model.embed_tokens.weight").contiguous(), norm=g(l, "model.norm.weight"),

@@ -220,9 +220,40 @@ def run_maskpool_kats():
     print(f"op_kats -> {path} ({os.path.getsize(path)/1e6:.2f} MB)")
 
 
+PROJECTOR_TYPES = ("linear", "mlp2x_gelu", "mlp3x_gelu", "identity")
+
+
+@torch.no_grad()
+def run_projector_kats():
+    """The reference MultimodalProjector (base_projector.py:55-94) for its non-default types, fp32, seeded weights that are
+    stored in the fixture (keys = the reference module's own state-dict names)."""
+    ref_shim.install()
+    from llava.model.multimodal_projector.base_projector import MultimodalProjector, MultimodalProjectorConfig
+
+    g = torch.Generator().manual_seed(321)
+    C, H = 48, 64
+    arrays = {}
+    x = torch.randn(2, 9, C, generator=g).to(torch.bfloat16).float()
+    arrays["x"] = x.numpy()
+    for t in PROJECTOR_TYPES:
+        m = MultimodalProjector(MultimodalProjectorConfig(t), SimpleNamespace(mm_hidden_size=C, hidden_size=H)).float().eval()
+        sd = {k: (torch.randn(v.shape, generator=g) * 0.1).to(torch.bfloat16).float() for k, v in m.state_dict().items()}
+        m.load_state_dict(sd, strict=True)
+        arrays[f"{t}__out"] = m(x).numpy()
+        for k, v in sd.items():
+            arrays[f"{t}__w__{k}"] = v.numpy()
+    path = os.path.join(HERE, "proj_kats.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"proj_kats -> {path}: {[k for k in arrays if '__w__' in k]}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["proj"]:  # only the projector-type fixture (the others regenerate bit-identically but take minutes)
+        run_projector_kats()
+        sys.exit(0)
     for n in CASES:
         run_case(n)
     run_maskpool_kats()
+    run_projector_kats()

@@ -232,3 +232,28 @@ def test_missing_cuda_inputs_fail_loudly():
     with pytest.raises(SrgptError):
         ops.layernorm(torch.zeros(4, 8, dtype=torch.bfloat16), torch.ones(8, dtype=torch.bfloat16),
                       torch.zeros(8, dtype=torch.bfloat16), 1e-6)
+
+
+@pytest.mark.parametrize("ptype", ["linear", "mlp2x_gelu", "mlp3x_gelu", "identity"])
+def test_projector_types_match_reference_fixture(golden_dir, ptype):
+    """base_projector.py:69-72,81-91: the non-default mm_projector types through MultimodalProjector (same tcgen05 GEMM, other
+    epilogues) against outputs of the reference's own module (tests/golden/proj_kats.npz)."""
+    from spatialrgpt_b200 import LlavaConfig
+    from spatialrgpt_b200.multimodal_projector import MultimodalProjector
+    from spatialrgpt_b200.weights import ProjectorW
+
+    g = load_npz(os.path.join(golden_dir, "proj_kats.npz"))
+    w = {k.split("__w__")[1]: v.to(DEV, torch.bfloat16) for k, v in g.items() if k.startswith(ptype + "__w__")}
+    if ptype == "linear":
+        pw = ProjectorW(linears=[(w["layers.weight"], w["layers.bias"])])
+    elif ptype == "identity":
+        pw = ProjectorW()
+    else:
+        pw = ProjectorW(linears=[(w[f"layers.{2 * i}.weight"], w[f"layers.{2 * i}.bias"]) for i in range(len(w) // 2)])
+    cfg = LlavaConfig()
+    cfg.mm_projector_type = ptype
+    out = MultimodalProjector(cfg, pw)(g["x"].to(DEV, torch.bfloat16))
+    assert_close(out, g[ptype + "__out"], **BF16_CHAIN, what=ptype)
+    with pytest.raises(ValueError):
+        cfg.mm_projector_type = "mlp_gelu"
+        MultimodalProjector(cfg, pw)

@@ -8,6 +8,7 @@ import torch
 
 from oracle import srgpt_oracle as O
 from tests.golden.make_golden import CASES
+from tests.util import load_npz
 
 
 def _load(golden_dir, name):
@@ -89,3 +90,12 @@ def test_depth_to_u8x3():
     assert out.shape == (6, 8, 3) and out.dtype == torch.uint8
     assert out.min() == 0 and out.max() == 255
     assert torch.equal(out[..., 0], out[..., 2])
+
+
+@pytest.mark.parametrize("ptype", ["linear", "mlp2x_gelu", "mlp3x_gelu", "identity"])
+def test_projector_types_match_reference_module(golden_dir, ptype):
+    """The non-default mm_projector types against the reference's MultimodalProjector (fixture by make_golden.py proj)."""
+    g = load_npz(os.path.join(golden_dir, "proj_kats.npz"))
+    w = {k.split("__w__")[1]: v for k, v in g.items() if k.startswith(ptype + "__w__")}
+    out = O.mm_projector_forward(O.OracleConfig(), w, g["x"], ptype=ptype)
+    assert torch.allclose(out, g[ptype + "__out"], rtol=1e-5, atol=1e-6)

@@ -69,3 +69,8 @@ for k, d in kinds.items():
     summary[k]["n"] = d["n"]
     print("  %-10s n=%3d  dur=%7.2f  exposed=%7.2f  early=%6.2f  release=%6.2f" % (k, d["n"], *(summary[k][x] for x in ("dur", "busy", "early", "rel"))))
 json.dump({"step_us": total / 1e3, "kinds": summary}, open("gpurun_out/decode_trace.json", "w"), indent=1)
+# JSON lines for tools/ab.py (microseconds in the ms_median field)
+print(json.dumps({"kernel": "decode_step_us", "ms_median": round(total / 1e3, 2)}))
+for k, d in summary.items():
+    print(json.dumps({"kernel": f"exposed_us {k}", "ms_median": d["busy"]}))
+    print(json.dumps({"kernel": f"release_us {k}", "ms_median": d["rel"]}))

@@ -111,6 +111,15 @@ if "gemm" in which:
         ms, best = timeit(lambda: ops.gemm(a, w, bias=bias, residual=res, epilogue=epi, out=out), flush=False)
         emit(f"gemm {M}x{N}x{K} epi{epi}", ms, best, flops=2.0 * M * N * K, bytes_=(M * K + N * K + M * n_out) * 2)
 
+if "cublas" in which:
+    # context only: the vendor library (torch.matmul -> cuBLAS) on the short-K SigLIP shapes and one long-K shape, no epilogue
+    for (M, N, K) in [(65536, 1152, 1152), (65536, 3456, 1152), (65536, 4304, 1152), (65536, 1152, 4304), (8192, 8192, 8192), (2048, 1152, 1152),
+                      (259, 28672, 4096)]:
+        a, w = rnd(M, K), rnd(N, K)
+        out = torch.empty(M, N, dtype=BF, device=dev)
+        ms, best = timeit(lambda: torch.matmul(a, w.t(), out=out), flush=False)
+        emit(f"cublas {M}x{N}x{K}", ms, best, flops=2.0 * M * N * K)
+
 if "attn" in which:
     for (B, S, nh, nkv, hd, causal) in [(2, 1024, 16, 16, 72, False), (64, 1024, 16, 16, 72, False), (1, 259, 32, 8, 128, True), (32, 259, 32, 8, 128, True)]:
         qkv = rnd(B * S, (nh + 2 * nkv) * hd)

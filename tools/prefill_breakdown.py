@@ -27,7 +27,7 @@ def main():
     v, l = cfg.vision, cfg.llama
     T, Dv, Iv, Lv = v.grid ** 2, v.hidden_size, v.intermediate_size, v.num_hidden_layers - 1
     nums = algorithmic_numbers(cfg)
-    _, tensor_peak, _ = load_peaks()
+    _, tensor_peak, _, _ = load_peaks()
     stages = {}
 
     def ev():
