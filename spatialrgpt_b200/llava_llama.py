@@ -145,6 +145,11 @@ class LlavaLlamaModel:
         N = images.shape[0]
         mask_embeds = depth_embeds = None
         use_depth = cfg.enable_region and cfg.enable_depth and depths is not None
+        if cfg.enable_region and self.region_extractor is not None and masks is not None:
+            # the mask -> pooling-weight kernels need only the masks: side stream, under the tower passes launched next
+            g = cfg.vision.grid
+            self.region_extractor.mask_pooling.precompute(masks, N, [(4 * g, ops.ORDER_NESTED)] + ([(g, ops.ORDER_ROWMAJOR)] if use_depth else []),
+                                                          self.device)
         if use_depth and depths.shape == images.shape:
             # one tower pass over [images; depths] (same weights, llava_arch.py:398,404): twice the GEMM M
             both = self.vision_tower(torch.cat([images.to(self.device), depths.to(self.device).to(images.dtype)], dim=0))
@@ -285,7 +290,9 @@ class LlavaLlamaModel:
                  attention_mask: Optional[torch.Tensor] = None, **generation_kwargs):
         do_sample = bool(generation_kwargs.pop("do_sample", False))
         temperature = generation_kwargs.pop("temperature", None)
-        generation_kwargs.pop("top_p", None)
+        top_p = generation_kwargs.pop("top_p", None)
+        top_k = generation_kwargs.pop("top_k", None)
+        seed = generation_kwargs.pop("seed", None)
         num_beams = int(generation_kwargs.pop("num_beams", 1) or 1)
         max_new_tokens = generation_kwargs.pop("max_new_tokens", None)
         max_length = generation_kwargs.pop("max_length", None)
@@ -295,8 +302,11 @@ class LlavaLlamaModel:
         eos_token_id = generation_kwargs.pop("eos_token_id", self.config.llama.eos_token_id)
         return_logits = bool(generation_kwargs.pop("output_logits", False))
         use_graph = bool(generation_kwargs.pop("use_cuda_graph", True))
-        if do_sample and temperature not in (None, 0, 0.0):
-            raise NotImplementedError("sampling is a next-round item (SURVEY.md §8f.4); the graded mode is greedy")
+        # do_sample=True -> HF's TemperatureLogitsWarper + TopPLogitsWarper + multinomial, here one kernel per token
+        # (eval_spatial.py:231-236 passes do_sample = temperature > 0, so temperature 0 stays greedy)
+        sampling = None
+        if do_sample and temperature not in (0, 0.0):
+            sampling = dict(temperature=1.0 if temperature is None else float(temperature), top_p=top_p, top_k=top_k, seed=seed)
         if num_beams != 1:
             raise NotImplementedError("beam search is a next-round item (SURVEY.md §8f.4)")
         if generation_kwargs:
@@ -326,7 +336,7 @@ class LlavaLlamaModel:
             n = lens[0]
             emb = packed if packed is not None else (inputs_embeds[0, inputs_embeds.shape[1] - n:] if left else inputs_embeds[0, :n])
             r = self.llm.generate_from_embeds(emb, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
-                                              use_graph=use_graph, return_logits=return_logits)
+                                              use_graph=use_graph, return_logits=return_logits, sampling=sampling)
             if return_logits:
                 r, lg = r
                 all_logits.append(lg)
@@ -338,7 +348,7 @@ class LlavaLlamaModel:
                 T = inputs_embeds.shape[1]
                 packed = torch.cat([inputs_embeds[b, T - lens[b]:] if left else inputs_embeds[b, :lens[b]] for b in range(B)], 0)
             r = self.llm.generate_batch(packed, lens, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
-                                        use_graph=use_graph, return_logits=return_logits)
+                                        use_graph=use_graph, return_logits=return_logits, sampling=sampling)
             if return_logits:
                 outs, all_logits = r
             else:

@@ -315,6 +315,19 @@ def lm_head_argmax(x: torch.Tensor, w: torch.Tensor, norm_weight: Optional[torch
                                                 _stream()), "srgpt_lm_head_argmax_bf16")
 
 
+def sample_top_p(logits: torch.Tensor, params: torch.Tensor, seed: int, step: torch.Tensor, step_offset: int, out_ids: torch.Tensor,
+                 embed_table: Optional[torch.Tensor] = None, next_x: Optional[torch.Tensor] = None) -> None:
+    """One token from softmax(logits / T) restricted to its top-p nucleus -> out_ids[step + step_offset] (and next_x = embed row).
+    ``params`` = device float32 [temperature, top_p, top_k (0 = off)]; ``step`` = device int32 [1]."""
+    _need(logits, torch.float32, "sample_top_p.logits"); _need(params, torch.float32, "sample_top_p.params")
+    _need(step, torch.int32, "sample_top_p.step"); _need(out_ids, torch.int64, "sample_top_p.out_ids")
+    if logits.dim() != 1 or not logits.is_contiguous() or params.numel() < 3:
+        raise SrgptError("sample_top_p: logits must be a contiguous fp32 vector [V] and params [temperature, top_p, top_k]")
+    K = 0 if embed_table is None else embed_table.shape[1]
+    check(_lib.load().srgpt_sample_top_p_f32(_p(logits), logits.numel(), _p(params), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(step), step_offset,
+                                             _p(out_ids), _p(embed_table), _p(next_x), K, _stream()), "srgpt_sample_top_p_f32")
+
+
 def argmax_f32(x: torch.Tensor) -> torch.Tensor:
     _need(x, torch.float32, "argmax_f32.x")
     rows, cols = x.shape

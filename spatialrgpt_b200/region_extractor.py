@@ -32,19 +32,60 @@ class MaskPooling:
         idx = [i for i in range(B) if mask_list[i] is not None]
         if not idx:
             return out
-        same = all(mask_list[i].shape == mask_list[idx[0]].shape and mask_list[i].dtype == mask_list[idx[0]].dtype for i in idx)
-        if same and len(idx) == B and B > 1:
-            masks = torch.stack([self._prep(mask_list[i], x.device) for i in idx], 0)
-            pooled = ops.mask_pool(x, ops.mask_weights(masks, side, order))
-            for j, i in enumerate(idx):
-                out[i] = pooled[j]
+        pre = getattr(self, "_pre", None)
+        if pre is not None and pre[0] is mask_list and pre[1] == B and (side, order) in pre[2]:
+            # weights were computed on the side stream while the tower ran (precompute): order the pooling after them
+            cur = torch.cuda.current_stream(x.device)
+            cur.wait_event(pre[3])
+            kind, wts = pre[2][(side, order)]
+            if kind == "stack":
+                wts.record_stream(cur)
+                pooled = ops.mask_pool(x, wts)
+                for j, i in enumerate(idx):
+                    out[i] = pooled[j]
+            else:
+                for i in idx:
+                    wts[i].record_stream(cur)
+                    out[i] = ops.mask_pool(x[i:i + 1], wts[i])[0]
         else:
-            for i in idx:
-                m = self._prep(mask_list[i], x.device)[None]
-                out[i] = ops.mask_pool(x[i:i + 1], ops.mask_weights(m, side, order))[0]
+            kind, wts = self._weights(mask_list, idx, B, side, order, x.device)
+            if kind == "stack":
+                pooled = ops.mask_pool(x, wts)
+                for j, i in enumerate(idx):
+                    out[i] = pooled[j]
+            else:
+                for i in idx:
+                    out[i] = ops.mask_pool(x[i:i + 1], wts[i])[0]
         if not return_list:
             return torch.cat([o for o in out if o is not None])
         return out
+
+    def _weights(self, mask_list, idx, B: int, side: int, order: int, device):
+        """Normalised bf16 pooling weights: one [B, M, L] tensor when every image has the same number of regions, else per image."""
+        same = all(mask_list[i].shape == mask_list[idx[0]].shape and mask_list[i].dtype == mask_list[idx[0]].dtype for i in idx)
+        if same and len(idx) == B and B > 1:
+            return "stack", ops.mask_weights(torch.stack([self._prep(mask_list[i], device) for i in idx], 0), side, order)
+        return "list", {i: ops.mask_weights(self._prep(mask_list[i], device)[None], side, order) for i in idx}
+
+    def precompute(self, mask_list, n_images: int, specs, device) -> None:
+        """The pooling weights depend on the masks alone (base_extractor.py:53-66), not on any feature map: compute them for the
+        given (side, order) geometries on a SIDE stream now - the caller launches the vision tower next, so the resampling /
+        normalisation kernels run under it instead of between the refinement and the pooling.  ``forward`` picks them up."""
+        self._pre = None
+        if mask_list is None:
+            return
+        idx = [i for i in range(min(n_images, len(mask_list))) if mask_list[i] is not None]
+        if not idx or len(mask_list) != n_images:
+            return
+        cur = torch.cuda.current_stream(device)
+        if getattr(self, "_stream", None) is None:
+            self._stream = torch.cuda.Stream(device=device)
+        self._stream.wait_stream(cur)  # the masks (e.g. their host->device copies) are ordered before the side work
+        with torch.cuda.stream(self._stream):
+            table = {(side, order): self._weights(mask_list, idx, n_images, side, order, device) for side, order in specs}
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        self._pre = (mask_list, n_images, table, ev)
 
     @staticmethod
     def _prep(mask: torch.Tensor, device) -> torch.Tensor:
@@ -102,6 +143,7 @@ class RegionExtractor:
         depth_embeds = None
         if depth_features is not None:
             depth_embeds = self.extract_region_features(depth_features, masks, w.depth_w, w.depth_b, ops.ORDER_ROWMAJOR)
+        self.mask_pooling._pre = None  # precomputed weights (if any) belong to this request only
         return mask_embeds, depth_embeds
 
     __call__ = forward

@@ -487,3 +487,48 @@ def test_lm_head_argmax(ops, V, K):
     assert int(step) == 4 and int(pos) == 42
     assert torch.equal(nxt.cpu(), emb[tok])
     assert out_ids.tolist()[:3] == [-1, -1, -1]
+
+
+# ------------------------------------------------------------------------------------------ sampling
+def _hf_nucleus(logits, temperature, top_k, top_p):
+    """Probabilities after HF's TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper (transformers 4.37.2 semantics)."""
+    scores = logits.double() / temperature
+    if top_k and top_k < scores.numel():
+        kth = scores.topk(top_k).values[-1]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
+    if top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(scores, descending=False)
+        cum = sorted_logits.softmax(-1).cumsum(-1)
+        remove = cum <= (1 - top_p)
+        remove[-1:] = False  # min_tokens_to_keep = 1
+        scores = scores.masked_fill(torch.zeros_like(remove).scatter(0, sorted_idx, remove), float("-inf"))
+    return scores.softmax(-1)
+
+
+@pytest.mark.parametrize("V,temperature,top_k,top_p", [(1000, 0.7, 50, 0.8), (4099, 1.0, 0, 0.9), (333, 1.3, 20, 1.0), (128259, 0.2, 50, 0.7)])
+def test_sample_top_p_matches_hf_distribution(ops, V, temperature, top_k, top_p):
+    g = torch.Generator().manual_seed(V)
+    logits = (torch.randn(V, generator=g) * 2.5)
+    ref = _hf_nucleus(logits, temperature, top_k, top_p)
+    support = ref > 0
+    n = 3000
+    d_logits = logits.to(DEV)
+    params = torch.tensor([temperature, top_p, float(top_k)], device=DEV)
+    out = torch.zeros(n, dtype=torch.int64, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for i in range(n):
+        step.fill_(i + 1)
+        ops.sample_top_p(d_logits, params, 1234, step, -1, out)
+    ids = out.cpu()
+    assert bool(support[ids].all()), "a sampled token lies outside the HF nucleus"
+    freq = torch.bincount(ids, minlength=V).double() / n
+    # every token's frequency within 5 binomial standard deviations (+ one count) of its HF probability
+    sd = (ref * (1 - ref) / n).sqrt()
+    assert bool(((freq - ref).abs() <= 5 * sd + 1.5 / n).all()), float(((freq - ref).abs() - 5 * sd).max())
+    # same (seed, step) -> same token; top_k = 1 -> the arg max
+    step.fill_(7)
+    a = torch.zeros(8, dtype=torch.int64, device=DEV); b = torch.zeros(8, dtype=torch.int64, device=DEV)
+    ops.sample_top_p(d_logits, params, 99, step, -1, a); ops.sample_top_p(d_logits, params, 99, step, -1, b)
+    assert int(a[6]) == int(b[6])
+    ops.sample_top_p(d_logits, torch.tensor([temperature, top_p, 1.0], device=DEV), 5, step, -1, a)
+    assert int(a[6]) == int(logits.argmax())

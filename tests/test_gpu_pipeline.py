@@ -257,3 +257,28 @@ def test_projector_types_match_reference_fixture(golden_dir, ptype):
     with pytest.raises(ValueError):
         cfg.mm_projector_type = "mlp_gelu"
         MultimodalProjector(cfg, pw)
+
+
+def test_generate_with_sampling(golden_dir):
+    """do_sample=True (eval_spatial.py:231-236 with temperature > 0): reproducible per seed, top_k=1 degenerates to greedy,
+    CUDA-graph and eager decode agree, and EOS / stopping criteria still apply."""
+    name = "tiny_masks_gqa"
+    kw, n_regions, t_text, kind, n_new, depth_on = CASES[name]
+    g = load_npz(os.path.join(golden_dir, name + ".npz"))
+    oc, sd, model = build_model(kw, int(g["weight_seed"]))
+    input_ids, images, depths, masks = O.synth_request(oc, n_regions, t_text, seed=1234, kind=kind)
+    args = dict(images=images.to(DEV), depths=depths.to(DEV), masks=[m.to(DEV) for m in masks], max_new_tokens=n_new)
+    ids = input_ids.to(DEV)
+    greedy = model.generate(ids, do_sample=False, **args)[0].tolist()
+    assert greedy == g["new_ids"].tolist()
+    assert model.generate(ids, do_sample=True, temperature=0.9, top_p=0.95, top_k=1, seed=3, **args)[0].tolist() == greedy
+    assert model.generate(ids, do_sample=True, temperature=0, **args)[0].tolist() == greedy  # the reference's temperature-0 call
+    s1 = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, **args)[0].tolist()
+    s2 = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, **args)[0].tolist()
+    s3 = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, use_cuda_graph=False, **args)[0].tolist()
+    assert s1 == s2 == s3 and len(s1) == n_new
+    draws = {tuple(model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=s, **args)[0].tolist()) for s in range(6)}
+    assert len(draws) > 1, "six seeds at temperature 1.5 should not all give the same continuation"
+    stop_at = s1[2]
+    cut = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, eos_token_id=stop_at, **args)[0].tolist()
+    assert cut == s1[: s1.index(stop_at) + 1]
