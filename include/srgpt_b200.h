@@ -51,6 +51,12 @@ enum {
   SRGPT_EPI_BIAS_RESIDUAL = 4,  /* C = bf16(acc + bias) + residual[row (% res_row_mod), n]        */
   SRGPT_EPI_SWIGLU = 5          /* W rows interleaved (gate_i, up_i): C[:, i] = silu(g) * u; C has N/2 cols */
 };
+/* Optional workspace of the short-prompt ("tall stream-K") configuration: M <= 384 rows, all rows in one CTA, the (n-tile,
+ * k-block) units balanced over the SMs, split tiles combined through fp32 partials in this buffer.  The caller owns the memory
+ * (no hidden allocation): srgpt_gemm_workspace_bytes() bytes, 1024-byte aligned, ZEROED when registered, used by one stream at a
+ * time, alive until unregistered with (NULL, 0).  Without a workspace short prompts run on the default 128-row tiles. */
+long long srgpt_gemm_workspace_bytes(void);
+int srgpt_gemm_set_workspace(void* workspace, long long bytes);
 int srgpt_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                     const void* bias /*bf16[N] or NULL*/, const void* residual /*bf16 or NULL*/, int ldr,
                     int res_row_mod /*0 = none*/, int epilogue, int out_fp32, void* stream);

@@ -29,6 +29,8 @@ SIGNATURES = {
     "srgpt_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
     "srgpt_trace_begin": (ci, [vp, ci]),
     "srgpt_trace_end": (ci, []),
+    "srgpt_gemm_workspace_bytes": (cll, []),
+    "srgpt_gemm_set_workspace": (ci, [vp, cll]),
     "srgpt_gemm_bf16": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
     "srgpt_layernorm_bf16": (ci, [vp, ci, vp, vp, vp, ci, ci, ci, cf, ci, vp]),
     "srgpt_downsample_layernorm_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, vp]),

@@ -881,6 +881,225 @@ gemm_tall_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// "Tall stream-K" configuration for short prompts (M <= 384 rows: the S = 259 prompt of config c2, the B <= 128 last rows of a
+// batched lm_head).  These GEMMs stream the weights once and are bound by the bytes every SM has to ingest (smem capacity /
+// L2 latency ~ 85 GB/s per SM, DESIGN.md "GEMM"), so the design minimises exactly that:
+//   * ONE CTA holds ALL M rows (MT = ceil(M/128) accumulators of 128 x 128 in TMEM), so a weight tile is ingested once, not once
+//     per 128-row tile (3x for M = 259);
+//   * stream-K: the (n-tile, k-block) units are cut into gridDim.x equal contiguous ranges, one per SM, so every SM ingests the
+//     same number of bytes whatever N / 128 is (down_proj: 32 n-tiles x 3 row tiles = 96 CTAs of the default kernel left a third
+//     of the chip idle).  A tile whose k-range is split is owned by the CTA that holds its first k-block; the other CTAs write
+//     their fp32 partial accumulators to a workspace slot (at most one per CTA: only the FIRST segment of a range can start
+//     mid-tile) and raise an epoch flag; the owner adds the partials in CTA order (deterministic) and runs the fused epilogue.
+//     Owners only ever wait on FIRST segments of higher CTAs, which wait on nothing: no cycles; all CTAs are co-resident
+//     (grid <= number of SMs, one CTA per SM).
+// The workspace (flags + one slot per CTA) is registered by the caller with srgpt_gemm_set_workspace; without it this path is off.
+// ---------------------------------------------------------------------------------------------
+constexpr int TSK_BN = 128;
+constexpr int TSK_MAX_CTAS = 256;
+constexpr int TSK_FLAG_BYTES = TSK_MAX_CTAS * 4;
+constexpr long long TSK_SLOT_FLOATS = 3LL * BM * TSK_BN;  // MT = 3 accumulators of 128 x 128
+
+template <int MT>
+struct TskCfg {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
+  static constexpr int B_BYTES = TSK_BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // 32 / 48 / 64 KB
+  static constexpr int STAGES = MT == 3 ? 3 : (MT == 2 ? 4 : 6);  // 192 KB in flight in every case
+  static constexpr int TMEM_COLS = MT == 1 ? 128 : (MT == 2 ? 256 : 512);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+};
+
+struct TskWs {
+  float* partial;        // [gridDim.x][MT][128][128] fp32
+  unsigned int* flags;   // [gridDim.x], == epoch once CTA c's partial is complete
+  unsigned int epoch;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int EPI, int MT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p, const TskWs ws) {
+  using C = TskCfg<MT>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, BN = TSK_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const long long total = (long long)tiles_n * num_kb;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  auto range_begin = [&](int c) { return (int)(total * c / G); };
+  const int u_begin = range_begin(cta), u_end = range_begin(cta + 1);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    mbar_init(smem_u32(tmem_empty_bar), NUM_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_base_slot), C::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: runs ahead across segments =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = u_begin; u < u_end; ++u) {
+        const int tile = u / num_kb, kb = u - tile * num_kb;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, STAGE_BYTES);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) tma_load_2d(smem_u32(sa + mt * A_STAGE_BYTES), &tmap_a, fb, kb * BK, mt * BM);  // rows >= M zero-filled
+        tma_load_2d(smem_u32(sa + C::A_BYTES), &tmap_b, fb, kb * BK, tile * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      int u = u_begin;
+      while (u < u_end) {
+        const int tile = u / num_kb;
+        const int seg_end = min(u_end, (tile + 1) * num_kb);
+        mbar_wait(smem_u32(tmem_empty_bar), acc_phase ^ 1);
+        tcgen05_fence_after();
+        bool first = true;
+        for (; u < seg_end; ++u) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + C::A_BYTES);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr + mt * A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16(tmem_base + mt * BN, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(tmem_full_bar));
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9) =====================
+    const int lg = warp & 3, cpart = (warp - 2) >> 2;  // lane group (rows), column half of the 128-wide tile
+    uint32_t acc_phase = 0;
+    int u = u_begin;
+    while (u < u_end) {
+      const int tile = u / num_kb;
+      const int seg_end = min(u_end, (tile + 1) * num_kb);
+      const int k0 = u - tile * num_kb;
+      const bool owner = k0 == 0;
+      const int n0 = tile * BN;
+      // contributors of an owned, split tile: the CTAs after this one up to the one holding the tile's last k-block
+      int c_last = cta;
+      if (owner && seg_end < (tile + 1) * num_kb) {
+        const int last_unit = (tile + 1) * num_kb - 1;
+        while (c_last + 1 < G && range_begin(c_last + 1) <= last_unit) ++c_last;
+      }
+      mbar_wait(smem_u32(tmem_full_bar), acc_phase);
+      tcgen05_fence_after();
+      if (owner) {
+        for (int cc = cta + 1; cc <= c_last; ++cc) {  // partials complete?  (lane 0 polls, the warp follows)
+          if (lane == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_u32(ws.flags + cc) != ws.epoch) {
+              __nanosleep(64);
+              if (++spins > (1u << 24)) __trap();  // deadlock breaker
+            }
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt * BM >= p.M) break;  // warp-uniform
+        const int trow = lg * 32 + lane;  // row inside the 128-row accumulator
+        const int row = mt * BM + trow;
+#pragma unroll 1
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = cpart * 2 + ci;
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + mt * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
+          tmem_ld_wait();
+          if (!owner) {
+            float4* dst = reinterpret_cast<float4*>(ws.partial + ((size_t)cta * MT + mt) * (BM * BN) + (size_t)trow * BN + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          } else {
+            for (int cc = cta + 1; cc <= c_last; ++cc) {  // fixed order: deterministic sums
+              const float4* src = reinterpret_cast<const float4*>(ws.partial + ((size_t)cc * MT + mt) * (BM * BN) + (size_t)trow * BN + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 v = __ldcg(src + j);
+                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+              }
+            }
+            if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty_bar));
+      if (!owner) {
+        // publish the partial: every epilogue thread's stores, then one release store of the epoch
+        __threadfence();
+        named_bar_sync(1, 32 * NUM_EPI_WARPS);
+        if (warp == 2 && lane == 0) st_release_u32(ws.flags + cta, ws.epoch);
+      }
+      acc_phase ^= 1;
+      u = seg_end;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1042,12 +1261,68 @@ static int launch_tall(const void* A, int lda, const void* W, int ldw, const Par
   return SRGPT_OK;
 }
 
+// ---- tall stream-K: workspace registration + launch
+struct TskState {
+  void* base = nullptr;
+  long long bytes = 0;
+  unsigned int epoch = 0;
+};
+static TskState g_tsk;
+
+static long long tsk_workspace_bytes(int ctas) { return TSK_FLAG_BYTES + (long long)ctas * TSK_SLOT_FLOATS * 4; }
+
+template <int EPI, int MT>
+static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
+  using C = TskCfg<MT>;
+  static bool configured = false;
+  if (!configured) {
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tall_sk_kernel<EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  if (rc != SRGPT_OK) return rc;
+  rc = make_tmap(&tb, W, p.N, p.K, ldw, TSK_BN);
+  if (rc != SRGPT_OK) return rc;
+  const long long total = (long long)ceil_div(p.N, TSK_BN) * ceil_div(p.K, BK);
+  int grid = sm_count();
+  if (grid > TSK_MAX_CTAS) grid = TSK_MAX_CTAS;
+  if ((long long)grid > total) grid = (int)total;
+  while (tsk_workspace_bytes(grid) > g_tsk.bytes && grid > 1) --grid;  // a small workspace only narrows the grid
+  TskWs ws;
+  ws.flags = reinterpret_cast<unsigned int*>(g_tsk.base);
+  ws.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_tsk.base) + TSK_FLAG_BYTES);
+  if (++g_tsk.epoch == 0) g_tsk.epoch = 1;  // flags start at 0 (zeroed workspace) and never equal a future epoch
+  ws.epoch = g_tsk.epoch;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tall_sk_kernel<EPI, MT>, ta, tb, p, ws));
+  return SRGPT_OK;
+}
+
+template <int EPI>
+static int launch_tall_sk(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
+  const int mt = ceil_div(p.M, BM);
+  if (mt == 1) return launch_tall_sk_mt<EPI, 1>(A, lda, W, ldw, p, stream);
+  if (mt == 2) return launch_tall_sk_mt<EPI, 2>(A, lda, W, ldw, p, stream);
+  return launch_tall_sk_mt<EPI, 3>(A, lda, W, ldw, p, stream);
+}
+
 template <int EPI>
 static int launch(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
   // short prompts: all rows in one CTA, activation tile multicast across a 4-CTA cluster.  Implemented, parity-tested and
   // MEASURED SLOWER (profiles/r01_microbench_gemm_tall.jsonl: 259x4096x14336 147 vs 82 us, TTFT 17.6 vs 13.4 ms): multicast
   // removes L2 reads but every SM still has to ingest the whole 48 KB activation tile per k-block, and the per-SM TMA ingest
   // rate (~45 B/clk) is what bounds these kernels, not L2 read bandwidth.  Opt-in: SRGPT_GEMM_TALL=1.
+  // short prompts, default: the tall stream-K kernel (all rows in one CTA, k-ranges balanced over the SMs) whenever the caller
+  // registered a workspace and the weight matrix is big enough to be worth streaming (>= 4 MB); SRGPT_GEMM_TSK=-1 turns it off
+  static const int tsk_env = env_int("SRGPT_GEMM_TSK");
+  if (tsk_env >= 0 && g_tsk.base != nullptr && p.M <= TALL_MT * BM && (tsk_env > 0 || (long long)p.N * p.K * 2 >= (4LL << 20)) &&
+      g_tsk.bytes >= tsk_workspace_bytes(8))
+    return launch_tall_sk<EPI>(A, lda, W, ldw, p, stream);
   static const int tall_on = env_int("SRGPT_GEMM_TALL");
   if (tall_on && p.M > BM && p.M <= TALL_MT * BM && !p.out_fp32) {
     // 128-column tiles when they give every SM a tile, else 64-column tiles (more CTAs pulling weights)
@@ -1161,6 +1436,24 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
 }  // namespace srgpt
 
 using namespace srgpt;
+
+extern "C" __attribute__((visibility("default"))) long long srgpt_gemm_workspace_bytes(void) {
+  int n = sm_count();
+  if (n <= 0 || n > gemm::TSK_MAX_CTAS) n = gemm::TSK_MAX_CTAS;
+  return gemm::tsk_workspace_bytes(n);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_gemm_set_workspace(void* workspace, long long bytes) {
+  if (workspace == nullptr || bytes <= 0) {  // unregister
+    gemm::g_tsk = gemm::TskState{};
+    return SRGPT_OK;
+  }
+  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && bytes >= gemm::tsk_workspace_bytes(8));
+  gemm::g_tsk.base = workspace;
+  gemm::g_tsk.bytes = bytes;
+  gemm::g_tsk.epoch = 0;  // the caller hands over ZEROED memory
+  return SRGPT_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K,
                                const void* bias, const void* residual, int ldr, int res_row_mod, int epilogue,

@@ -202,6 +202,9 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
   //      to L2 with one bulk prefetch per row (cp.async.bulk.prefetch.L2, SASS UBLKPF).  A kernel whose CTAs are resident while
   //      its producer still runs (o_proj under the decode attention, gate/up under o_proj's tail, every kernel across the
   //      ~1 us dependency release) then keeps HBM streaming through what used to be idle gaps and later reads L2 hits.
+  //      MEASURED SLOWER on the in-graph timeline (profiles/r02_ab_decode_l2pf.txt: step 2.74 -> 2.93 ms; gate/up 35.4 -> 37.3 us,
+  //      down 20.4 -> 22.0 us, lm_head 146 -> 156 us exposed): the prefetch and the demand loads of the same rows race and both
+  //      reach DRAM.  Off by default; SRGPT_GEMV_L2PF=1 keeps the experiment reproducible.
   if (p.l2pf && active && lane < 2) {
     const int c_req = first_full ? (32 * NPRE + 128 * n_spre) : 0;  // chunks per row already requested above
     if (c_req < nchunk) {
@@ -424,7 +427,7 @@ static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
   q.spre = spre_default();
   static const int l2pf = [] {
     const char* v = getenv("SRGPT_GEMV_L2PF");
-    return (v != nullptr && v[0] != 0) ? atoi(v) : 1;
+    return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
   }();
   q.l2pf = l2pf;
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, PRE>, q));

@@ -53,12 +53,32 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> int:
     return t.stride(0)
 
 
+# workspace of the short-prompt GEMM configuration (include/srgpt_b200.h: srgpt_gemm_set_workspace): owned here, one per process,
+# registered on the first GEMM call on a device (the library keeps only the pointer)
+_GEMM_WS = None
+
+
+def _ensure_gemm_workspace(device) -> None:
+    global _GEMM_WS
+    if _GEMM_WS is not None:
+        return
+    lib = _lib.load()
+    n = int(lib.srgpt_gemm_workspace_bytes())
+    _GEMM_WS = torch.zeros(n + 1024, dtype=torch.uint8, device=device)
+    off = (-_GEMM_WS.data_ptr()) % 1024
+    torch.cuda.synchronize(device)  # the zero fill is complete before any kernel polls the flags
+    check(lib.srgpt_gemm_set_workspace(_GEMM_WS.data_ptr() + off, n), "srgpt_gemm_set_workspace")
+    global LAUNCHES
+    LAUNCHES -= 1
+
+
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None, out_fp32: bool = False,
          res_row_mod: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores."""
     _need(a, BF16, "gemm.a"); _need(w, BF16, "gemm.w")
+    _ensure_gemm_workspace(a.device)
     lda, ldw = _rowmajor2d(a, "gemm.a"), _rowmajor2d(w, "gemm.w")
     M, K = a.shape
     N, K2 = w.shape
@@ -372,6 +392,7 @@ def make_llama_layer_array(layers, kv_pages_per_layer):
 def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: int, D: int, heads: int, I: int, eps: float) -> torch.Tensor:
     """n_layers SigLIP encoder layers in place on x [n_img*T, D]."""
     _need(x, BF16, "siglip_layers.x")
+    _ensure_gemm_workspace(x.device)
     M = n_img * T
     dev = x.device
     ws_h = torch.empty((M, D), dtype=BF16, device=dev)
@@ -391,6 +412,7 @@ def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos,
     (page_table [cap], start_pos [1]) or, with cu_seqlens [n_seqs+1], n_seqs prompts packed back to back
     (page_table [n_seqs, cap], start_pos [n_seqs])."""
     _need(x, BF16, "llama_prefill_layers.x")
+    _ensure_gemm_workspace(x.device)
     n_seqs, pt_stride = 1, 0
     if cu_seqlens is not None:
         _need(cu_seqlens, torch.int32, "llama_prefill_layers.cu_seqlens")

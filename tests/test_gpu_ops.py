@@ -98,12 +98,49 @@ def test_gemm_cluster_multicast_path():
         "print('CLUSTER_OK')\n")
     # 2-CTA shared weight tile; 4-CTA shared activation tile (M <= 384); grouped tile rasterisation (3 m-units per group)
     # ... and the CTA-pair kernel (tcgen05 cta_group::2, one 256 x 256 tile per 2-CTA cluster) forced on for every shape
+    # ... the tall stream-K kernel forced on for every M <= 384 whatever the weight size / off everywhere, and the direct
+    # (non-TMA-store) epilogue
     for knob, val in (("SRGPT_GEMM_CL", "2"), ("SRGPT_GEMM_TALL", "1"), ("SRGPT_GEMM_GM", "3"), ("SRGPT_GEMM_PAIR", "1"),
-                      ("SRGPT_GEMM_EW", "16")):
+                      ("SRGPT_GEMM_EW", "16"), ("SRGPT_GEMM_TSK", "1"), ("SRGPT_GEMM_TSK", "-1"), ("SRGPT_GEMM_DIRECT_EPI", "1")):
         env = dict(os.environ, **{knob: val})
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert r.returncode == 0 and "CLUSTER_OK" in r.stdout, knob + ": " + r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(259, 6144, 4096, "none"), (259, 4096, 14336, "residual"), (259, 28672, 4096, "swiglu"),
+                                       (300, 4608, 1152, "gelu_erf"), (100, 20008, 1024, "bias"), (384, 1000, 4096, "none"),
+                                       (130, 520, 8200, "residual"), (3, 128259, 4096, "none")])
+def test_gemm_tall_stream_k(ops, M, N, K, epi):
+    """Short prompts (M <= 384): all rows in one CTA, (n-tile, k-block) units balanced over the SMs, split tiles combined through
+    fp32 partials (gemm_tall_sk_kernel).  Shapes above 4 MB of weights take this path by default; every epilogue; ragged M / N / K;
+    repeated launches (epoch flags) and bit-identical results across launches (deterministic partial order)."""
+    a, w = rnd(M, K, seed=21), rnd(N, K, seed=22, scale=K ** -0.5)
+    acc = a.float() @ w.float().t()
+    ad, wd = a.to(DEV), w.to(DEV)
+    bias, res = rnd(N, seed=23), rnd(M, N, seed=24)
+    if epi == "none":
+        ldc = (N + 7) // 8 * 8
+        run = lambda: ops.gemm(ad, wd, out=torch.empty(M, ldc, dtype=BF, device=DEV)[:, :N])  # noqa: E731
+        ref, tol = acc, BF16_1ROUND
+    elif epi == "bias":
+        run = lambda: ops.gemm(ad, wd, bias=bias.to(DEV), epilogue=ops.EPI_BIAS)  # noqa: E731
+        ref, tol = acc + bias.float(), BF16_1ROUND
+    elif epi == "gelu_erf":
+        run = lambda: ops.gemm(ad, wd, bias=bias.to(DEV), epilogue=ops.EPI_BIAS_GELU_ERF)  # noqa: E731
+        ref, tol = F.gelu(acc + bias.float()), BF16_CHAIN
+    elif epi == "residual":
+        def run():
+            x = res.to(DEV)
+            return ops.gemm(ad, wd, residual=x, epilogue=ops.EPI_BIAS_RESIDUAL, out=x)  # in place, as the decoder layers use it
+        ref, tol = acc + res.float(), BF16_CHAIN
+    else:
+        run = lambda: ops.gemm(ad, wd, epilogue=ops.EPI_SWIGLU)  # noqa: E731
+        ref, tol = F.silu(acc[:, 0::2]) * acc[:, 1::2], BF16_CHAIN
+    out1 = run()
+    assert_close(out1, ref, **tol, what=f"tall stream-K {epi}")
+    for _ in range(3):
+        assert torch.equal(run(), out1)
 
 
 def test_gemm_grouped_rasterisation_large_activation(ops):
