@@ -93,6 +93,8 @@ int srgpt_splice_rows_bf16(const void* src0, const void* src1, const void* src2,
  * GEMMs produce (see DESIGN.md "hres layout").  rscale = (float)(1.0 / scale_factor) exactly as ATen
  * computes it.  workspace: srgpt_mask_weights_workspace(n_img, M, side) bytes. */
 long long srgpt_mask_weights_workspace(int n_img, int M, int side);
+/* Layout of w (here and in srgpt_mask_pool_bf16): [n_img, M, ld] bf16 with ld = L rounded up to a multiple of 8 elements (16-byte
+ * rows for the TMA view of the pooling kernel; L = side^2 is odd for odd sides); the pad elements are never read. */
 int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW,
                        int side, float rscale, int order, void* stream);
 /* Mask pooling proper (base_extractor.py:74-78): out[i,m,:] = sum_l w[i,m,l] * x[i,l,:] — bf16 tensor-core
@@ -183,6 +185,36 @@ int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out
  * srgpt_lm_head_argmax_bf16 / srgpt_llama_decode_step_bf16 (which advanced *step) with step_offset = -1. */
 int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed, const int* step, int step_offset,
                            long long* out_ids, const void* embed_table, void* next_x, int K, void* stream);
+
+/* ---- batched decode (B sequences, one new token each; llava_arch.py:549-611 pads, modeling_llama.py:540-562 un-pads: here
+ * the rows are never padded).  The projections are srgpt_gemm_bf16 over the B rows (tall stream-K configuration: every weight is
+ * streamed once for the whole batch), RoPE / KV append is srgpt_rope_kv_append_varlen_bf16 with one row per sequence. */
+int srgpt_attention_decode_batched_bf16(const void* q, int q_ld, void* out, int o_ld, const void* kv_pages, const int* page_tables,
+                                        int pt_stride, int page_size, const int* kv_len_minus1, int batch, int n_heads, int n_kv_heads,
+                                        int head_dim, float scale, void* stream);
+/* ids [B] (the step's arg max per sequence) -> out_ids[*step * B + b], h[b, :] = embed_table[ids[b], :], ++pos[b], ++*step. */
+int srgpt_decode_batch_advance(const long long* ids, const void* embed_table, void* h, int H, long long* out_ids, int* step, int* pos,
+                               int B, void* ticket, void* stream);
+
+/* ---- tensor-parallel decode (SURVEY.md §8e "optional TP", BASELINE config c5; no reference counterpart, parity = TP-1) ----------
+ * Megatron-style sharding of the Llama decoder over `world` ranks: column-parallel fused QKV (a rank owns n_heads/world query
+ * heads and their kv heads) and gate/up, row-parallel o_proj / down_proj whose fp32 partial sums are all-reduced, vocabulary-
+ * parallel lm_head with an (value, index) all-gather.  The KV cache keeps the FULL layout on every rank (a rank only ever reads
+ * and writes its own kv heads), so prefill stays the replicated path. */
+int srgpt_gemv_tp_bf16(const void* x, const void* W, int ldw, void* y, int N, int K, const void* norm_weight, float eps, int mode,
+                       int n_heads, int n_kv_heads, int head_dim, const void* cos_tab, const void* sin_tab, const int* pos, void* kv_pages,
+                       const int* page_table, int page_size, int kv_heads_total, int kv_head_off, float* partial_f32, void* stream);
+int srgpt_attention_decode_tp_bf16(const void* q, void* out, const void* kv_pages, const int* page_table, int page_size,
+                                   const int* kv_len_minus1, int n_heads_local, int group, int n_kv_total, int kv_head_off, int head_dim,
+                                   float scale, void* stream);
+/* h[n] = bf16(bf16(partial[n]) + h[n]) after the all-reduce of the row-parallel partial sums (modeling_llama.py:668,682). */
+int srgpt_tp_residual_add_bf16(void* h, const float* partial, int n, void* stream);
+/* rows [index_base, index_base + V_local) of lm_head: best = device int[2] {best bf16-rounded logit (float bits), GLOBAL index}. */
+int srgpt_lm_head_local_best_bf16(const void* x, const void* W_local, int ldw, int V_local, int K, const void* norm_weight, float eps,
+                                  void* workspace, int index_base, int* best, void* stream);
+/* best_all = the all-gathered int[world][2]; writes out_ids[*step], next_x = embed_table[token], ++*step, ++*pos. */
+int srgpt_tp_pick_token(const int* best_all, int world, const void* embed_table, void* next_x, int K, long long* out_ids, int* step,
+                        int* pos, void* stream);
 
 /* ---- composite entry points (layers.cu): one call per tower pass / prompt / decode step -------------------
  * Pure sequencing of the kernels above on `stream` (no allocation, no sync); they exist because a Python-side

@@ -55,6 +55,13 @@ SIGNATURES = {
     "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
     "srgpt_argmax_bf16": (ci, [vp, ci, ci, ci, vp, vp]),
     "srgpt_sample_top_p_f32": (ci, [vp, ci, vp, C.c_ulonglong, vp, ci, vp, vp, vp, ci, vp]),
+    "srgpt_attention_decode_batched_bf16": (ci, [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, cf, vp]),
+    "srgpt_decode_batch_advance": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, vp, vp]),
+    "srgpt_gemv_tp_bf16": (ci, [vp, vp, ci, vp, ci, ci, vp, cf, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]),
+    "srgpt_attention_decode_tp_bf16": (ci, [vp, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
+    "srgpt_tp_residual_add_bf16": (ci, [vp, vp, ci, vp]),
+    "srgpt_lm_head_local_best_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, ci, vp, vp]),
+    "srgpt_tp_pick_token": (ci, [vp, ci, vp, vp, ci, vp, vp, vp, vp]),
     "srgpt_siglip_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]),
     "srgpt_llama_prefill_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, ci, vp, ci, ci, vp]),
     "srgpt_llama_decode_step_bf16": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp,

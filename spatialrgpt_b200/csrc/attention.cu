@@ -321,11 +321,17 @@ __device__ __forceinline__ void dec_load_kv(const bf16* __restrict__ kv_pages, c
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf16* __restrict__ kv_pages,
                    const int* __restrict__ page_table, int page_size, const int* __restrict__ kv_len_minus1, int n_kv_heads,
-                   int group, float scale_log2, unsigned long long* trace, int prefetch) {
+                   int group, float scale_log2, unsigned long long* trace, int prefetch, int kv_head_off, int q_ld, int o_ld, int pt_stride) {
   constexpr int HD = 128;
+  // batched decode (gridDim.y sequences, one new token each): row b of q / out, page table b, position b
+  q += (size_t)blockIdx.y * q_ld;
+  out += (size_t)blockIdx.y * o_ld;
+  page_table += (size_t)blockIdx.y * pt_stride;
+  kv_len_minus1 += blockIdx.y;
   __shared__ float s_m[DEC_HW], s_l[DEC_HW];
   __shared__ float s_acc[DEC_HW][HD];
-  const int head = blockIdx.x, kvh = head / group;
+  // tensor parallelism: q / out hold this rank's heads only, the cache keeps the full layout (n_kv_heads = heads per cache row)
+  const int head = blockIdx.x, kvh = head / group + kv_head_off;
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const size_t row_stride = (size_t)n_kv_heads * HD;
   trace_mark(trace, 0);
@@ -558,6 +564,54 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bf1
   static const bool no_prefetch = env_flag("SRGPT_ATTN_NO_PREFETCH");
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn::attn_decode_kernel, reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out),
                                       reinterpret_cast<const bf16*>(kv_pages), page_table, page_size, kv_len_minus1, n_kv_heads,
-                                      n_heads / n_kv_heads, scale * 1.4426950408889634f, trace_next_slot(), no_prefetch ? 0 : 1));
+                                      n_heads / n_kv_heads, scale * 1.4426950408889634f, trace_next_slot(), no_prefetch ? 0 : 1, 0, 0, 0, 0));
+  return SRGPT_OK;
+}
+
+// B sequences, one new token each (batched decode): q rows [B, q_ld] (e.g. the q columns of a fused qkv buffer), out [B, o_ld],
+// page_tables [B, pt_stride], kv_len_minus1 [B] (position of each sequence's newest row).
+extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_batched_bf16(const void* q, int q_ld, void* out, int o_ld, const void* kv_pages,
+                                                                                          const int* page_tables, int pt_stride, int page_size,
+                                                                                          const int* kv_len_minus1, int batch, int n_heads, int n_kv_heads,
+                                                                                          int head_dim, float scale, void* stream) {
+  SRGPT_CHECK_ARG(q && out && kv_pages && page_tables && kv_len_minus1 && batch > 0 && batch <= 65535);
+  SRGPT_CHECK_ARG(n_heads > 0 && n_kv_heads > 0 && (n_heads % n_kv_heads) == 0 && page_size > 0 && pt_stride > 0);
+  SRGPT_CHECK_ARG(aligned16(q) && aligned16(kv_pages) && (q_ld % 8) == 0 && q_ld >= n_heads * head_dim && o_ld >= n_heads * head_dim);
+  if (head_dim != 128) {
+    set_last_error("srgpt_attention_decode_batched_bf16: head_dim %d unsupported (128 only)", head_dim);
+    return SRGPT_ERR_UNSUPPORTED;
+  }
+  attn::attn_decode_kernel<<<dim3(n_heads, batch), attn::DEC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(kv_pages), page_tables, page_size, kv_len_minus1,
+      n_kv_heads, n_heads / n_kv_heads, scale * 1.4426950408889634f, nullptr, 1, 0, q_ld, o_ld, pt_stride);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+// One rank of a tensor-parallel decoder: n_heads_local query heads (q / out are [n_heads_local * 128]) over kv heads
+// [kv_head_off, kv_head_off + n_heads_local / group) of a cache whose rows hold n_kv_total heads.
+extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_tp_bf16(const void* q, void* out, const void* kv_pages, const int* page_table, int page_size,
+                                                                                     const int* kv_len_minus1, int n_heads_local, int group, int n_kv_total,
+                                                                                     int kv_head_off, int head_dim, float scale, void* stream) {
+  SRGPT_CHECK_ARG(q && out && kv_pages && page_table && kv_len_minus1);
+  SRGPT_CHECK_ARG(n_heads_local > 0 && group > 0 && (n_heads_local % group) == 0 && page_size > 0);
+  SRGPT_CHECK_ARG(kv_head_off >= 0 && kv_head_off + n_heads_local / group <= n_kv_total);
+  SRGPT_CHECK_ARG(aligned16(q) && aligned16(kv_pages));
+  if (head_dim != 128) {
+    set_last_error("srgpt_attention_decode_tp_bf16: head_dim %d unsupported (128 only)", head_dim);
+    return SRGPT_ERR_UNSUPPORTED;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_heads_local);
+  cfg.blockDim = dim3(attn::DEC_THREADS);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn::attn_decode_kernel, reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out),
+                                      reinterpret_cast<const bf16*>(kv_pages), page_table, page_size, kv_len_minus1, n_kv_total, group,
+                                      scale * 1.4426950408889634f, trace_next_slot(), 1, kv_head_off, 0, 0, 0));
   return SRGPT_OK;
 }

@@ -1085,6 +1085,12 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __threadfence();
         named_bar_sync(1, 32 * NUM_EPI_WARPS);
         if (warp == 2 && lane == 0) st_release_u32(ws.flags + cta, ws.epoch);
+      } else if (c_last > cta) {
+        // every epilogue warp has consumed the contributors' partials: clear their flags, so that a CUDA-graph REPLAY of this
+        // launch (same baked epoch) starts from zeroed flags again
+        named_bar_sync(1, 32 * NUM_EPI_WARPS);
+        if (warp == 2 && lane == 0)
+          for (int cc = cta + 1; cc <= c_last; ++cc) st_release_u32(ws.flags + cc, 0u);
       }
       acc_phase ^= 1;
       u = seg_end;
@@ -1320,8 +1326,13 @@ static int launch(const void* A, int lda, const void* W, int ldw, const Params& 
   // short prompts, default: the tall stream-K kernel (all rows in one CTA, k-ranges balanced over the SMs) whenever the caller
   // registered a workspace and the weight matrix is big enough to be worth streaming (>= 4 MB); SRGPT_GEMM_TSK=-1 turns it off
   static const int tsk_env = env_int("SRGPT_GEMM_TSK");
-  if (tsk_env >= 0 && g_tsk.base != nullptr && p.M <= TALL_MT * BM && (tsk_env > 0 || (long long)p.N * p.K * 2 >= (4LL << 20)) &&
-      g_tsk.bytes >= tsk_workspace_bytes(8))
+  // MEASURED (profiles/r02_ab_gemm_tsk.txt): at 128 < M <= 384 the tall tiles LOSE to the default 128-row tiles (259 x 6144 x 4096:
+  // 69 vs 37 us, gate/up 117 vs 97 us, down 118 vs 85 us; TTFT 16.7 vs 12.4 ms) - three 64 KB stages keep fewer bytes in flight than
+  // six 32 KB ones, a third of every A stage is zero fill, and the un-overlapped fix-up epilogue stalls the single accumulator set -
+  // so that range is opt-in (SRGPT_GEMM_TSK=1).  At M <= 128 (one accumulator, 32 KB stages, the batched-decode projections and the
+  // batched lm_head) stream-K is what fills the chip: N / 128 tiles alone leave most SMs idle.
+  const bool tsk_default = p.M <= BM && (long long)p.N * p.K * 2 >= (4LL << 20);
+  if (tsk_env >= 0 && g_tsk.base != nullptr && p.M <= TALL_MT * BM && (tsk_env > 0 || tsk_default) && g_tsk.bytes >= tsk_workspace_bytes(8))
     return launch_tall_sk<EPI>(A, lda, W, ldw, p, stream);
   static const int tall_on = env_int("SRGPT_GEMM_TALL");
   if (tall_on && p.M > BM && p.M <= TALL_MT * BM && !p.out_fp32) {

@@ -54,6 +54,10 @@ struct Params {
   unsigned long long* trace;  // optional timeline record (srgpt_trace_begin)
   int spre;                   // number of extra 4-chunk batches per row staged in shared memory before the wait (0..SPRE_MAX)
   int l2pf;                   // 1: the rest of the warp's two rows is requested into L2 (bulk prefetch) before the dependency wait
+  // tensor parallelism (srgpt_gemv_tp_bf16): this rank's slice of the heads / of the reduction dimension
+  int kv_heads_total;         // KV-cache row = kv_heads_total * hd elements (0: n_kv_heads); the rank writes heads [kv_head_off, +n_kv_heads)
+  int kv_head_off;
+  float* y_f32;               // PLAIN mode: un-rounded fp32 partial dot products go here instead of bf16 y (+ residual)
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -287,7 +291,10 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
   float best = -INFINITY;
   int besti = 0x7fffffff;
   if (active && lane == 0) {
-    if (MODE == SRGPT_GEMV_PLAIN) {
+    if (MODE == SRGPT_GEMV_PLAIN && p.y_f32 != nullptr) {
+      // row-parallel linear of a tensor-parallel rank: the partial sums over this rank's K slice, reduced across ranks afterwards
+      *reinterpret_cast<float2*>(p.y_f32 + r0) = make_float2(a0, a1);
+    } else if (MODE == SRGPT_GEMV_PLAIN) {
       float y0 = bf16_round(a0), y1 = bf16_round(a1);
       if (p.residual != nullptr) {
         y0 += __bfloat162float(p.residual[r0]);
@@ -316,8 +323,9 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
       } else {
         const int page = p.page_table[pos / p.page_size], slot = pos % p.page_size;
         const bool is_v = head >= p.n_heads + p.n_kv_heads;
-        const int kh = head - p.n_heads - (is_v ? p.n_kv_heads : 0);
-        bf16* dst = p.kv_pages + (((size_t)page * 2 + (is_v ? 1 : 0)) * p.page_size + slot) * p.n_kv_heads * p.hd + kh * p.hd;
+        const int kh = head - p.n_heads - (is_v ? p.n_kv_heads : 0) + p.kv_head_off;
+        const int kv_row = (p.kv_heads_total > 0 ? p.kv_heads_total : p.n_kv_heads) * p.hd;
+        bf16* dst = p.kv_pages + (((size_t)page * 2 + (is_v ? 1 : 0)) * p.page_size + slot) * kv_row + kh * p.hd;
         dst[j] = __float2bfloat16_rn(v0);
         dst[j + half] = __float2bfloat16_rn(v1);
       }
@@ -385,6 +393,71 @@ lm_head_finalize_kernel(const float* __restrict__ part_val, const int* __restric
     *step += 1;
     *pos += 1;
   }
+}
+
+// ---- tensor-parallel helpers ------------------------------------------------------------------------
+// vocabulary-parallel lm_head: this rank's best (bf16-rounded logit, GLOBAL row index) -> best[0] = value bits, best[1] = index
+__global__ void __launch_bounds__(256)
+lm_head_local_best_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int nparts, int index_base, int* __restrict__ best) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+    if (better(part_val[i], part_idx[i], bv, bi)) { bv = part_val[i]; bi = part_idx[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+    best[0] = __float_as_int(bv);
+    best[1] = (bi == 0x7fffffff) ? index_base : bi + index_base;
+  }
+}
+
+// after the all-gather of every rank's (value, index): the global arg max (lowest index on ties, like torch.argmax), then the same
+// bookkeeping as lm_head_finalize_kernel (token id, next embedding row, ++step, ++pos); identical on every rank
+__global__ void __launch_bounds__(256)
+tp_pick_token_kernel(const int* __restrict__ best_all, int world, const bf16* __restrict__ embed_table, bf16* __restrict__ next_x, int K,
+                     long long* __restrict__ out_ids, int* step, int* pos) {
+  __shared__ int s_tok;
+  if (threadIdx.x == 0) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int r = 0; r < world; ++r) {
+      const float v = __int_as_float(best_all[2 * r]);
+      const int i = best_all[2 * r + 1];
+      if (better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    s_tok = bi;
+    out_ids[*step] = (long long)bi;
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  if (embed_table != nullptr && next_x != nullptr) {
+    const uint4* src = reinterpret_cast<const uint4*>(embed_table + (size_t)tok * K);
+    for (int c = threadIdx.x; c < (K >> 3); c += blockDim.x) reinterpret_cast<uint4*>(next_x)[c] = src[c];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *step += 1;
+    *pos += 1;
+  }
+}
+
+// h = bf16(bf16(sum of the ranks' partial dot products) + h): the rounding points of `residual + o_proj(x)` (modeling_llama.py:668,682)
+__global__ void __launch_bounds__(256) tp_residual_add_kernel(bf16* __restrict__ h, const float* __restrict__ partial, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) h[i] = __float2bfloat16_rn(bf16_round(partial[i]) + __bfloat162float(h[i]));
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -501,6 +574,95 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemv_bf16(const void
       return gemv::launch<SRGPT_GEMV_QKV_ROPE>(p, N / 2, st);
   }
   return SRGPT_ERR_INVALID;
+}
+
+// Tensor-parallel variants of the decode GEMV (SURVEY.md §8e "optional TP", BASELINE config c5): a rank owns n_heads q heads and
+// n_kv_heads kv heads of the fused qkv projection (column parallel; K/V rows land in the FULL-layout cache at kv_head_off), and a K
+// slice of o_proj / down_proj (row parallel): PLAIN mode with partial_f32 != NULL writes the un-rounded fp32 partial sums that the
+// ranks then all-reduce.  Everything else is srgpt_gemv_bf16.
+extern "C" __attribute__((visibility("default"))) int srgpt_gemv_tp_bf16(const void* x, const void* W, int ldw, void* y, int N, int K, const void* norm_weight, float eps,
+                                                                         int mode, int n_heads, int n_kv_heads, int head_dim, const void* cos_tab, const void* sin_tab,
+                                                                         const int* pos, void* kv_pages, const int* page_table, int page_size, int kv_heads_total,
+                                                                         int kv_head_off, float* partial_f32, void* stream) {
+  SRGPT_CHECK_ARG(x && W && N > 0 && K > 0 && (y != nullptr || partial_f32 != nullptr));
+  SRGPT_CHECK_ARG((N % 2) == 0 && (K % 8) == 0 && (ldw % 8) == 0 && ldw >= K && K * 2 <= 200 * 1024);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(W) && (norm_weight == nullptr || aligned16(norm_weight)));
+  SRGPT_CHECK_ARG(mode == SRGPT_GEMV_PLAIN || mode == SRGPT_GEMV_QKV_ROPE);
+  gemv::Params p = {};
+  p.x = reinterpret_cast<const bf16*>(x);
+  p.W = reinterpret_cast<const bf16*>(W);
+  p.ldw = ldw;
+  p.y = reinterpret_cast<bf16*>(y);
+  p.N = N; p.K = K;
+  p.norm_weight = reinterpret_cast<const bf16*>(norm_weight);
+  p.eps = eps;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mode == SRGPT_GEMV_PLAIN) {
+    SRGPT_CHECK_ARG(partial_f32 != nullptr && (reinterpret_cast<uintptr_t>(partial_f32) & 7) == 0);
+    p.hd = 2;
+    p.y_f32 = partial_f32;
+    return gemv::launch<SRGPT_GEMV_PLAIN>(p, N / 2, st);
+  }
+  SRGPT_CHECK_ARG(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 3) == 0 && x != y);
+  SRGPT_CHECK_ARG(n_heads > 0 && n_kv_heads > 0 && head_dim > 0 && (head_dim % 2) == 0 && N == (n_heads + 2 * n_kv_heads) * head_dim);
+  SRGPT_CHECK_ARG(cos_tab && sin_tab && pos && kv_pages && page_table && page_size > 0);
+  SRGPT_CHECK_ARG(kv_heads_total >= n_kv_heads && kv_head_off >= 0 && kv_head_off + n_kv_heads <= kv_heads_total);
+  p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.hd = head_dim;
+  p.cos_tab = reinterpret_cast<const bf16*>(cos_tab);
+  p.sin_tab = reinterpret_cast<const bf16*>(sin_tab);
+  p.pos = pos;
+  p.kv_pages = reinterpret_cast<bf16*>(kv_pages);
+  p.page_table = page_table;
+  p.page_size = page_size;
+  p.kv_heads_total = kv_heads_total;
+  p.kv_head_off = kv_head_off;
+  return gemv::launch<SRGPT_GEMV_QKV_ROPE>(p, N / 2, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_tp_residual_add_bf16(void* h, const float* partial, int n, void* stream) {
+  SRGPT_CHECK_ARG(h && partial && n > 0);
+  gemv::tp_residual_add_kernel<<<ceil_div(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<bf16*>(h), partial, n);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+// Vocabulary-parallel lm_head of one rank: rows [index_base, index_base + V_local) of the table.  best = device int[2]
+// {bf16-rounded best logit (float bits), its GLOBAL row index}; all-gather the pairs, then srgpt_tp_pick_token.
+extern "C" __attribute__((visibility("default"))) int srgpt_lm_head_local_best_bf16(const void* x, const void* W_local, int ldw, int V_local, int K, const void* norm_weight,
+                                                                                    float eps, void* workspace, int index_base, int* best, void* stream) {
+  SRGPT_CHECK_ARG(x && W_local && workspace && best && V_local > 0 && K > 0 && index_base >= 0);
+  SRGPT_CHECK_ARG((K % 8) == 0 && (ldw % 8) == 0 && ldw >= K && K * 2 <= 200 * 1024);
+  SRGPT_CHECK_ARG(aligned16(x) && aligned16(W_local) && (norm_weight == nullptr || aligned16(norm_weight)));
+  const int npairs = (V_local + 1) / 2;
+  const int g = gemv::grid_for(npairs);
+  gemv::Params p = {};
+  p.x = reinterpret_cast<const bf16*>(x);
+  p.W = reinterpret_cast<const bf16*>(W_local);
+  p.ldw = ldw; p.N = V_local; p.K = K;
+  p.norm_weight = reinterpret_cast<const bf16*>(norm_weight);
+  p.eps = eps;
+  p.hd = 2;
+  p.part_val = reinterpret_cast<float*>(workspace);
+  p.part_idx = reinterpret_cast<int*>(p.part_val + g);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = gemv::launch<gemv::MODE_LM>(p, npairs, st);
+  if (rc != SRGPT_OK) return rc;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  gemv::pdl_config(cfg, attr, 1, 256, 0, st);
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv::lm_head_local_best_kernel, (const float*)p.part_val, (const int*)p.part_idx, g, index_base, best));
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_tp_pick_token(const int* best_all, int world, const void* embed_table, void* next_x, int K, long long* out_ids,
+                                                                          int* step, int* pos, void* stream) {
+  SRGPT_CHECK_ARG(best_all && world > 0 && out_ids && step && pos);
+  SRGPT_CHECK_ARG((embed_table == nullptr) == (next_x == nullptr));
+  SRGPT_CHECK_ARG(embed_table == nullptr || ((K % 8) == 0 && aligned16(embed_table) && aligned16(next_x)));
+  gemv::tp_pick_token_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(best_all, world, reinterpret_cast<const bf16*>(embed_table),
+                                                                                  reinterpret_cast<bf16*>(next_x), K, out_ids, step, pos);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) long long srgpt_lm_head_workspace(int V) {

@@ -10,6 +10,7 @@
 //       + ((y&1)*2 + (x&1)).  This is the order in which the two ConvTranspose2d(k=2,s=2) GEMMs emit
 //       pixels, so the refinement never needs a pixel-shuffle pass over the 37.7 MB/image tensor.
 #include "common.cuh"
+#include "tcgen05.cuh"
 #include "srgpt_b200.h"
 
 namespace srgpt {
@@ -47,6 +48,9 @@ __device__ __forceinline__ float bilinear_tap(const T* __restrict__ img, int IH,
 //   pass 2  same grid: denorm = bf16(bf16(sum) + 1e-8) (base_extractor.py:61), w = bf16(v / denorm)
 // ---------------------------------------------------------------------------------------------
 constexpr int MW_SPLITS = 16;
+// rows of the pooling-weight matrices [n_img, M, L] are padded to a multiple of 8 elements (16 bytes): the TMA view of mask_pool_kernel
+// needs 16-byte row strides and L = side^2 is odd for odd sides (27 x 27 tower tokens of a 384-px SigLIP)
+__host__ __device__ __forceinline__ int mask_row_ld(int L) { return (L + 7) & ~7; }
 
 // MaskPooling.forward is a chain of four small kernels (taps -> normalise -> pool -> reduce); at one image each lasts 1-8 us, so
 // the launch gaps between them were a third of the whole op.  Every kernel after the first is a PROGRAMMATIC DEPENDENT launch: it
@@ -64,7 +68,7 @@ mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __res
   const int split = blockIdx.x, m = blockIdx.y, img = blockIdx.z;
   const T* src = masks + ((size_t)img * M + m) * IH * IW;
   const int L = side * side;
-  bf16* dst = w + ((size_t)img * M + m) * L;
+  bf16* dst = w + ((size_t)img * M + m) * mask_row_ld(L);
   const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
   const int l_end = min(L, (split + 1) * per);
   float sum = 0.f;
@@ -88,8 +92,8 @@ mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, const fl
 #pragma unroll
   for (int i = 0; i < MW_SPLITS; ++i) total += ps[i];
   const float denorm = bf16_round(bf16_round(total) + 1e-8f);
-  const bf16* src = v + ((size_t)img * M + m) * L;
-  bf16* dst = w + ((size_t)img * M + m) * L;
+  const bf16* src = v + ((size_t)img * M + m) * mask_row_ld(L);
+  bf16* dst = w + ((size_t)img * M + m) * mask_row_ld(L);
   const int per = (L + MW_SPLITS - 1) / MW_SPLITS;
   const int l_end = min(L, (split + 1) * per);
   // rows are a permutation of l; normalising the contiguous range [split*per, l_end) of ROWS covers every row once
@@ -114,109 +118,99 @@ constexpr int MP_THREADS = 256;
 constexpr int MP_CH = 128;        // channels per CTA
 constexpr int MP_MT = 16;         // masks per pass (MMA M)
 constexpr int MP_SROWS = 64;      // feature rows per pipeline stage
-constexpr int MP_NST = 4;         // pipeline stages
-constexpr int MP_XLD = MP_CH + 8; // smem row stride of the feature tile (elements): +16 B -> conflict-free ldmatrix
-constexpr int MP_WLD = MP_SROWS + 8;
+constexpr int MP_NST = 5;         // pipeline stages
 constexpr int MP_MAX_ROWS = 1024; // rows per CTA upper bound (planning only)
-constexpr int MP_STAGE_X = MP_SROWS * MP_XLD;  // elements
-constexpr int MP_STAGE_W = MP_MT * MP_WLD;
-constexpr int MP_SMEM_BYTES = MP_NST * (MP_STAGE_X + MP_STAGE_W) * 2;
+constexpr int MP_X_BOX = MP_SROWS * 128;                 // one TMA box: 64 rows x 64 channels, 128-byte rows, SWIZZLE_128B (8 KB)
+constexpr int MP_STAGE_X = 2 * MP_X_BOX;                 // channels [0, 64) and [64, 128)
+constexpr int MP_STAGE_W = MP_MT * 128;                  // 16 masks x 64 rows of weights, 128-byte rows, SWIZZLE_128B (2 KB)
+constexpr int MP_STAGE_BYTES = MP_STAGE_X + MP_STAGE_W;  // 18 KB
+constexpr int MP_SMEM_BYTES = MP_NST * MP_STAGE_BYTES + 1024 /*alignment*/ + 64 /*barriers*/;
 
 __device__ __forceinline__ uint32_t mp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mp_cp_async16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(mp_smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void mp_tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(x), "r"(y)
+               : "memory");
 }
 
+// Round 2: the feature / weight tiles arrive by TMA (cp.async.bulk.tensor, one elected thread, SASS UTMALDG) into 128B-swizzled
+// tiles that ldmatrix reads conflict-free, 5 stages of 18 KB per CTA, completion on mbarriers.  Round 1 issued 1024 16-byte
+// cp.async per stage from all threads and kept 3 stages in flight: ncu showed the kernel waiting on memory (long scoreboard) at 31 %
+// of the DRAM throughput (profiles/r02_ncu_full_mask_pool_summary.txt).  Rows past the end of an image belong to the NEXT image in the
+// flattened [(n_img L), C] view; their weights are out of bounds in the [(n_img M), L] view of w and arrive as zeros, so they add 0.
 __global__ void __launch_bounds__(MP_THREADS, 2)
-mask_pool_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, float* __restrict__ partial, int M, int L, int C,
+mask_pool_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, float* __restrict__ partial, int M, int L, int C,
                  int rows_per_cta, int R) {
-  extern __shared__ __align__(16) uint8_t mp_smem[];
-  bf16* sx = reinterpret_cast<bf16*>(mp_smem);                     // [NST][SROWS][XLD]
-  bf16* sw = sx + MP_NST * MP_STAGE_X;                              // [NST][MT][WLD]
+  extern __shared__ uint8_t mp_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mp_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + MP_NST * MP_STAGE_BYTES);
   const int img = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cbase = blockIdx.y * MP_CH;
   const int l0 = blockIdx.x * rows_per_cta;
   const int nrows = min(rows_per_cta, L - l0);
   const int nstages = (nrows + MP_SROWS - 1) / MP_SROWS;
-  const bf16* xb = x + ((size_t)img * L + l0) * C;
   const int lr = lane & 7, lmat = lane >> 3, g = lane >> 2, t4 = lane & 3;
-  // before the dependency wait: the feature rows of this CTA (independent of the mask weights being normalised by the producer)
-  // are requested into L2, one 128-byte line per thread and step; a hint only, so it is safe whatever wrote x
-  {
-    const int lines_per_row = (min(MP_CH, C - cbase) * 2 + 127) / 128;
-    for (int i = threadIdx.x; i < nrows * lines_per_row; i += MP_THREADS) {
-      const int r = i / lines_per_row, ln = i - r * lines_per_row;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (size_t)r * C + cbase + ln * 64));
-    }
+  const uint32_t sbase = mp_smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmap_x);
+    tc::prefetch_tmap(&tmap_w);
+    for (int i = 0; i < MP_NST; ++i) tc::mbar_init(mp_smem_u32(&full_bar[i]), 1);
+    tc::fence_barrier_init();
   }
+  __syncthreads();
   chain_launch_dependents();
-  chain_wait();
+  chain_wait();  // the normalised weights of the producer kernel are visible (the feature rows were written long before)
 
-  for (int m0 = 0; m0 < M; m0 += MP_MT) {
+  const int n_pass = (M + MP_MT - 1) / MP_MT;
+  const int total = n_pass * nstages;  // global stage index gs = pass * nstages + st; slot = gs % NST, parity = (gs / NST) & 1
+  auto issue = [&](int gs) {           // thread 0 only
+    const int pass = gs / nstages, st = gs - pass * nstages;
+    const uint32_t slot = sbase + (gs % MP_NST) * MP_STAGE_BYTES;
+    const uint32_t bar = mp_smem_u32(&full_bar[gs % MP_NST]);
+    tc::mbar_expect_tx(bar, MP_STAGE_BYTES);  // out-of-bounds parts are zero-filled and still counted
+    const int row = img * L + l0 + st * MP_SROWS;
+    mp_tma_load_2d(slot, &tmap_x, bar, cbase, row);
+    mp_tma_load_2d(slot + MP_X_BOX, &tmap_x, bar, cbase + 64, row);
+    mp_tma_load_2d(slot + MP_STAGE_X, &tmap_w, bar, l0 + st * MP_SROWS, img * M + pass * MP_MT);
+  };
+  if (threadIdx.x == 0)
+    for (int gs = 0; gs < MP_NST && gs < total; ++gs) issue(gs);
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int m0 = pass * MP_MT;
     const int mt = min(MP_MT, M - m0);
-    const bf16* wb = w + ((size_t)img * M + m0) * L + l0;
-
-    auto issue = [&](int st) {  // stage `st` of this CTA's rows -> ring slot st % NST (zero-filled outside the tensor)
-      bf16* dx = sx + (st % MP_NST) * MP_STAGE_X;
-      bf16* dw = sw + (st % MP_NST) * MP_STAGE_W;
-      const int r0 = st * MP_SROWS;
-      for (int i = threadIdx.x; i < MP_SROWS * (MP_CH / 8); i += MP_THREADS) {
-        const int r = i >> 4, ch = (i & 15) * 8;
-        const bool ok = (r0 + r < nrows) && (cbase + ch < C);
-        const bf16* src = ok ? xb + (size_t)(r0 + r) * C + cbase + ch : x;
-        mp_cp_async16(dx + r * MP_XLD + ch, src, ok ? 16 : 0);
-      }
-      if (threadIdx.x < MP_MT * (MP_SROWS / 8)) {  // 16 masks x 8 chunks of 8 rows
-        const int mm = threadIdx.x >> 3, rc = (threadIdx.x & 7) * 8;
-        // a 16-byte chunk of weights is used only when all 8 rows are inside the CTA's range and 16-byte aligned
-        const bool ok = (mm < mt) && (r0 + rc + 8 <= nrows) && ((((size_t)(wb - w) + (size_t)mm * L + r0 + rc) & 7) == 0);
-        if (ok) {
-          mp_cp_async16(dw + mm * MP_WLD + rc, wb + (size_t)mm * L + r0 + rc, 16);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            dw[mm * MP_WLD + rc + k] = (mm < mt && r0 + rc + k < nrows) ? wb[(size_t)mm * L + r0 + rc + k] : __float2bfloat16_rn(0.f);
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    __syncthreads();  // ring is free (previous pass finished)
-    for (int st = 0; st < MP_NST - 1; ++st) {
-      if (st < nstages) issue(st);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
-    }
     float acc[2][4];
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-
     for (int st = 0; st < nstages; ++st) {
-      asm volatile("cp.async.wait_group %0;" ::"n"(MP_NST - 2) : "memory");
-      __syncthreads();  // stage st visible to every warp; slot (st-1) % NST is free again
-      if (st + MP_NST - 1 < nstages) issue(st + MP_NST - 1);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
-      const bf16* tx = sx + (st % MP_NST) * MP_STAGE_X;
-      const bf16* tw = sw + (st % MP_NST) * MP_STAGE_W;
+      const int gs = pass * nstages + st;
+      tc::mbar_wait(mp_smem_u32(&full_bar[gs % MP_NST]), (uint32_t)(gs / MP_NST) & 1u);
+      const uint32_t tx = sbase + (gs % MP_NST) * MP_STAGE_BYTES;
+      const uint32_t tw = tx + MP_STAGE_X;
 #pragma unroll
       for (int kk = 0; kk < MP_SROWS / 16; ++kk) {
         uint32_t a[4], b[4];
-        // A (weights [m][l]): matrices (m0..7,k0..7) (m8..15,k0..7) (m0..7,k8..15) (m8..15,k8..15)
-        const bf16* ap = tw + (lr + (lmat & 1) * 8) * MP_WLD + kk * 16 + (lmat >> 1) * 8;
+        // A (weights [m][l], 128-byte rows, 16-byte chunk c of row m at ((c ^ (m & 7)) << 4)):
+        //   matrices (m0..7,k0..7) (m8..15,k0..7) (m0..7,k8..15) (m8..15,k8..15)
+        const int am = lr + (lmat & 1) * 8, ac = kk * 2 + (lmat >> 1);
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(mp_smem_u32(ap)));
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(tw + am * 128 + ((ac ^ (am & 7)) << 4)));
         // B (features [l][c], transposed on load): (k0..7,c0..7) (k8..15,c0..7) (k0..7,c8..15) (k8..15,c8..15)
-        const bf16* bp = tx + (kk * 16 + lr + (lmat & 1) * 8) * MP_XLD + warp * 16 + (lmat >> 1) * 8;
+        const int bl = kk * 16 + lr + (lmat & 1) * 8, c0 = warp * 16 + (lmat >> 1) * 8;
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(mp_smem_u32(bp)));
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                     : "r"(tx + (c0 >> 6) * MP_X_BOX + bl * 128 + ((((c0 & 63) >> 3) ^ (bl & 7)) << 4)));
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
           asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                        : "+f"(acc[nb][0]), "+f"(acc[nb][1]), "+f"(acc[nb][2]), "+f"(acc[nb][3])
                        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[2 * nb]), "r"(b[2 * nb + 1]));
       }
+      __syncthreads();  // every warp has read the slot: refill it with the stage NST ahead
+      if (threadIdx.x == 0 && gs + MP_NST < total) issue(gs + MP_NST);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // accumulator fragment: c0,c1 -> (m = g, ch = 2*t4, +1); c2,c3 -> (m = g + 8, ...)
     float* pb = partial + (((size_t)img * R + blockIdx.x) * M + m0) * C;
 #pragma unroll
@@ -386,7 +380,7 @@ static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, int blo
 
 extern "C" __attribute__((visibility("default"))) long long srgpt_mask_weights_workspace(int n_img, int M, int side) {
   if (n_img <= 0 || M <= 0 || side <= 0) return -1;
-  return (long long)n_img * M * (MW_SPLITS * (long long)sizeof(float) + (long long)side * side * (long long)sizeof(bf16));
+  return (long long)n_img * M * (MW_SPLITS * (long long)sizeof(float) + (long long)mask_row_ld(side * side) * (long long)sizeof(bf16));
 }
 
 extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const void* masks, int mask_is_bf16, void* w, void* workspace, int n_img, int M, int IH, int IW,
@@ -396,7 +390,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_weights(const v
   dim3 grid(MW_SPLITS, M, n_img);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int L = side * side;
-  // workspace: [n_img*M*MW_SPLITS] fp32 partial sums, then [n_img*M*L] bf16 un-normalised resampled masks
+  // workspace: [n_img*M*MW_SPLITS] fp32 partial sums, then [n_img*M*ld(L)] bf16 un-normalised resampled masks (rows padded like w)
   float* psum = reinterpret_cast<float*>(workspace);
   bf16* v = reinterpret_cast<bf16*>(psum + (size_t)n_img * M * MW_SPLITS);
   if (mask_is_bf16)
@@ -428,9 +422,21 @@ extern "C" __attribute__((visibility("default"))) int srgpt_mask_pool_bf16(const
     configured = true;
   }
   dim3 grid(R, Q, n_img);
+  // tensor maps: features as [(n_img L), C] with boxes of 64 rows x 64 channels, weights as [(n_img M), L] with boxes of 16 masks x 64 rows
+  CUtensorMap tm_x, tm_w;
+  {
+    const cuuint64_t dx[2] = {(cuuint64_t)C, (cuuint64_t)n_img * L}, sx[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t bx[2] = {64, (cuuint32_t)MP_SROWS};
+    const cuuint64_t dw[2] = {(cuuint64_t)L, (cuuint64_t)n_img * M}, sw[1] = {(cuuint64_t)mask_row_ld(L) * 2};
+    const cuuint32_t bw[2] = {(cuuint32_t)MP_SROWS, (cuuint32_t)MP_MT};
+    if (tc::encode_tmap_bf16(&tm_x, x, 2, dx, sx, bx, CU_TENSOR_MAP_SWIZZLE_128B) != 0 ||
+        tc::encode_tmap_bf16(&tm_w, w, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B) != 0) {
+      set_last_error("srgpt_mask_pool_bf16: cuTensorMapEncodeTiled failed (x=%p w=%p L=%d C=%d)", x, w, L, C);
+      return SRGPT_ERR_CUDA;
+    }
+  }
   // behind mask_normalise_kernel (or whatever precedes it in the stream: every kernel of the chain waits before it reads)
-  SRGPT_CHECK_CUDA(launch_dependent(mask_pool_kernel, grid, MP_THREADS, MP_SMEM_BYTES, st, reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(w),
-                                    reinterpret_cast<float*>(workspace), M, L, C, rpc, R));
+  SRGPT_CHECK_CUDA(launch_dependent(mask_pool_kernel, grid, MP_THREADS, MP_SMEM_BYTES, st, tm_x, tm_w, reinterpret_cast<float*>(workspace), M, L, C, rpc, R));
   SRGPT_CHECK_CUDA(launch_dependent(mask_pool_reduce_kernel, dim3(ceil_div(C, 256), M, n_img), 256, 0, st, reinterpret_cast<const float*>(workspace),
                                     reinterpret_cast<bf16*>(out), M, C, R));
   return SRGPT_OK;

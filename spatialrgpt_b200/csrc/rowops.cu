@@ -246,6 +246,29 @@ __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ x, in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched decode bookkeeping: one CTA per sequence b: out_ids[*step * B + b] = ids[b]; h[b,:] = embed[ids[b],:]; ++pos[b];
+// the last CTA to finish (atomic ticket) advances *step, so one launch serves the whole batch inside a CUDA graph
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+decode_batch_advance_kernel(const long long* __restrict__ ids, const bf16* __restrict__ embed, bf16* __restrict__ h, int H, long long* __restrict__ out_ids,
+                            int* step, int* pos, int B, unsigned int* ticket) {
+  const int b = blockIdx.x;
+  const long long tok = ids[b];
+  const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tok * H);
+  uint4* dst = reinterpret_cast<uint4*>(h + (size_t)b * H);
+  for (int c = threadIdx.x; c < (H >> 3); c += blockDim.x) dst[c] = src[c];
+  if (threadIdx.x == 0) {
+    out_ids[(size_t)(*step) * B + b] = tok;
+    pos[b] += 1;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == (unsigned int)(B - 1)) {  // every CTA has read *step
+      *ticket = 0u;
+      *step += 1;
+    }
+  }
+}
+
 }  // namespace srgpt
 
 using namespace srgpt;
@@ -338,6 +361,18 @@ extern "C" __attribute__((visibility("default"))) int srgpt_argmax_f32(const flo
 extern "C" __attribute__((visibility("default"))) int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream) {
   SRGPT_CHECK_ARG(x && out && rows > 0 && cols > 0 && ldx >= cols);
   argmax_kernel<bf16><<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, cols, out);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+// Batched greedy decode bookkeeping after the row-wise arg max of a step: ids [B] -> out_ids[*step, :], next embedding rows, ++pos[b],
+// ++*step.  `ticket` = one zeroed device uint (returned to zero by the kernel).
+extern "C" __attribute__((visibility("default"))) int srgpt_decode_batch_advance(const long long* ids, const void* embed_table, void* h, int H, long long* out_ids,
+                                                                                 int* step, int* pos, int B, void* ticket, void* stream) {
+  SRGPT_CHECK_ARG(ids && embed_table && h && out_ids && step && pos && ticket && B > 0 && H > 0 && (H % 8) == 0);
+  SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(embed_table) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0);
+  decode_batch_advance_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, reinterpret_cast<const bf16*>(embed_table), reinterpret_cast<bf16*>(h), H,
+                                                                                     out_ids, step, pos, B, reinterpret_cast<unsigned int*>(ticket));
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

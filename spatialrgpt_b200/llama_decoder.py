@@ -353,12 +353,119 @@ class LlamaDecoder:
             return out, logits[:n]
         return out
 
+    # ---- batched decode: B sequences advance one token per step, every weight streamed ONCE for the whole batch ----------------
+    def _batch_state(self, B: int):
+        st = getattr(self, "_bstate", None)
+        if st is not None and st["B"] == B and st["cache"] is self.cache:
+            return st
+        d, dev = self.dims, self.device
+        H, nh, nkv, hd, I, V = d.hidden_size, d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.intermediate_size, d.vocab_size
+        z = lambda *shape, dtype=torch.bfloat16: torch.zeros(shape, dtype=dtype, device=dev)  # noqa: E731
+        st = dict(B=B, cache=self.cache, graph=None, h=z(B, H), xn=z(B, H), qkv=z(B, (nh + 2 * nkv) * hd), attn=z(B, nh * hd), act=z(B, I),
+                  logits=z(B, (V + 7) // 8 * 8), pos=z(B, dtype=torch.int32), step=z(1, dtype=torch.int32), ids=z(B, dtype=torch.int64),
+                  out=z(self.out_ids.numel() * B, dtype=torch.int64), ticket=z(1, dtype=torch.int32),
+                  cu=torch.arange(B + 1, dtype=torch.int32, device=dev))
+        self._bstate = st
+        return st
+
+    def _batch_step_launch(self, st) -> None:
+        """One decode step of all B sequences (llava_arch.py:549-611 + modeling_llama.py:540-562 semantics without padding): the
+        projections are tcgen05 GEMMs over the B rows (tall stream-K configuration), RoPE / KV append and attention per sequence."""
+        d, w, B = self.dims, self.w, st["B"]
+        nh, nkv, hd, V = d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.vocab_size
+        qd = nh * hd
+        h, xn, qkv, attn, act = st["h"], st["xn"], st["qkv"], st["attn"], st["act"]
+        pts = self.cache.page_tables
+        for l, lw in enumerate(w.layers):
+            pages = self.cache.layer(l)
+            ops.rmsnorm(h, lw.in_norm, d.rms_norm_eps, out=xn)
+            ops.gemm(xn, lw.qkv_w, out=qkv)
+            ops.rope_kv_append_varlen(qkv, nh, nkv, hd, self.cos, self.sin, st["pos"], pages, pts, PAGE_SIZE, st["cu"])
+            ops.attention_decode_batched(qkv[:, :qd], attn, pages, pts, PAGE_SIZE, st["pos"], nh, nkv, hd, self.scale)
+            ops.gemm(attn, lw.o_w, residual=h, epilogue=ops.EPI_BIAS_RESIDUAL, out=h)
+            ops.rmsnorm(h, lw.post_norm, d.rms_norm_eps, out=xn)
+            ops.gemm(xn, lw.gateup_w, epilogue=ops.EPI_SWIGLU, out=act)
+            ops.gemm(act, lw.down_w, residual=h, epilogue=ops.EPI_BIAS_RESIDUAL, out=h)
+        ops.rmsnorm(h, w.norm, d.rms_norm_eps, out=xn)
+        lg = st["logits"][:, :V]
+        ops.gemm(xn, w.lm_head, out=lg)  # bf16 logits (modeling_llama.py:1044), arg max with the lowest index on ties
+        ops.argmax_bf16(lg, out=st["ids"])
+        ops.decode_batch_advance(st["ids"], w.embed, h, st["out"], st["step"], st["pos"], st["ticket"])
+
+    def _decode_batched(self, first: torch.Tensor, seq_lens: List[int], max_new_tokens: int, eos, stopping_fn, use_graph: bool):
+        """Greedy decode of B prefilled sequences together.  Returns a list of LongTensor [n_b] (each cut at its own stop)."""
+        B = len(seq_lens)
+        st = self._batch_state(B)
+        zero = torch.zeros(B, dtype=torch.int32, device=self.device)
+        st["out"][:B].copy_(first)
+        st["h"].copy_(ops.splice_rows(self.w.embed, None, None, None, zero, first.to(torch.int32)))
+        st["pos"].copy_(torch.tensor(seq_lens, dtype=torch.int32))
+        st["step"].fill_(1)
+        if use_graph and st["graph"] is None:
+            saved = {k: st[k].clone() for k in ("h", "pos", "step", "out")}
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._batch_step_launch(st)  # warm-up outside capture (lazy kernel attribute setup)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for k, v in saved.items():
+                st[k].copy_(v)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._batch_step_launch(st)
+            st["graph"] = g
+        kernels = 8 * self.dims.num_hidden_layers + 4
+        need_check = bool(eos) or stopping_fn is not None
+        host = torch.empty((max_new_tokens, B), dtype=torch.int64, pin_memory=True) if need_check else None
+        side = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=self.device)
+        self._copy_stream = side
+        out2d = st["out"][: max_new_tokens * B].view(max_new_tokens, B)
+        stopped = [None] * B  # length at which sequence b stopped
+        done = {}
+
+        def fetch(k: int) -> None:
+            e = torch.cuda.Event()
+            e.record()
+            side.wait_event(e)
+            with torch.cuda.stream(side):
+                host[k].copy_(out2d[k], non_blocking=True)
+                dn = torch.cuda.Event()
+                dn.record(side)
+            done[k] = dn
+
+        n = 1
+        if need_check:
+            fetch(0)
+        checked = 0
+        while n < max_new_tokens:
+            if use_graph:
+                st["graph"].replay()
+                ops.LAUNCHES += kernels
+            else:
+                self._batch_step_launch(st)
+            if need_check:  # same pipelining as the single-sequence loop: inspect row n-1 while row n is being computed
+                fetch(n)
+                for k in range(checked, n):
+                    done.pop(k).synchronize()
+                    for b in range(B):
+                        if stopped[b] is None and (int(host[k, b]) in eos or (stopping_fn is not None and stopping_fn(host[:k + 1, b]))):
+                            stopped[b] = k + 1
+                checked = n
+                if all(s is not None for s in stopped):
+                    break
+            n += 1
+        n = min(n, max_new_tokens)
+        res = out2d[:n].t().contiguous()
+        return [res[b, : (stopped[b] if stopped[b] is not None else n)].clone() for b in range(B)]
+
     @torch.no_grad()
     def generate_batch(self, packed_embeds: torch.Tensor, seq_lens: List[int], max_new_tokens: int, eos_token_ids=None,
                        stopping_fn=None, use_graph: bool = True, return_logits: bool = False, sampling=None):
-        """Greedy decoding of B prompts: ONE packed prefill pass (tensor-core bound, all prompts share every GEMM), one
-        lm_head GEMM for the B first tokens, then each sequence is decoded from its own KV pages with the single-
-        sequence weight-streaming step.  Returns a list of LongTensor [n_b] (and a list of fp32 logits)."""
+        """Decoding of B prompts: ONE packed prefill pass (tensor-core bound, all prompts share every GEMM), one lm_head GEMM for the
+        B first tokens, then BATCHED decode: every step advances all B sequences, each weight streamed once per step for the
+        whole batch (_decode_batched).  With ``return_logits`` or sampling the sequences are decoded one after the other with the
+        single-sequence weight-streaming step.  Returns a list of LongTensor [n_b] (and a list of fp32 logits)."""
         d, w = self.dims, self.w
         B = len(seq_lens)
         if max_new_tokens < 1:
@@ -380,6 +487,8 @@ class LlamaDecoder:
         sample = self._set_sampling(sampling)
         if max_new_tokens == 1 and not return_logits and not sample:
             return [first[b:b + 1] for b in range(B)]
+        if not return_logits and not sample and B > 1:
+            return self._decode_batched(first, seq_lens, max_new_tokens, eos, stopping_fn, use_graph)
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         for b in range(B):
             logits = None

@@ -36,7 +36,9 @@ class LlavaLlamaModel:
     main_input_name = "input_embeds"
 
     def __init__(self, config: LlavaConfig, weights: ModelWeights, tokenizer=None, image_processor=None,
-                 max_seq_len: int = 4096):
+                 max_seq_len: int = 4096, tensor_parallel=None):
+        """``tensor_parallel`` = None, or (rank, world[, process_group]): the Llama DECODE step is sharded over `world` ranks
+        (tensor_parallel.py, BASELINE config c5); encoders and the prompt prefill stay replicated."""
         # fail loudly when the CUDA extension or a B200 is missing: there is no CPU path
         from . import _lib
         _lib.load()
@@ -49,7 +51,12 @@ class LlavaLlamaModel:
         self.vision_tower = VisionTower(config, weights.vision, image_processor)
         self.mm_projector = MultimodalProjector(config, weights.projector)
         self.region_extractor = RegionExtractor(config, weights.region) if (config.enable_region and weights.region is not None) else None
-        self.llm = LlamaDecoder(config.llama, weights.llama, max_seq_len=max_seq_len)
+        if tensor_parallel is not None and int(tensor_parallel[1]) > 1:
+            from .tensor_parallel import TPLlamaDecoder
+            self.llm = TPLlamaDecoder(config.llama, weights.llama, int(tensor_parallel[0]), int(tensor_parallel[1]),
+                                      group=tensor_parallel[2] if len(tensor_parallel) > 2 else None, max_seq_len=max_seq_len)
+        else:
+            self.llm = LlamaDecoder(config.llama, weights.llama, max_seq_len=max_seq_len)
         self.training = False
 
     # ---- accessors (llava_arch.py:252-278) -----------------------------------------------------------

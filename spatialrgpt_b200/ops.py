@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import SrgptError
 from ._lib import check as _check_rc
 
-_KERNELS_PER_CALL = {"srgpt_mask_pool_bf16": 2, "srgpt_mask_weights": 2, "srgpt_lm_head_argmax_bf16": 2, "srgpt_depth_to_u8x3": 3}
+_KERNELS_PER_CALL = {"srgpt_lm_head_local_best_bf16": 2, "srgpt_mask_pool_bf16": 2, "srgpt_mask_weights": 2, "srgpt_lm_head_argmax_bf16": 2, "srgpt_depth_to_u8x3": 3}
 
 
 def check(rc: int, what: str) -> None:
@@ -187,7 +187,9 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
         raise SrgptError(f"mask_weights: floor({IH}x{IW} * {scale_factor}) != {side} (non-square masks are unsupported)")
     rscale = float(torch.tensor(1.0 / scale_factor, dtype=torch.float64).to(torch.float32))
     lib = _lib.load()
-    w = torch.empty((n, M, side * side), dtype=BF16, device=masks.device)
+    L = side * side
+    ld = (L + 7) // 8 * 8  # rows padded to 16 bytes (include/srgpt_b200.h); the returned view hides the pad
+    w = torch.empty((n, M, ld), dtype=BF16, device=masks.device)[:, :, :L]
     ws = torch.empty(lib.srgpt_mask_weights_workspace(n, M, side), dtype=torch.uint8, device=masks.device)
     check(lib.srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), _p(ws), n, M, IH, IW, side, rscale, order,
                                  _stream()), "srgpt_mask_weights")
@@ -197,10 +199,13 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
 def mask_pool(x: torch.Tensor, w: torch.Tensor, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [n_img, L, C] bf16, w [n_img, M, L] bf16 -> [n_img, M, C] bf16."""
     _need(x, BF16, "mask_pool.x"); _need(w, BF16, "mask_pool.w")
-    if x.dim() != 3 or w.dim() != 3 or not x.is_contiguous() or not w.is_contiguous():
+    if x.dim() != 3 or w.dim() != 3 or not x.is_contiguous():
         raise SrgptError("mask_pool: expected contiguous x [n, L, C] and w [n, M, L]")
     n, L, Cc = x.shape
     n2, M, L2 = w.shape
+    ld = (L2 + 7) // 8 * 8
+    if w.stride(2) != 1 or w.stride(1) != ld or w.stride(0) != M * ld:
+        raise SrgptError("mask_pool: w must be the [n, M, L] view of a [n, M, round_up(L, 8)] buffer (what mask_weights returns)")
     if n != n2 or L != L2:
         raise SrgptError("mask_pool: shape mismatch between x and w")
     need = _lib.load().srgpt_mask_pool_workspace(n, M, L, Cc)
@@ -322,6 +327,73 @@ def gemv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, norm_weight: Optiona
     return y
 
 
+# ---- batched decode ----------------------------------------------------------------------------------------------
+def attention_decode_batched(q: torch.Tensor, out: torch.Tensor, kv_pages: torch.Tensor, page_tables: torch.Tensor, page_size: int, pos: torch.Tensor,
+                             n_heads: int, n_kv_heads: int, head_dim: int, scale: float) -> torch.Tensor:
+    """q [B, >= n_heads*hd] (row-strided view, e.g. the q columns of a fused qkv buffer), out [B, n_heads*hd], page_tables [>= B, cap],
+    pos int32 [B] = position of every sequence's newest row."""
+    _need(q, BF16, "attention_decode_batched.q"); _need(out, BF16, "attention_decode_batched.out")
+    _need(page_tables, torch.int32, "attention_decode_batched.page_tables"); _need(pos, torch.int32, "attention_decode_batched.pos")
+    B = q.shape[0]
+    check(_lib.load().srgpt_attention_decode_batched_bf16(_p(q), _rowmajor2d(q, "q"), _p(out), _rowmajor2d(out, "out"), _p(kv_pages), _p(page_tables),
+                                                          page_tables.stride(0), page_size, _p(pos), B, n_heads, n_kv_heads, head_dim, scale, _stream()),
+          "srgpt_attention_decode_batched_bf16")
+    return out
+
+
+def decode_batch_advance(ids: torch.Tensor, embed_table: torch.Tensor, h: torch.Tensor, out_ids: torch.Tensor, step: torch.Tensor, pos: torch.Tensor,
+                         ticket: torch.Tensor) -> None:
+    _need(ids, torch.int64, "decode_batch_advance.ids"); _need(out_ids, torch.int64, "decode_batch_advance.out_ids")
+    B, H = h.shape
+    check(_lib.load().srgpt_decode_batch_advance(_p(ids), _p(embed_table), _p(h), H, _p(out_ids), _p(step), _p(pos), B, _p(ticket), _stream()),
+          "srgpt_decode_batch_advance")
+
+
+# ---- tensor-parallel decode (one rank's share) ---------------------------------------------------------------------
+def gemv_tp_qkv(x, w_local, y_local, norm_weight, eps: float, n_heads_local: int, n_kv_local: int, head_dim: int, cos_tab, sin_tab, pos,
+                kv_pages, page_table, page_size: int, kv_heads_total: int, kv_head_off: int) -> torch.Tensor:
+    """RMSNorm + this rank's q/k/v rows + RoPE; K/V rows are appended to the full-layout cache at kv head `kv_head_off`."""
+    N, K = w_local.shape
+    check(_lib.load().srgpt_gemv_tp_bf16(_p(x), _p(w_local), w_local.stride(0), _p(y_local), N, K, _p(norm_weight), eps, GEMV_QKV_ROPE, n_heads_local,
+                                         n_kv_local, head_dim, _p(cos_tab), _p(sin_tab), _p(pos), _p(kv_pages), _p(page_table), page_size,
+                                         kv_heads_total, kv_head_off, None, _stream()), "srgpt_gemv_tp_bf16")
+    return y_local
+
+
+def gemv_tp_partial(x_local, w_local, partial_f32) -> torch.Tensor:
+    """Row-parallel linear: fp32 partial sums over this rank's K slice (all-reduced by the caller)."""
+    N, K = w_local.shape
+    _need(partial_f32, torch.float32, "gemv_tp_partial.partial")
+    check(_lib.load().srgpt_gemv_tp_bf16(_p(x_local), _p(w_local), w_local.stride(0), None, N, K, None, 0.0, GEMV_PLAIN, 0, 0, 0, None, None, None,
+                                         None, None, 0, 0, 0, _p(partial_f32), _stream()), "srgpt_gemv_tp_bf16")
+    return partial_f32
+
+
+def attention_decode_tp(q_local, out_local, kv_pages, page_table, page_size: int, pos, n_heads_local: int, group: int, n_kv_total: int,
+                        kv_head_off: int, head_dim: int, scale: float) -> torch.Tensor:
+    check(_lib.load().srgpt_attention_decode_tp_bf16(_p(q_local), _p(out_local), _p(kv_pages), _p(page_table), page_size, _p(pos), n_heads_local, group,
+                                                     n_kv_total, kv_head_off, head_dim, scale, _stream()), "srgpt_attention_decode_tp_bf16")
+    return out_local
+
+
+def tp_residual_add(h, partial_f32) -> None:
+    check(_lib.load().srgpt_tp_residual_add_bf16(_p(h), _p(partial_f32), h.numel(), _stream()), "srgpt_tp_residual_add_bf16")
+
+
+def lm_head_local_best(x, w_local, norm_weight, eps: float, workspace, index_base: int, best) -> None:
+    V, K = w_local.shape
+    _need(best, torch.int32, "lm_head_local_best.best")
+    check(_lib.load().srgpt_lm_head_local_best_bf16(_p(x), _p(w_local), w_local.stride(0), V, K, _p(norm_weight), eps, _p(workspace), index_base, _p(best),
+                                                    _stream()), "srgpt_lm_head_local_best_bf16")
+
+
+def tp_pick_token(best_all, world: int, embed_table, next_x, out_ids, step, pos) -> None:
+    _need(best_all, torch.int32, "tp_pick_token.best_all")
+    K = 0 if embed_table is None else embed_table.shape[1]
+    check(_lib.load().srgpt_tp_pick_token(_p(best_all), world, _p(embed_table), _p(next_x), K, _p(out_ids), _p(step), _p(pos), _stream()),
+          "srgpt_tp_pick_token")
+
+
 def lm_head_workspace(V: int, device) -> torch.Tensor:
     return torch.empty(_lib.load().srgpt_lm_head_workspace(V), dtype=torch.uint8, device=device)
 
@@ -356,11 +428,12 @@ def argmax_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def argmax_bf16(x: torch.Tensor) -> torch.Tensor:
+def argmax_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need(x, BF16, "argmax_bf16.x")
     ldx = _rowmajor2d(x, "argmax_bf16.x")
     rows, cols = x.shape
-    out = torch.empty(rows, dtype=torch.int64, device=x.device)
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int64, device=x.device)
     check(_lib.load().srgpt_argmax_bf16(_p(x), ldx, rows, cols, _p(out), _stream()), "srgpt_argmax_bf16")
     return out
 

@@ -569,3 +569,85 @@ def test_sample_top_p_matches_hf_distribution(ops, V, temperature, top_k, top_p)
     assert int(a[6]) == int(b[6])
     ops.sample_top_p(d_logits, torch.tensor([temperature, top_p, 1.0], device=DEV), 5, step, -1, a)
     assert int(a[6]) == int(logits.argmax())
+
+
+# ------------------------------------------------------------------------------------------ tensor-parallel pieces (one GPU)
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_shards_reproduce_the_full_decode_ops(ops, world):
+    """The per-rank kernels of tensor_parallel.py, all ranks emulated on ONE GPU: the column-parallel QKV GEMV (+RoPE, KV append at the
+    rank's kv-head offset) writes exactly the q / K / V the full kernel writes; attention over the rank's heads equals the slice of
+    the full attention; row-parallel partial sums add up (fp32) to the full o_proj product; vocabulary-parallel (value, index)
+    candidates pick the full arg max."""
+    from spatialrgpt_b200.config import LlamaDims
+    from spatialrgpt_b200.llama_decoder import build_rope_tables
+    nh, nkv, hd, H, V = 8, 4, 128, 512, 1003
+    dims = LlamaDims(hidden_size=H, num_attention_heads=nh, num_key_value_heads=nkv, head_dim=hd, intermediate_size=1024, vocab_size=V)
+    cos, sin = build_rope_tables(dims, 256, DEV)
+    x = rnd(H, seed=1).to(DEV)
+    nw = (1 + 0.1 * rnd(H, seed=2)).to(DEV)
+    wqkv = rnd((nh + 2 * nkv) * hd, H, seed=3, scale=H ** -0.5).to(DEV)
+    n_pages, page = 8, 16
+    pt = torch.arange(n_pages, dtype=torch.int32, device=DEV)
+    pos = torch.tensor([37], dtype=torch.int32, device=DEV)
+    base_pages = rnd(n_pages, 2, page, nkv, hd, seed=4).to(DEV)
+    full_pages, tp_pages = base_pages.clone(), base_pages.clone()
+    q_full = torch.zeros(nh * hd, dtype=BF, device=DEV)
+    ops.gemv(x, wqkv, q_full, norm_weight=nw, eps=1e-5, mode=ops.GEMV_QKV_ROPE, n_heads=nh, n_kv_heads=nkv, head_dim=hd, cos_tab=cos, sin_tab=sin,
+             pos=pos, kv_pages=full_pages, page_table=pt, page_size=page)
+    attn_full = torch.zeros(nh * hd, dtype=BF, device=DEV)
+    ops.attention_decode(q_full, attn_full, full_pages, pt, page, pos, nh, nkv, hd, hd ** -0.5)
+    wo = rnd(H, nh * hd, seed=5, scale=(nh * hd) ** -0.5).to(DEV)
+    o_ref = attn_full.float() @ wo.float().t()
+    nhl, nkvl = nh // world, nkv // world
+    partial_sum = torch.zeros(H, dtype=torch.float32, device=DEV)
+    for r in range(world):
+        w_local = torch.cat([wqkv[r * nhl * hd:(r + 1) * nhl * hd], wqkv[(nh + r * nkvl) * hd:(nh + (r + 1) * nkvl) * hd],
+                             wqkv[(nh + nkv + r * nkvl) * hd:(nh + nkv + (r + 1) * nkvl) * hd]], 0).contiguous()
+        q_loc = torch.zeros(nhl * hd, dtype=BF, device=DEV)
+        ops.gemv_tp_qkv(x, w_local, q_loc, nw, 1e-5, nhl, nkvl, hd, cos, sin, pos, tp_pages, pt, page, nkv, r * nkvl)
+        assert torch.equal(q_loc, q_full[r * nhl * hd:(r + 1) * nhl * hd])
+        a_loc = torch.zeros(nhl * hd, dtype=BF, device=DEV)
+        ops.attention_decode_tp(q_loc, a_loc, tp_pages, pt, page, pos, nhl, nh // nkv, nkv, r * nkvl, hd, hd ** -0.5)
+        assert torch.equal(a_loc, attn_full[r * nhl * hd:(r + 1) * nhl * hd])
+        part = torch.zeros(H, dtype=torch.float32, device=DEV)
+        ops.gemv_tp_partial(a_loc, wo[:, r * nhl * hd:(r + 1) * nhl * hd].contiguous(), part)
+        partial_sum += part
+    assert torch.equal(tp_pages, full_pages), "the ranks together append exactly the K/V rows of the full kernel"
+    assert_close(partial_sum, o_ref, rel_rms=1e-4, rel_max=1e-3, what="row-parallel partial sums")
+    h = rnd(H, seed=6).to(DEV)
+    h2 = h.clone()
+    ops.tp_residual_add(h2, partial_sum)
+    assert torch.equal(h2, (partial_sum.to(BF).float() + h.float()).to(BF))
+    # vocabulary-parallel arg max (ties -> lowest index, like the full kernel)
+    wl = rnd(V, H, seed=7, scale=H ** -0.5).to(DEV)
+    wl[700] = wl[123]  # an exact tie across two ranks' blocks
+    full_ids = torch.zeros(4, dtype=torch.int64, device=DEV)
+    st, ps = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.lm_head_argmax(x, wl, nw, 1e-5, ops.lm_head_workspace(V, DEV), full_ids, st, ps)
+    per = (V + world - 1) // world
+    best_all = torch.zeros(2 * world, dtype=torch.int32, device=DEV)
+    for r in range(world):
+        v0, v1 = min(V, r * per), min(V, (r + 1) * per)
+        ops.lm_head_local_best(x, wl[v0:v1], nw, 1e-5, ops.lm_head_workspace(v1 - v0, DEV), v0, best_all[2 * r:2 * r + 2])
+    tp_ids = torch.zeros(4, dtype=torch.int64, device=DEV)
+    st2, ps2 = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    nxt = torch.zeros(H, dtype=BF, device=DEV)
+    emb = rnd(V, H, seed=8).to(DEV)
+    ops.tp_pick_token(best_all, world, emb, nxt, tp_ids, st2, ps2)
+    assert int(tp_ids[0]) == int(full_ids[0]) and int(st2) == 1 and int(ps2) == 1
+    assert torch.equal(nxt, emb[int(full_ids[0])])
+
+
+@pytest.mark.parametrize("side,C,M,R", [(27, 72, 5, 378), (27, 1152, 17, 384), (24, 200, 1, 336)])
+def test_mask_pool_odd_sides_and_ragged_channels(ops, side, C, M, R):
+    """L = side^2 not a multiple of 8 (the 27 x 27 tower grid of a 384-px SigLIP: padded weight rows, TMA view of L columns), channel
+    counts that are not a multiple of the 128-channel CTA tile (out-of-bounds channels are zero-filled and never stored), more than
+    16 masks (two passes over the features)."""
+    x = rnd(2, side * side, C, seed=13)
+    masks = (torch.rand(2, M, R, R, generator=torch.Generator().manual_seed(14)) > 0.6).float()
+    ref = torch.stack(O.mask_pooling(x.float(), [masks[0], masks[1]]))
+    w = ops.mask_weights(masks.to(DEV), side, ops.ORDER_ROWMAJOR)
+    assert w.shape == (2, M, side * side)
+    out = ops.mask_pool(x.to(DEV), w)
+    assert_close(out, ref, **BF16_CHAIN, what="odd-side mask_pool")
+    assert torch.equal(ops.mask_pool(x.to(DEV), w), out)

@@ -159,6 +159,29 @@ def test_read_checkpoint_roundtrip(tmp_path):
         builder.load_pretrained_model(root, "x", load_4bit=True)
 
 
+def test_read_checkpoint_with_tokenizer_registers_special_tokens(tmp_path):
+    """builder.py:186-199 on a synthetic four-directory checkpoint WITH tokenizer / processor files: <mask> and <depth> are added as
+    special tokens and their ids recorded on the config, the token tables are resized to len(tokenizer), the image processor comes
+    from vision_tower/, and the stop ids come from llm/generation_config.json (a list for Llama-3 style checkpoints)."""
+    from oracle import srgpt_oracle as O
+    from spatialrgpt_b200 import builder
+    from tests.golden.make_golden import CASES
+    from tests.util import write_synthetic_checkpoint
+
+    oc = O.OracleConfig(**CASES["tiny_boxes"][0])
+    sd = O.make_weights(oc, seed=1)
+    root = str(tmp_path / "ckpt")
+    n_vocab = write_synthetic_checkpoint(root, oc, sd, generation_eos=[2, 7])
+    cfg, got, tok, proc = builder.read_checkpoint(root)
+    assert tok is not None and proc is not None and proc.size["height"] == oc.image_size
+    assert cfg.llm_mask_token_id == n_vocab and cfg.llm_depth_token_id == n_vocab + 1 and len(tok) == n_vocab + 2
+    assert tok.convert_tokens_to_ids("<mask>") == n_vocab and tok("<mask> <depth>").input_ids[-2:] == [n_vocab, n_vocab + 1]
+    assert cfg.llama.vocab_size == len(tok) and got["llm"]["model.embed_tokens.weight"].shape[0] == len(tok)
+    assert torch.equal(got["llm"]["lm_head.weight"], sd["llm"]["lm_head.weight"][: len(tok)])  # the tables shrink from 512 rows
+    assert cfg.llama.eos_token_id == [2, 7]
+    assert not cfg.mm_use_im_patch_token and tok.convert_tokens_to_ids("<im_patch>") in (None, tok.unk_token_id)
+
+
 def test_bench_algorithmic_numbers_match_the_survey():
     """bench.py's FLOP / byte model of config c2 equals SURVEY.md §8(d): 5.58 TFLOP per request to the first token,
     15.01 GB streamed per decoded token, 131072 B of KV per cached token, 234.9 MB for the gate/up GEMV."""
