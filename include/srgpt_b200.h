@@ -216,6 +216,19 @@ int srgpt_lm_head_local_best_bf16(const void* x, const void* W_local, int ldw, i
 int srgpt_tp_pick_token(const int* best_all, int world, const void* embed_table, void* next_x, int K, long long* out_ids, int* step,
                         int* pos, void* stream);
 
+/* Fused collectives over NVLink peer memory (tp_comm.cu): every rank's partial sums / arg-max candidates live in a SYMMETRIC buffer
+ * (srgpt_tp_comm_bytes bytes, zeroed, same layout on every GPU, peer-mapped by the caller - torch symmetric memory); one kernel
+ * signals the peers, waits for all of them, pulls their 16 KB partials through NVLink, reduces in rank order and applies the residual
+ * add (or picks the token).  peer_bases = HOST array [world] of peer-mapped base addresses; idx < 128 numbers the collectives of a
+ * step; epoch / step are device ints (request counter, the decoder's step counter), so CUDA-graph replays need no host values. */
+long long srgpt_tp_comm_bytes(int world, int n_slots, int slot_floats);
+long long srgpt_tp_comm_slot_offset(int world, int slot, int slot_floats);
+int srgpt_tp_allreduce_residual_bf16(const unsigned long long* peer_bases, int rank, int world, long long slot_off_bytes, int idx,
+                                     const int* epoch, const int* step, void* h, int n, void* stream);
+int srgpt_tp_allgather_pick_token(const unsigned long long* peer_bases, int rank, int world, long long slot_off_bytes, int idx,
+                                  const int* epoch, const void* embed_table, void* next_x, int K, long long* out_ids, int* step, int* pos,
+                                  void* stream);
+
 /* ---- composite entry points (layers.cu): one call per tower pass / prompt / decode step -------------------
  * Pure sequencing of the kernels above on `stream` (no allocation, no sync); they exist because a Python-side
  * launch costs more host time than several of these kernels take on the device.  Weights are the re-laid-out

@@ -62,6 +62,10 @@ SIGNATURES = {
     "srgpt_tp_residual_add_bf16": (ci, [vp, vp, ci, vp]),
     "srgpt_lm_head_local_best_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, ci, vp, vp]),
     "srgpt_tp_pick_token": (ci, [vp, ci, vp, vp, ci, vp, vp, vp, vp]),
+    "srgpt_tp_comm_bytes": (cll, [ci, ci, ci]),
+    "srgpt_tp_comm_slot_offset": (cll, [ci, ci, ci]),
+    "srgpt_tp_allreduce_residual_bf16": (ci, [vp, ci, ci, cll, ci, vp, vp, vp, ci, vp]),
+    "srgpt_tp_allgather_pick_token": (ci, [vp, ci, ci, cll, ci, vp, vp, vp, ci, vp, vp, vp, vp]),
     "srgpt_siglip_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]),
     "srgpt_llama_prefill_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, ci, vp, ci, ci, vp]),
     "srgpt_llama_decode_step_bf16": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp,

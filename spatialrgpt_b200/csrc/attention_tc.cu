@@ -433,6 +433,313 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_fwd_tc_kernel(const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Round 2: PING-PONG kernel for the SigLIP tower (head_dim 72, non-causal, dense batch).
+//
+// The kernel above keeps ONE q tile in flight: its eight softmax warps walk the per-tile chain S -> max -> (pair exchange) -> ex2 -> P
+// -> fold in lock step, so nothing hides their latencies (ncu: tensor pipe 20 %, XU 33 %, issue 35 %; ~3000 clk per 128 x 128 tile
+// against 640 clk of MMA and 1024 clk of ex2).  Here a CTA works on a PAIR of q tiles (256 query rows of one head) against ONE K / V
+// stream:
+//   * softmax group A (warps 2-5) owns q tile A, group B (warps 6-9) q tile B: ONE thread per query row (TMEM lane = row), so there
+//     is no cross-thread max exchange and no named barrier; while one group waits (S from the tensor pipe, its TMEM loads, the SFU),
+//     the other group's warps on the same schedulers run - the two chains interleave instead of idling;
+//   * every K / V tile is loaded once and used by both q tiles (half the TMA / shared-memory traffic per tile product);
+//   * two passes over S in TMEM (pass 1: row max; pass 2: ex2 + bf16 P) keep 32 S values live instead of 128, so the 72 fp32
+//     output channels of the row fit in registers next to them; O_j is still a FRESH accumulator folded into registers
+//     (o = o * alpha + O_j), between the two passes, so P V of tile j never waits for the fold of tile j - 1;
+//   * TMEM: S_A | S_B | O_A | O_B = 4 x 128 columns; shared memory: Q_A Q_B (40 KB) + 3 K + 2 V stages (100 KB) + P_A P_B (64 KB).
+// MMA issue order per kv tile j:  P_A V_j -> S_A(j+1) -> P_B V_j -> S_B(j+1).
+// ---------------------------------------------------------------------------------------------
+namespace pp {
+constexpr int HD = 72, BN = 128;
+using G = Geo<HD, BN>;
+enum PBar { PQ_FULL = 0, PQ_EMPTY = 1, PK_FULL = 2, PK_EMPTY = 5, PV_FULL = 8, PV_EMPTY = 10, PS_FULL = 12, PS_EMPTY = 14, PP_FULL = 16, PP_EMPTY = 18,
+            PO_FULL = 20, PO_EMPTY = 22, P_NUM_BARS = 24 };
+constexpr int OFF_Q = 0, OFF_K = 2 * G::Q_BYTES, OFF_V = OFF_K + KST * G::KV_BYTES, OFF_P = OFF_V + 2 * G::KV_BYTES, OFF_BAR = OFF_P + 2 * G::P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + P_NUM_BARS * 8 + 16 + 1024;
+
+struct Item {
+  int row_base, q0, head, n_tiles;
+  bool b_active;
+};
+struct ItemIter {
+  const Params& p;
+  int w, n_work, n_pairs;
+  Item k;
+  __device__ ItemIter(const Params& p_) : p(p_), w((int)blockIdx.x - (int)gridDim.x) {
+    n_pairs = (p.nqt + 1) >> 1;
+    n_work = n_pairs * p.n_heads * p.batch;
+  }
+  __device__ bool next() {
+    w += gridDim.x;
+    if (w >= n_work) return false;
+    const int pair = w % n_pairs, hb = w / n_pairs;
+    k.head = hb % p.n_heads;
+    k.row_base = (hb / p.n_heads) * p.seqlen;
+    k.q0 = pair * 2 * BM;
+    k.b_active = k.q0 + BM < p.seqlen;
+    k.n_tiles = (p.seqlen + BN - 1) / BN;
+    return true;
+  }
+};
+}  // namespace pp
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_constant__ Maps maps, const Params p) {
+  using namespace pp;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NUM_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto bar = [&](int which) { return bar0 + which * 8; };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.q0); prefetch_tmap(&maps.q1); prefetch_tmap(&maps.k0);
+    prefetch_tmap(&maps.k1); prefetch_tmap(&maps.v0); prefetch_tmap(&maps.v1);
+    mbar_init(bar(PQ_FULL), 1);
+    mbar_init(bar(PQ_EMPTY), 1);
+    for (int i = 0; i < KST; ++i) { mbar_init(bar(PK_FULL + i), 1); mbar_init(bar(PK_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(PV_FULL + i), 1);
+      mbar_init(bar(PV_EMPTY + i), 1);
+      mbar_init(bar(PS_FULL + i), 1);
+      mbar_init(bar(PS_EMPTY + i), 4);   // the four warps of a softmax group
+      mbar_init(bar(PP_FULL + i), 4);
+      mbar_init(bar(PP_EMPTY + i), 1);
+      mbar_init(bar(PO_FULL + i), 1);
+      mbar_init(bar(PO_EMPTY + i), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t t = 0, it = 0;
+      ItemIter wi(p);
+      while (wi.next()) {
+        const Item& k = wi.k;
+        mbar_wait(bar(PQ_EMPTY), (it & 1) ^ 1);
+        mbar_expect_tx(bar(PQ_FULL), (k.b_active ? 2 : 1) * G::Q_BYTES);
+        tma_load_3d(sbase + OFF_Q, &maps.q0, bar(PQ_FULL), 0, k.head, k.row_base + k.q0);
+        tma_load_3d(sbase + OFF_Q + G::Q_C0, &maps.q1, bar(PQ_FULL), 64, k.head, k.row_base + k.q0);
+        if (k.b_active) {
+          tma_load_3d(sbase + OFF_Q + G::Q_BYTES, &maps.q0, bar(PQ_FULL), 0, k.head, k.row_base + k.q0 + BM);
+          tma_load_3d(sbase + OFF_Q + G::Q_BYTES + G::Q_C0, &maps.q1, bar(PQ_FULL), 64, k.head, k.row_base + k.q0 + BM);
+        }
+        for (int j = 0; j < k.n_tiles; ++j, ++t) {
+          const int row = k.row_base + j * BN;
+          const int ik = t % KST, iv = t & 1;
+          mbar_wait(bar(PK_EMPTY + ik), ((t / KST) & 1) ^ 1);
+          mbar_expect_tx(bar(PK_FULL + ik), G::KV_BYTES);
+          tma_load_3d(sbase + OFF_K + ik * G::KV_BYTES, &maps.k0, bar(PK_FULL + ik), 0, k.head, row);
+          tma_load_3d(sbase + OFF_K + ik * G::KV_BYTES + G::KV_C0, &maps.k1, bar(PK_FULL + ik), 64, k.head, row);
+          mbar_wait(bar(PV_EMPTY + iv), ((t >> 1) & 1) ^ 1);
+          mbar_expect_tx(bar(PV_FULL + iv), G::KV_BYTES);
+          tma_load_3d(sbase + OFF_V + iv * G::KV_BYTES, &maps.v0, bar(PV_FULL + iv), 0, k.head, row);
+          tma_load_3d(sbase + OFF_V + iv * G::KV_BYTES + G::KV_C0, &maps.v1, bar(PV_FULL + iv), 64, k.head, row);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_v0 = umma_idesc_bf16(BM, 64, 0, 1);
+      constexpr uint32_t idesc_v1 = umma_idesc_bf16(BM, G::W1, 0, 1);
+      uint32_t tg[2] = {0, 0};  // tiles issued so far per group (S and P V use the same count, P V one behind inside an item)
+      uint32_t tpv[2] = {0, 0};
+      uint32_t tk = 0, it = 0;  // kv tile counter (K / V ring positions), item counter
+      auto issue_s = [&](int g, uint32_t tkk) {  // S_g = Q_g K^T of the kv tile at ring position tkk
+        const int ik = tkk % KST;
+        mbar_wait(bar(PK_FULL + ik), (tkk / KST) & 1);
+        mbar_wait(bar(PS_EMPTY + g), (tg[g] & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + g * BN;
+        const uint32_t qa = sbase + OFF_Q + g * G::Q_BYTES, ka = sbase + OFF_K + ik * G::KV_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(d, umma_desc(UMMA_DESC_SW128, qa + k * 32), umma_desc(UMMA_DESC_SW128, ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < G::W1 / 16; ++k)
+          umma_f16(d, umma_desc(G::F1, qa + G::Q_C0 + k * 32), umma_desc(G::F1, ka + G::KV_C0 + k * 32), idesc_s, 1u);
+        umma_commit(bar(PS_FULL + g));
+        ++tg[g];
+      };
+      auto issue_pv = [&](int g, uint32_t tkk) {  // O_g = P_g V of the kv tile at ring position tkk (fresh accumulator)
+        const int iv = tkk & 1;
+        mbar_wait(bar(PP_FULL + g), tpv[g] & 1);
+        mbar_wait(bar(PV_FULL + iv), (tkk >> 1) & 1);
+        mbar_wait(bar(PO_EMPTY + g), (tpv[g] & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + O_COL + g * 128;
+        const uint32_t pa = sbase + OFF_P + g * G::P_BYTES, va = sbase + OFF_V + iv * G::KV_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          const uint64_t a = umma_desc(UMMA_DESC_SW128, pa + (ks >> 2) * (BM * 128) + (ks & 3) * 32);
+          umma_f16(d, a, umma_desc(UMMA_DESC_SW128, va + ks * 2048), idesc_v0, ks != 0 ? 1u : 0u);
+          umma_f16(d + 64, a, umma_desc(G::F1, va + G::KV_C0 + ks * G::V_ADV1), idesc_v1, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar(PO_FULL + g));
+        umma_commit(bar(PP_EMPTY + g));
+        ++tpv[g];
+      };
+      ItemIter wi(p);
+      while (wi.next()) {
+        const Item& k = wi.k;
+        const int n = k.n_tiles;
+        const bool b = k.b_active;
+        mbar_wait(bar(PQ_FULL), it & 1);
+        issue_s(0, tk);
+        if (b) issue_s(1, tk);
+        umma_commit(bar(PK_EMPTY + tk % KST));
+        if (n == 1) umma_commit(bar(PQ_EMPTY));
+        for (int j = 0; j < n; ++j) {
+          const uint32_t tkk = tk + j;
+          issue_pv(0, tkk);
+          if (j + 1 < n) {
+            issue_s(0, tkk + 1);
+            if (!b) {
+              umma_commit(bar(PK_EMPTY + (tkk + 1) % KST));
+              if (j + 2 == n) umma_commit(bar(PQ_EMPTY));
+            }
+          }
+          if (b) issue_pv(1, tkk);
+          umma_commit(bar(PV_EMPTY + (tkk & 1)));
+          if (b && j + 1 < n) {
+            issue_s(1, tkk + 1);
+            umma_commit(bar(PK_EMPTY + (tkk + 1) % KST));
+            if (j + 2 == n) umma_commit(bar(PQ_EMPTY));
+          }
+        }
+        tk += n;
+        ++it;
+      }
+    }
+  } else {
+    // ===================== softmax groups: warps 2-5 = q tile A, warps 6-9 = q tile B; one thread per query row =====================
+    const int g = (warp - 2) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+    const float sl = p.scale_log2;
+    const uint32_t s_addr = tmem_base + g * BN + lane_addr;
+    const uint32_t o_addr = tmem_base + O_COL + g * 128 + lane_addr;
+    const uint32_t p_row = sbase + OFF_P + g * G::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    uint32_t t = 0;  // tiles processed by this group
+    ItemIter wi(p);
+    while (wi.next()) {
+      const Item k = wi.k;
+      if (g == 1 && !k.b_active) continue;  // no second q tile in this item: group B sits it out (the MMA warp skips it too)
+      float o[72];
+#pragma unroll
+      for (int c = 0; c < 72; ++c) o[c] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      auto fold = [&](uint32_t tt, float alpha) {  // o = o * alpha + O_tt
+        mbar_wait(bar(PO_FULL + g), tt & 1);
+        tcgen05_fence_after();
+        uint32_t v[72];
+        tmem_ld_32x32b_x32(o_addr, v);
+        tmem_ld_32x32b_x32(o_addr + 32, v + 32);
+        tmem_ld_32x32b_x8(o_addr + 64, v + 64);  // channels 64..71 (the 16-wide tail accumulator; 72..79 are zero padding)
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(PO_EMPTY + g));
+#pragma unroll
+        for (int c = 0; c < 72; ++c) o[c] = fmaf(o[c], alpha, __uint_as_float(v[c]));
+      };
+      for (int j = 0; j < k.n_tiles; ++j, ++t) {
+        mbar_wait(bar(PS_FULL + g), t & 1);
+        tcgen05_fence_after();
+        const bool ragged = j * BN + BN > p.seqlen;  // kv columns past the sequence end (last tile only)
+        // ---- pass 1: row max over the 128 columns of S
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(s_addr + c4 * 32, sv);
+          tmem_ld_wait();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float x = __uint_as_float(sv[c]);
+            if (ragged && j * BN + c4 * 32 + c >= p.seqlen) x = -INFINITY;
+            m4[c & 3] = fmaxf(m4[c & 3], x);
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = ex2_approx((m_run - m_use) * sl);  // m_run = -inf -> 0
+        m_run = m_new;
+        const float msl = m_use * sl;
+        // ---- the previous tile's P V product, folded while the tensor pipe may still be busy with the other group
+        if (j > 0) fold(t - 1, alpha_prev);
+        alpha_prev = alpha;
+        // ---- pass 2: P = 2^(s * scale - m) -> bf16 -> 128B-swizzled K-major tile, row sum
+        mbar_wait(bar(PP_EMPTY + g), (t & 1) ^ 1);
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(s_addr + c4 * 32, sv);
+          tmem_ld_wait();
+          if (c4 == 3) {  // S is in registers for the last time: the tensor pipe may overwrite it with the next tile's S
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(PS_EMPTY + g));
+          }
+          float e[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float x = __uint_as_float(sv[c]);
+            if (ragged && j * BN + c4 * 32 + c >= p.seqlen) x = -INFINITY;
+            e[c] = ex2_approx(fmaf(x, sl, -msl));
+            sum4[c & 3] += e[c];
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int col = c4 * 32 + cc * 8;
+            const int kb = col >> 6, cin = (col & 63) >> 3;
+            st_shared_v4(p_row + kb * (BM * 128) + ((cin ^ (r & 7)) << 4), pack8(e + cc * 8));
+          }
+        }
+        l_run = fmaf(l_run, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(PP_FULL + g));
+      }
+      // ---- last product of the item, normalisation, store (72 channels = nine 16-byte vectors per row)
+      fold(t - 1, alpha_prev);
+      const int qrow = k.q0 + g * BM + r;
+      if (qrow < p.seqlen) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+#pragma unroll
+        for (int c = 0; c < 72; ++c) o[c] *= inv;
+        bf16* orow = p.out + (size_t)(k.row_base + qrow) * p.o_ld + k.head * HD;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = pack8(o + c * 8);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 template <int HD, int BN, bool CAUSAL>
 static int launch(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch, int seqlen, const int* cu,
                   long long total_rows, int n_heads, int n_kv_heads, float scale, cudaStream_t st) {
@@ -470,6 +777,22 @@ static int launch(const void* q, const void* k, const void* v, void* out, int q_
   p.o_ld = o_ld;
   static const int s_ahead_env = getenv("SRGPT_ATTN_S_AHEAD") ? atoi(getenv("SRGPT_ATTN_S_AHEAD")) : 0;
   p.s_ahead = (s_ahead_env == 1 || s_ahead_env == 2) ? s_ahead_env : 1;
+  if (HD == 72 && BN == 128 && !CAUSAL && cu == nullptr && n_heads == n_kv_heads) {
+    // the SigLIP tower: ping-pong kernel (two q tiles per CTA); SRGPT_ATTN_PP=-1 selects the single-tile kernel (A/B knob)
+    static const int pp_env = getenv("SRGPT_ATTN_PP") ? atoi(getenv("SRGPT_ATTN_PP")) : 0;
+    if (pp_env >= 0) {
+      static bool pp_configured = false;
+      if (!pp_configured) {
+        SRGPT_CHECK_CUDA(cudaFuncSetAttribute(attn_vit_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_BYTES));
+        pp_configured = true;
+      }
+      const long long n_items = (long long)((p.nqt + 1) / 2) * n_heads * batch;
+      const int grid_pp = (int)(n_items < sm_count() ? n_items : sm_count());
+      attn_vit_pp_kernel<<<grid_pp, NTHREADS, pp::SMEM_BYTES, st>>>(maps, p);
+      SRGPT_CHECK_LAUNCH();
+      return SRGPT_OK;
+    }
+  }
   const long long n_work = (long long)p.nqt * n_heads * batch;
   const int grid = (int)(n_work < sm_count() ? n_work : sm_count());
   attn_fwd_tc_kernel<HD, BN, CAUSAL><<<grid, NTHREADS, G::SMEM_BYTES, st>>>(maps, p);
