@@ -643,39 +643,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
 #pragma unroll
       for (int c = 0; c < 72; ++c) o[c] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-      auto fold = [&](uint32_t tt, float alpha) {  // o = o * alpha + O_tt
+      auto fold = [&](uint32_t tt, float alpha) {  // o = o * alpha + O_tt, in three chunks so only 32 loaded values are live
         mbar_wait(bar(PO_FULL + g), tt & 1);
         tcgen05_fence_after();
-        uint32_t v[72];
+        uint32_t v[32];
         tmem_ld_32x32b_x32(o_addr, v);
-        tmem_ld_32x32b_x32(o_addr + 32, v + 32);
-        tmem_ld_32x32b_x8(o_addr + 64, v + 64);  // channels 64..71 (the 16-wide tail accumulator; 72..79 are zero padding)
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] = fmaf(o[c], alpha, __uint_as_float(v[c]));
+        tmem_ld_32x32b_x32(o_addr + 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[32 + c] = fmaf(o[32 + c], alpha, __uint_as_float(v[c]));
+        tmem_ld_32x32b_x8(o_addr + 64, v);  // channels 64..71 (the 16-wide tail accumulator; 72..79 are zero padding)
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(PO_EMPTY + g));
 #pragma unroll
-        for (int c = 0; c < 72; ++c) o[c] = fmaf(o[c], alpha, __uint_as_float(v[c]));
+        for (int c = 0; c < 8; ++c) o[64 + c] = fmaf(o[64 + c], alpha, __uint_as_float(v[c]));
       };
       for (int j = 0; j < k.n_tiles; ++j, ++t) {
         mbar_wait(bar(PS_FULL + g), t & 1);
         tcgen05_fence_after();
-        const bool ragged = j * BN + BN > p.seqlen;  // kv columns past the sequence end (last tile only)
-        // ---- pass 1: row max over the 128 columns of S
+        const bool ragged = j * BN + BN > p.seqlen;  // kv columns past the sequence end (last tile only): the slow, masked path
+        const int n_valid = p.seqlen - j * BN;       // valid columns of this tile when ragged
+        // ---- pass 1: row max over the 128 columns of S; the TMEM load of chunk c + 1 is in flight while chunk c is reduced
         float mx = -INFINITY;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t sv[32];
-          tmem_ld_32x32b_x32(s_addr + c4 * 32, sv);
+        {
+          uint32_t sa[32], sb[32];
+          tmem_ld_32x32b_x32(s_addr, sa);
+          tmem_ld_32x32b_x32(s_addr + 32, sb);
           tmem_ld_wait();
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          auto red = [&](const uint32_t* sv, int c0) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (!ragged) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float x = __uint_as_float(sv[c]);
-            if (ragged && j * BN + c4 * 32 + c >= p.seqlen) x = -INFINITY;
-            m4[c & 3] = fmaxf(m4[c & 3], x);
-          }
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+              for (int c = 0; c < 32; c += 2) m4[(c >> 1) & 3] = fmaxf(m4[(c >> 1) & 3], fmaxf(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) m4[c & 3] = fmaxf(m4[c & 3], c0 + c < n_valid ? __uint_as_float(sv[c]) : -INFINITY);
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          };
+          red(sa, 0);
+          tmem_ld_32x32b_x32(s_addr + 64, sa);
+          red(sb, 32);
+          tmem_ld_32x32b_x32(s_addr + 96, sb);
+          tmem_ld_wait();
+          red(sa, 64);
+          red(sb, 96);
         }
         const float m_new = fmaxf(m_run, mx);
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -685,33 +702,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
         // ---- the previous tile's P V product, folded while the tensor pipe may still be busy with the other group
         if (j > 0) fold(t - 1, alpha_prev);
         alpha_prev = alpha;
-        // ---- pass 2: P = 2^(s * scale - m) -> bf16 -> 128B-swizzled K-major tile, row sum
+        // ---- pass 2: P = 2^(s * scale - m) -> bf16 -> 128B-swizzled K-major tile, row sum; loads pipelined as in pass 1
         mbar_wait(bar(PP_EMPTY + g), (t & 1) ^ 1);
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          uint32_t sa[32], sb[32];
+          auto emit = [&](const uint32_t* sv, int c0) {
+            float e[32];
+            if (!ragged) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t sv[32];
-          tmem_ld_32x32b_x32(s_addr + c4 * 32, sv);
+              for (int c = 0; c < 32; ++c) {
+                e[c] = ex2_approx(fmaf(__uint_as_float(sv[c]), sl, -msl));
+                sum4[c & 3] += e[c];
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                e[c] = c0 + c < n_valid ? ex2_approx(fmaf(__uint_as_float(sv[c]), sl, -msl)) : 0.f;
+                sum4[c & 3] += e[c];
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int col = c0 + cc * 8;
+              const int kb = col >> 6, cin = (col & 63) >> 3;
+              st_shared_v4(p_row + kb * (BM * 128) + ((cin ^ (r & 7)) << 4), pack8(e + cc * 8));
+            }
+          };
+          tmem_ld_32x32b_x32(s_addr, sa);
+          tmem_ld_32x32b_x32(s_addr + 32, sb);
           tmem_ld_wait();
-          if (c4 == 3) {  // S is in registers for the last time: the tensor pipe may overwrite it with the next tile's S
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(PS_EMPTY + g));
-          }
-          float e[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float x = __uint_as_float(sv[c]);
-            if (ragged && j * BN + c4 * 32 + c >= p.seqlen) x = -INFINITY;
-            e[c] = ex2_approx(fmaf(x, sl, -msl));
-            sum4[c & 3] += e[c];
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int col = c4 * 32 + cc * 8;
-            const int kb = col >> 6, cin = (col & 63) >> 3;
-            st_shared_v4(p_row + kb * (BM * 128) + ((cin ^ (r & 7)) << 4), pack8(e + cc * 8));
-          }
+          emit(sa, 0);
+          tmem_ld_32x32b_x32(s_addr + 64, sa);
+          emit(sb, 32);
+          tmem_ld_32x32b_x32(s_addr + 96, sb);
+          tmem_ld_wait();
+          // S is in registers for the last time: the tensor pipe may overwrite it with the next tile's S
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(PS_EMPTY + g));
+          emit(sa, 64);
+          emit(sb, 96);
         }
         l_run = fmaf(l_run, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
         fence_proxy_async();

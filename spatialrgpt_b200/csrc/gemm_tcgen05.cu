@@ -1048,6 +1048,9 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (mt * BM >= p.M) break;  // warp-uniform
         const int trow = lg * 32 + lane;  // row inside the 128-row accumulator
         const int row = mt * BM + trow;
+        if (mt * BM + lg * 32 >= p.M) continue;  // warp-uniform: none of this warp's 32 rows exists (M = 32 of a batched decode step:
+                                                  // three of the four lane groups have nothing to read, write or add)
+        const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int ci = 0; ci < 2; ++ci) {
           const int c = cpart * 2 + ci;
@@ -1056,6 +1059,7 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + mt * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
           tmem_ld_wait();
+          if (!row_ok) continue;  // rows >= M: zero-filled operand rows, never stored, never exchanged
           if (!owner) {
             float4* dst = reinterpret_cast<float4*>(ws.partial + ((size_t)cta * MT + mt) * (BM * BN) + (size_t)trow * BN + c * 32);
 #pragma unroll
@@ -1073,7 +1077,7 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
               }
             }
-            if (row < p.M) store_chunk<EPI>(r, p, row, col0);
+            store_chunk<EPI>(r, p, row, col0);
           }
         }
       }

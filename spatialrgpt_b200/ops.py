@@ -394,6 +394,19 @@ def tp_pick_token(best_all, world: int, embed_table, next_x, out_ids, step, pos)
           "srgpt_tp_pick_token")
 
 
+def tp_allreduce_residual(peer_bases, rank: int, world: int, slot_off: int, idx: int, epoch, step, h) -> None:
+    """All-reduce of the ranks' fp32 partial sums (slot `slot_off` of every rank's symmetric buffer) over NVLink peer memory, fused
+    with h = bf16(bf16(sum) + h).  ``peer_bases`` = ctypes array of the peer-mapped buffer addresses."""
+    check(_lib.load().srgpt_tp_allreduce_residual_bf16(peer_bases, rank, world, slot_off, idx, _p(epoch), _p(step), _p(h), h.numel(), _stream()),
+          "srgpt_tp_allreduce_residual_bf16")
+
+
+def tp_allgather_pick(peer_bases, rank: int, world: int, slot_off: int, idx: int, epoch, embed_table, next_x, out_ids, step, pos) -> None:
+    K = 0 if embed_table is None else embed_table.shape[1]
+    check(_lib.load().srgpt_tp_allgather_pick_token(peer_bases, rank, world, slot_off, idx, _p(epoch), _p(embed_table), _p(next_x), K, _p(out_ids), _p(step),
+                                                    _p(pos), _stream()), "srgpt_tp_allgather_pick_token")
+
+
 def lm_head_workspace(V: int, device) -> torch.Tensor:
     return torch.empty(_lib.load().srgpt_lm_head_workspace(V), dtype=torch.uint8, device=device)
 

@@ -13,8 +13,17 @@ the TP-1 decoder of llama_decoder.py.  Megatron-style sharding of the decode ste
 The residual stream h, the position / step counters and the generated ids are replicated and stay bit-identical on all ranks
 (the all-reduce result and the gathered arg-max candidates are the same everywhere).  The KV cache keeps the FULL layout on every
 rank - a rank only reads and writes its own kv heads - so the prompt runs through the replicated, tensor-core bound prefill of
-LlamaDecoder unchanged and decode continues from it.  The collectives are NCCL calls on the compute stream, captured with the
-kernels in ONE CUDA graph per decode step (2 x layers all-reduces of H fp32 = 16 KB each + one 8-byte-per-rank all-gather).
+LlamaDecoder unchanged and decode continues from it.
+
+Collectives (2 x layers all-reduces of H fp32 = 16 KB + one 8-byte-per-rank all-gather per token), two implementations:
+  comm="p2p"  (default)  FUSED over NVLink peer memory (csrc/tp_comm.cu): the row-parallel GEMV writes its partial sums straight into
+              this rank's slot of a symmetric buffer (torch.distributed._symmetric_memory: cuMem allocation mapped into every peer);
+              one kernel then signals the peers, waits for their signals, pulls their slots through NVLink, reduces in rank order
+              and applies the residual add (the lm_head all-gather kernel also picks the token and advances the step) - no NCCL
+              call and no separate reduction kernel on the decode path;
+  comm="nccl"             torch.distributed all_reduce / all_gather_into_tensor on the compute stream + the residual / pick kernels:
+              the baseline the fused version is measured against (SRGPT_TP_COMM=nccl).
+Both run inside ONE CUDA graph per decode step.
 """
 from __future__ import annotations
 
@@ -52,7 +61,7 @@ class TPShard:
 
 
 class TPLlamaDecoder(LlamaDecoder):
-    def __init__(self, dims: LlamaDims, w: LlamaW, rank: int, world: int, group=None, max_seq_len: int = 4096, **kw):
+    def __init__(self, dims: LlamaDims, w: LlamaW, rank: int, world: int, group=None, max_seq_len: int = 4096, comm: Optional[str] = None, **kw):
         super().__init__(dims, w, max_seq_len=max_seq_len, **kw)
         if dims.num_attention_heads % world or dims.num_key_value_heads % world or dims.intermediate_size % world:
             raise ValueError(f"heads {dims.num_attention_heads}/{dims.num_key_value_heads} and intermediate size {dims.intermediate_size} must divide by TP={world}")
@@ -77,6 +86,47 @@ class TPLlamaDecoder(LlamaDecoder):
         self.best_all = torch.zeros(2 * world, dtype=torch.int32, device=dev)
         self.kernels_per_decode_step = 7 * dims.num_hidden_layers + 3
         self.allreduce_bytes_per_token = 2 * dims.num_hidden_layers * dims.hidden_size * 4
+        import os
+        self.comm = (comm or os.environ.get("SRGPT_TP_COMM") or "p2p") if world > 1 else "none"
+        self.tp_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.comm == "p2p":
+            self._init_p2p()
+
+    def _init_p2p(self) -> None:
+        """Symmetric buffer: flags [world][128] int32 | (2 x layers + 1) slots of H floats; peer-mapped through torch's symmetric
+        memory (plumbing: allocation + address exchange only; every byte moved on the decode path is moved by tp_comm.cu)."""
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        lib = _lib.load()
+        d = self.dims
+        n_slots = 2 * d.num_hidden_layers + 1
+        H = d.hidden_size
+        nbytes = int(lib.srgpt_tp_comm_bytes(self.world, n_slots, H))
+        group = self.group if self.group is not None else dist.group.WORLD
+        if hasattr(symm_mem, "enable_symm_mem_for_group"):
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:
+                pass
+        buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)  # every rank's flags are zero before anybody signals
+        self._symm = (buf, hdl)
+        self.peer_bases = (ctypes.c_ulonglong * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self.slot_off = [int(lib.srgpt_tp_comm_slot_offset(self.world, s, H)) for s in range(n_slots)]
+        self.slots = [buf[o // 4: o // 4 + H] for o in self.slot_off]
+        self.best_slot = self.slots[-1].view(torch.int32)[:2]
+        self.kernels_per_decode_step = 6 * d.num_hidden_layers + 2
+
+    def _decode_loop(self, *args, **kwargs):
+        self.tp_epoch.add_(1)  # a new request: flag values of the previous one can never match (tp_comm.cu seq_value)
+        return super()._decode_loop(*args, **kwargs)
 
     # ---- collectives (NCCL through torch.distributed, on the current stream; world 1 = no-ops) ------------------------------
     def _all_reduce(self, t: torch.Tensor) -> None:
@@ -98,12 +148,20 @@ class TPLlamaDecoder(LlamaDecoder):
         d, w = self.dims, self.w
         hd = d.head_dim
         group = d.num_attention_heads // d.num_key_value_heads
+        p2p = self.comm == "p2p"
         for l, sh in enumerate(self.shards):
             pages = self.cache.layer(l)
             ops.gemv_tp_qkv(self.h, sh.qkv_w, self.q_local, sh.in_norm, d.rms_norm_eps, self.nh_local, self.nkv_local, hd, self.cos, self.sin,
                             self.pos, pages, self.active_pt, PAGE_SIZE, d.num_key_value_heads, self.kv_off)
             ops.attention_decode_tp(self.q_local, self.attn_local, pages, self.active_pt, PAGE_SIZE, self.pos, self.nh_local, group,
                                     d.num_key_value_heads, self.kv_off, hd, self.scale)
+            if p2p:  # partial sums straight into the symmetric slots; reduce + residual fused over NVLink peer memory
+                ops.gemv_tp_partial(self.attn_local, sh.o_w, self.slots[2 * l])
+                ops.tp_allreduce_residual(self.peer_bases, self.rank, self.world, self.slot_off[2 * l], 2 * l, self.tp_epoch, self.step, self.h)
+                ops.gemv(self.h, sh.gateup_w, self.act_local, norm_weight=sh.post_norm, eps=d.rms_norm_eps, mode=ops.GEMV_SWIGLU)
+                ops.gemv_tp_partial(self.act_local, sh.down_w, self.slots[2 * l + 1])
+                ops.tp_allreduce_residual(self.peer_bases, self.rank, self.world, self.slot_off[2 * l + 1], 2 * l + 1, self.tp_epoch, self.step, self.h)
+                continue
             ops.gemv_tp_partial(self.attn_local, sh.o_w, self.partial)
             self._all_reduce(self.partial)
             ops.tp_residual_add(self.h, self.partial)
@@ -111,6 +169,12 @@ class TPLlamaDecoder(LlamaDecoder):
             ops.gemv_tp_partial(self.act_local, sh.down_w, self.partial)
             self._all_reduce(self.partial)
             ops.tp_residual_add(self.h, self.partial)
+        if p2p:
+            n_coll = 2 * d.num_hidden_layers
+            ops.lm_head_local_best(self.h, self.lm_local, w.norm, d.rms_norm_eps, self.lm_ws_local, self.v0, self.best_slot)
+            ops.tp_allgather_pick(self.peer_bases, self.rank, self.world, self.slot_off[n_coll], n_coll, self.tp_epoch, w.embed, self.h, self.out_ids,
+                                  self.step, self.pos)
+            return
         ops.lm_head_local_best(self.h, self.lm_local, w.norm, d.rms_norm_eps, self.lm_ws_local, self.v0, self.best)
         self._all_gather(self.best_all, self.best)
         ops.tp_pick_token(self.best_all, self.world, w.embed, self.h, self.out_ids, self.step, self.pos)

@@ -100,3 +100,63 @@ def test_driver_writes_the_reference_records(tmp_path):
     assert c1["ids"].shape[1] > c0["ids"].shape[1]  # the second turn carries the first question and an empty answer slot
     assert E.question_with_depth_tokens("a <mask> b <mask>") == "a <mask> <depth> b <mask> <depth>"
     assert E.stop_string("llava_v1") == "</s>" and E.clean_output(" x </s>", "</s>") == "x"
+
+
+# ---- region classification driver (spatialrgpt_b200/eval_region_cls.py, mirror of llava/eval/eval_region_cls.py) -------------------
+def test_region_cls_crop_box_matches_the_reference_rule():
+    from spatialrgpt_b200 import eval_region_cls as R
+    info = {"height": 100, "width": 160}
+    assert R.get_crop_box([[0, 0, 150, 40]], info) == [0, 0, 160, 100]            # wider than the short side: whole image
+    assert R.get_crop_box([[10, 10, 30, 40]], info) == [0, 0, 100, 100]           # window clipped at the left / top edge
+    # expected values = outputs of the reference's own get_crop_box (eval_region_cls.py:49-72) on these inputs; note its quirk: the
+    # right edge is compared with the SHORT side, so any window reaching past x = 100 snaps to the right border
+    assert R.get_crop_box([[60, 30, 100, 70]], info) == [60, 0, 160, 100]
+    assert R.get_crop_box([[120, 30, 150, 70]], info) == [60, 0, 160, 100]
+
+
+def test_region_cls_driver_end_to_end_with_a_stub_model(tmp_path):
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+
+    from spatialrgpt_b200 import eval_region_cls as R
+    Image.fromarray(np.random.RandomState(2).randint(0, 255, (60, 90, 3), dtype=np.uint8)).save(tmp_path / "img1.jpg")
+    os.makedirs(tmp_path / "coco" / "val2017")
+    os.replace(tmp_path / "img1.jpg", tmp_path / "coco" / "val2017" / "img1.jpg")
+    coco = {"images": [{"id": 5, "height": 60, "width": 90, "coco_url": "http://x/val2017/img1.jpg"}],
+            "categories": [{"id": 1, "name": "Dog"}, {"id": 2, "name": "cat"}],
+            "annotations": [{"id": 1, "image_id": 5, "category_id": 1, "iscrowd": 0, "bbox": [10, 5, 30, 40], "segmentation": [[12, 8, 38, 8, 38, 40, 12, 40]]},
+                            {"id": 2, "image_id": 5, "category_id": 2, "iscrowd": 1, "bbox": [0, 0, 5, 5], "segmentation": [[0, 0, 4, 0, 4, 4]]},
+                            {"id": 3, "image_id": 5, "category_id": 2, "iscrowd": 0, "bbox": [50, 20, 20, 20],
+                             "segmentation": {"size": [60, 90], "counts": [60 * 50 + 20, 20, 60 * 90 - 60 * 50 - 40]}}]}
+    (tmp_path / "ann.json").write_text(json.dumps(coco))
+    data = R.generate_data_list(str(tmp_path / "ann.json"))
+    assert [d["category_name"] for d in data] == ["dog", "cat"] and data[0]["bbox"] == [[10, 5, 40, 45]] and data[0]["image"] == os.path.join("coco", "val2017", "img1.jpg")
+    poly = R.segmentation_to_mask(data[0]["segmentation"][0], 60, 90)
+    assert poly.shape == (60, 90) and poly[20, 20] == 1 and poly[2, 2] == 0 and 800 < int(poly.sum()) < 1000
+    assert int(R.segmentation_to_mask(data[1]["segmentation"][0], 60, 90).sum()) == 20
+
+    proc = SiglipImageProcessor(size={"height": 28, "width": 28})
+    tok = ToyTokenizer()
+    seen = []
+
+    class Stub:
+        device = torch.device("cpu")
+        config = SimpleNamespace(image_aspect_ratio="resize", mm_use_im_start_end=False)
+
+        def generate(self, input_ids, images=None, masks=None, **kw):
+            seen.append((input_ids.clone(), tuple(images.shape), tuple(masks[0].shape), kw))
+            return torch.tensor([[tok._id("dog"), tok._id("</s>")]])
+
+    args = SimpleNamespace(model_path="m/tiny-cls", model_base=None, image_folder=str(tmp_path), annotation_file=str(tmp_path / "ann.json"),
+                           answers_file=str(tmp_path / "out" / "ans.jsonl"), conv_mode="llava_v1", num_chunks=1, chunk_idx=0, temperature=0.0, top_p=None,
+                           num_beams=1, dataset="coco", prompt_type="seg")
+    n = R.eval_model(args, loader=lambda p, name, base: (tok, Stub(), proc, 2048), seed=0)
+    rec = [json.loads(l) for l in open(args.answers_file)]
+    assert n == 2 and [r["gt_name"] for r in rec] == ["dog", "cat"] and rec[0]["text"] == "dog" and rec[0]["model_id"] == "tiny-cls"
+    assert rec[0]["question_id"] == data[0]["image"] and rec[0]["image_id"] == 5 and rec[1]["bbox"] == [[50, 20, 70, 40]]
+    ids, img_shape, mask_shape, kw = seen[0]
+    assert img_shape == (1, 3, 28, 28) and mask_shape == (1, 28, 28) and int((ids == IMAGE_TOKEN_INDEX).sum()) == 1
+    assert kw["max_new_tokens"] == 64 and kw["do_sample"] is False
+    # the box prompt type rasterises the box inside the same crop window
+    args.prompt_type = "box"
+    assert R.eval_model(args, loader=lambda p, name, base: (tok, Stub(), proc, 2048), seed=0) == 2

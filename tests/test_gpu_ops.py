@@ -365,9 +365,13 @@ def test_attention_prefill_varlen(ops, lens, nh, nkv, hd, causal):
         blk = qkv[o:o + n]
         ref = _sdpa_ref(blk[None, :, :qd], blk[None, :, qd:qd + kd], blk[None, :, qd + kd:], nh, nkv, hd, scale, causal)[0]
         assert_close(out[o:o + n], ref, rel_rms=1e-2, rel_max=8e-2, what=f"varlen attention len {n}")
-        # and bit-identical to the single-sequence entry point on the same rows
+        # and the single-sequence entry point on the same rows: bit-identical when both run the same kernel; the dense head-72 path
+        # may take the ping-pong kernel (different summation order) -> one bf16 rounding of difference at most
         one = ops.attention_prefill(d[o:o + n, :qd], d[o:o + n, qd:qd + kd], d[o:o + n, qd + kd:], 1, n, nh, nkv, hd, scale, causal)
-        assert torch.equal(one, out[o:o + n])
+        if hd == 72 and not causal:
+            assert_close(one, out[o:o + n], rel_rms=4e-3, rel_max=5e-2, what="dense vs varlen entry")
+        else:
+            assert torch.equal(one, out[o:o + n])
         o += n
 
 

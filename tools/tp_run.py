@@ -23,7 +23,10 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--new", type=int, default=512)
+    ap.add_argument("--comm", default="", help="p2p (fused NVLink peer-memory collectives, default) or nccl")
     args = ap.parse_args()
+    if args.comm:
+        os.environ["SRGPT_TP_COMM"] = args.comm
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
@@ -53,7 +56,7 @@ def main():
         if world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print(json.dumps({"mode": "check", "tp": world, "ok": bool(int(flags)), "ref_ids": ref, "tp_ids": got_graph}), flush=True)
+            print(json.dumps({"mode": "check", "tp": world, "comm": tp_model.llm.comm, "ok": bool(int(flags)), "ref_ids": ref, "tp_ids": got_graph}), flush=True)
         if not int(flags):
             sys.exit(1)
 
@@ -85,7 +88,7 @@ def main():
         ms_full, tp_ids = timed(model, args.new, 3)
         ms_ttft, _ = timed(model, 1, 3)
         step_ms = (ms_full - ms_ttft) / (args.new - 1)
-        line = {"mode": "bench", "config": "c5: Llama-3-8B TP decode, SigLIP@448, 8 mask regions, depth ON, 64-token prompt (S=259)", "tp": world,
+        line = {"mode": "bench", "config": "c5: Llama-3-8B TP decode, SigLIP@448, 8 mask regions, depth ON, 64-token prompt (S=259)", "tp": world, "comm": model.llm.comm if world > 1 else "none",
                 "new_tokens": args.new, "tokens_per_s": round(args.new / ms_full * 1e3, 1), "ms_per_request": round(ms_full, 2), "ttft_ms": round(ms_ttft, 2),
                 "decode_step_ms": round(step_ms, 4), "allreduce_bytes_per_token_per_rank": getattr(model.llm, "allreduce_bytes_per_token", 0),
                 "collectives_per_token": 2 * cfg.llama.num_hidden_layers + 1}
