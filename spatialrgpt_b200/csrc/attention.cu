@@ -442,6 +442,101 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
   trace_mark(trace, 2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched decode attention, one CTA per (kv head, sequence): the GROUP query heads that share a kv head (GQA) are served from ONE pass
+// over that head's K / V rows.  With a CTA per (q head, sequence) a 32-sequence step of Llama-3-8B launched 1024 CTAs that each
+// re-read their kv head's rows (48 us per layer in profiles/r02_launches_batched_decode.txt, against 6 us of bytes); here it is 256
+// CTAs and a quarter of the reads.  Same arithmetic per head as attn_decode_kernel (half-warp per kv row, base-2 online softmax).
+// ---------------------------------------------------------------------------------------------
+template <int GROUP>
+__global__ void __launch_bounds__(DEC_THREADS)
+attn_decode_gqa_kernel(const bf16* __restrict__ q, int q_ld, bf16* __restrict__ out, int o_ld, const bf16* __restrict__ kv_pages,
+                       const int* __restrict__ page_tables, int pt_stride, int page_size, const int* __restrict__ kv_len_minus1, int n_kv_heads,
+                       float scale_log2) {
+  constexpr int HD = 128;
+  __shared__ float s_m[DEC_HW], s_l[DEC_HW];
+  __shared__ float s_acc[DEC_HW][HD];
+  const int kvh = blockIdx.x, b = blockIdx.y;
+  const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const size_t row_stride = (size_t)n_kv_heads * HD;
+  const int* page_table = page_tables + (size_t)b * pt_stride;
+  const int kv_len = kv_len_minus1[b] + 1;
+  float qf[GROUP][8];
+#pragma unroll
+  for (int g = 0; g < GROUP; ++g) unpack8(*reinterpret_cast<const uint4*>(q + (size_t)b * q_ld + (kvh * GROUP + g) * HD + hl * 8), qf[g]);
+  float m[GROUP], l[GROUP], acc[GROUP][8];
+#pragma unroll
+  for (int g = 0; g < GROUP; ++g) {
+    m[g] = -INFINITY;
+    l[g] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[g][t] = 0.f;
+  }
+  for (int j0 = 0; j0 < kv_len; j0 += DEC_HW * DEC_UNROLL) {  // warp-uniform trip count
+    uint4 ku[DEC_UNROLL], vu[DEC_UNROLL];
+    bool valid[DEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int j = j0 + u * DEC_HW + hw;
+      valid[u] = j < kv_len;
+      ku[u] = make_uint4(0, 0, 0, 0);
+      vu[u] = make_uint4(0, 0, 0, 0);
+      if (valid[u]) dec_load_kv(kv_pages, page_table, page_size, row_stride, kvh, hl, j, ku[u], vu[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      float kf[8], vf[8], d[GROUP];
+      unpack8(ku[u], kf);
+      unpack8(vu[u], vf);
+#pragma unroll
+      for (int g = 0; g < GROUP; ++g) {
+        d[g] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d[g] = fmaf(qf[g][t], kf[t], d[g]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) d[g] += __shfl_xor_sync(0xffffffffu, d[g], o);  // stays inside the half-warp
+      }
+      if (valid[u]) {
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+          const float dd = d[g] * scale_log2;
+          const float m_new = fmaxf(m[g], dd);
+          const float a = exp2f(m[g] - m_new), pp = exp2f(dd - m_new);
+          l[g] = l[g] * a + pp;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[g][t] = acc[g][t] * a + pp * vf[t];
+          m[g] = m_new;
+        }
+      }
+    }
+  }
+  // cross-half-warp reduction, one head at a time through the same 16 KB of shared memory
+#pragma unroll
+  for (int g = 0; g < GROUP; ++g) {
+    __syncthreads();
+    if (hl == 0) { s_m[hw] = m[g]; s_l[hw] = l[g]; }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s_acc[hw][hl * 8 + t] = acc[g][t];
+    __syncthreads();
+    if (threadIdx.x < HD) {
+      float mt = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < DEC_HW; ++i) mt = fmaxf(mt, s_m[i]);
+      float lt = 0.f, at = 0.f;
+#pragma unroll
+      for (int i = 0; i < DEC_HW; ++i) {
+        const float w = (s_m[i] == -INFINITY) ? 0.f : exp2f(s_m[i] - mt);
+        lt += s_l[i] * w;
+        at += s_acc[i][threadIdx.x] * w;
+      }
+      out[(size_t)b * o_ld + (kvh * GROUP + g) * HD + threadIdx.x] = __float2bfloat16_rn(at / lt);
+    }
+  }
+}
+
 template <int HD, int HDP, bool CAUSAL>
 static int launch_prefill(const void* q, const void* k, const void* v, void* out, int q_ld, int kv_ld, int o_ld, int batch,
                           int seqlen, const int* cu_seqlens, int n_heads, int n_kv_heads, float scale, cudaStream_t st) {
@@ -581,9 +676,22 @@ extern "C" __attribute__((visibility("default"))) int srgpt_attention_decode_bat
     set_last_error("srgpt_attention_decode_batched_bf16: head_dim %d unsupported (128 only)", head_dim);
     return SRGPT_ERR_UNSUPPORTED;
   }
-  attn::attn_decode_kernel<<<dim3(n_heads, batch), attn::DEC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(q), reinterpret_cast<bf16*>(out), reinterpret_cast<const bf16*>(kv_pages), page_tables, page_size, kv_len_minus1,
-      n_kv_heads, n_heads / n_kv_heads, scale * 1.4426950408889634f, nullptr, 1, 0, q_ld, o_ld, pt_stride);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int group = n_heads / n_kv_heads;
+  const float sl2 = scale * 1.4426950408889634f;
+  const bf16* qp = reinterpret_cast<const bf16*>(q);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  const bf16* kp = reinterpret_cast<const bf16*>(kv_pages);
+  const dim3 grid(n_kv_heads, batch);
+  switch (group) {  // one CTA per (kv head, sequence): the group's query heads share one pass over the K / V rows
+    case 1: attn::attn_decode_gqa_kernel<1><<<grid, attn::DEC_THREADS, 0, st>>>(qp, q_ld, op, o_ld, kp, page_tables, pt_stride, page_size, kv_len_minus1, n_kv_heads, sl2); break;
+    case 2: attn::attn_decode_gqa_kernel<2><<<grid, attn::DEC_THREADS, 0, st>>>(qp, q_ld, op, o_ld, kp, page_tables, pt_stride, page_size, kv_len_minus1, n_kv_heads, sl2); break;
+    case 4: attn::attn_decode_gqa_kernel<4><<<grid, attn::DEC_THREADS, 0, st>>>(qp, q_ld, op, o_ld, kp, page_tables, pt_stride, page_size, kv_len_minus1, n_kv_heads, sl2); break;
+    case 8: attn::attn_decode_gqa_kernel<8><<<grid, attn::DEC_THREADS, 0, st>>>(qp, q_ld, op, o_ld, kp, page_tables, pt_stride, page_size, kv_len_minus1, n_kv_heads, sl2); break;
+    default:
+      attn::attn_decode_kernel<<<dim3(n_heads, batch), attn::DEC_THREADS, 0, st>>>(qp, op, kp, page_tables, page_size, kv_len_minus1, n_kv_heads, group, sl2,
+                                                                                 nullptr, 1, 0, q_ld, o_ld, pt_stride);
+  }
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

@@ -555,13 +555,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
       constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_v0 = umma_idesc_bf16(BM, 64, 0, 1);
       constexpr uint32_t idesc_v1 = umma_idesc_bf16(BM, G::W1, 0, 1);
-      uint32_t tg[2] = {0, 0};  // tiles issued so far per group (S and P V use the same count, P V one behind inside an item)
-      uint32_t tpv[2] = {0, 0};
-      uint32_t tk = 0, it = 0;  // kv tile counter (K / V ring positions), item counter
+      // Event-driven issue: four kinds of MMA batches are pending at any time - S_g(k) (needs K tile k and the S_g buffer back from the
+      // softmax group) and P_g V(k) (needs P_g(k), V tile k and the O_g buffer back) for g = A, B.  Each is issued the moment its
+      // barriers have flipped (non-blocking mbarrier.test_wait), in whatever order the two softmax groups get there: S_g(k+1) goes
+      // out as soon as group g has pulled S_g(k) into registers - long before P_g(k) exists - so the next S is ready when the group
+      // finishes the tile.  (First version: fixed order P_A V, S_A, P_B V, S_B with blocking waits; the profile showed the softmax
+      // warps spinning on S_FULL for a third of all samples.)
+      auto test = [&](int which, uint32_t parity) -> bool {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar(which)), "r"(parity) : "memory");
+        return ok != 0;
+      };
+      uint32_t tg[2] = {0, 0};   // S batches issued so far per group (all items)
+      uint32_t tpv[2] = {0, 0};  // P V batches issued so far per group
+      uint32_t tk = 0, it = 0;   // kv tiles consumed by finished items (K / V ring position of tile 0 of the item), item counter
       auto issue_s = [&](int g, uint32_t tkk) {  // S_g = Q_g K^T of the kv tile at ring position tkk
         const int ik = tkk % KST;
-        mbar_wait(bar(PK_FULL + ik), (tkk / KST) & 1);
-        mbar_wait(bar(PS_EMPTY + g), (tg[g] & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t d = tmem_base + g * BN;
         const uint32_t qa = sbase + OFF_Q + g * G::Q_BYTES, ka = sbase + OFF_K + ik * G::KV_BYTES;
@@ -576,9 +589,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
       };
       auto issue_pv = [&](int g, uint32_t tkk) {  // O_g = P_g V of the kv tile at ring position tkk (fresh accumulator)
         const int iv = tkk & 1;
-        mbar_wait(bar(PP_FULL + g), tpv[g] & 1);
-        mbar_wait(bar(PV_FULL + iv), (tkk >> 1) & 1);
-        mbar_wait(bar(PO_EMPTY + g), (tpv[g] & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t d = tmem_base + O_COL + g * 128;
         const uint32_t pa = sbase + OFF_P + g * G::P_BYTES, va = sbase + OFF_V + iv * G::KV_BYTES;
@@ -596,29 +606,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
       while (wi.next()) {
         const Item& k = wi.k;
         const int n = k.n_tiles;
-        const bool b = k.b_active;
+        const int ng = k.b_active ? 2 : 1;
         mbar_wait(bar(PQ_FULL), it & 1);
-        issue_s(0, tk);
-        if (b) issue_s(1, tk);
-        umma_commit(bar(PK_EMPTY + tk % KST));
-        if (n == 1) umma_commit(bar(PQ_EMPTY));
-        for (int j = 0; j < n; ++j) {
-          const uint32_t tkk = tk + j;
-          issue_pv(0, tkk);
-          if (j + 1 < n) {
-            issue_s(0, tkk + 1);
-            if (!b) {
-              umma_commit(bar(PK_EMPTY + (tkk + 1) % KST));
-              if (j + 2 == n) umma_commit(bar(PQ_EMPTY));
+        int s_done[2] = {0, 0}, pv_done[2] = {0, 0};  // batches issued inside this item
+        if (ng == 1) { s_done[1] = n; pv_done[1] = n; }
+        uint32_t spins = 0;
+        while (pv_done[0] < n || pv_done[1] < n) {
+          bool progressed = false;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g >= ng) continue;
+            if (s_done[g] < n) {
+              const uint32_t tkk = tk + s_done[g];
+              if (test(PK_FULL + tkk % KST, (tkk / KST) & 1) && test(PS_EMPTY + g, (tg[g] & 1) ^ 1)) {
+                issue_s(g, tkk);
+                ++s_done[g];
+                if (s_done[g ^ 1] >= s_done[g]) umma_commit(bar(PK_EMPTY + tkk % KST));          // both q tiles have read K tile k
+                if (s_done[0] == n && s_done[1] == n) umma_commit(bar(PQ_EMPTY));                 // the item's last S: Q may be reloaded
+                progressed = true;
+              }
+            }
+            if (pv_done[g] < s_done[g] || (pv_done[g] < n && s_done[g] == n)) {
+              const uint32_t tkk = tk + pv_done[g];
+              if (pv_done[g] < s_done[g] && test(PP_FULL + g, tpv[g] & 1) && test(PV_FULL + (tkk & 1), (tkk >> 1) & 1) &&
+                  test(PO_EMPTY + g, (tpv[g] & 1) ^ 1)) {
+                issue_pv(g, tkk);
+                ++pv_done[g];
+                if (pv_done[g ^ 1] >= pv_done[g]) umma_commit(bar(PV_EMPTY + (tkk & 1)));        // both q tiles have read V tile k
+                progressed = true;
+              }
             }
           }
-          if (b) issue_pv(1, tkk);
-          umma_commit(bar(PV_EMPTY + (tkk & 1)));
-          if (b && j + 1 < n) {
-            issue_s(1, tkk + 1);
-            umma_commit(bar(PK_EMPTY + (tkk + 1) % KST));
-            if (j + 2 == n) umma_commit(bar(PQ_EMPTY));
-          }
+          if (progressed) spins = 0;
+          else if (++spins > (1u << 28)) __trap();  // deadlock breaker
         }
         tk += n;
         ++it;

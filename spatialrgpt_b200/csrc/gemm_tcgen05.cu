@@ -1057,6 +1057,7 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t r[32];
+          __syncwarp();  // the row guard below diverges; tcgen05.ld is warp-collective
           tmem_ld_32x32b_x32(tmem_base + mt * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
           tmem_ld_wait();
           if (!row_ok) continue;  // rows >= M: zero-filled operand rows, never stored, never exchanged

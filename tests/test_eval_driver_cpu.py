@@ -160,3 +160,47 @@ def test_region_cls_driver_end_to_end_with_a_stub_model(tmp_path):
     # the box prompt type rasterises the box inside the same crop window
     args.prompt_type = "box"
     assert R.eval_model(args, loader=lambda p, name, base: (tok, Stub(), proc, 2048), seed=0) == 2
+
+
+# ---- multi-turn region chat (spatialrgpt_b200/chat.py, the follow-up flow of demo/gradio_web_server_multi.py:137-236) ---------------
+def test_region_chat_follow_up_flow_with_a_stub_model():
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+
+    from spatialrgpt_b200.chat import RegionChat
+    proc = SiglipImageProcessor(size={"height": 28, "width": 28})
+    tok = ToyTokenizer()
+    calls = []
+    answers = iter(["Region [0] is behind Region [1] </s>", "It is [0] </s>"])
+
+    class Stub:
+        device = torch.device("cpu")
+        config = SimpleNamespace(image_aspect_ratio="resize", mm_use_im_start_end=False)
+
+        def generate(self, input_ids, images=None, depths=None, masks=None, **kw):
+            calls.append((input_ids.clone(), masks[0].clone(), depths is not None, kw))
+            return torch.tensor([tok(next(answers)).input_ids[1:]])
+
+    img = Image.fromarray(np.random.RandomState(0).randint(0, 255, (40, 50, 3), dtype=np.uint8))
+    depth = Image.fromarray(np.random.RandomState(1).randint(0, 255, (40, 50, 3), dtype=np.uint8))
+    segs = [np.zeros((40, 50), dtype=np.uint8) for _ in range(4)]
+    for i, s in enumerate(segs):
+        s[5 * i:5 * i + 8, 4:20] = 1
+    chat = RegionChat(Stub(), tok, proc, conv_mode="llava_v1")
+    a1 = chat.ask("Is <region2> behind <region0> ?", img, segs, depth_image=depth)
+    assert a1 == "Region [2] is behind Region [0]"            # [k] = k-th region of the turn -> the user's region number
+    ids1, masks1, had_depth, kw = calls[0]
+    assert had_depth and masks1.shape[0] == 2 and int((ids1 == IMAGE_TOKEN_INDEX).sum()) == 1
+    assert kw["stopping_criteria"] and kw["do_sample"] is False
+    a2 = chat.ask("And how wide is <region3> ?", img, segs, depth_image=depth, follow_up=True)
+    assert a2 == "It is [3]"
+    ids2, masks2, _, _ = calls[1]
+    assert masks2.shape[0] == 3                                # the masks of ALL region references so far: regions 2, 0, 3
+    full = __import__("spatialrgpt_b200.mm_utils", fromlist=["process_regions"]).process_regions(segs, proc, Stub.config)
+    assert torch.equal(masks2.float(), full[[2, 0, 3]].to(torch.bfloat16).float())
+    assert ids2.shape[1] > ids1.shape[1] and int((ids2 == IMAGE_TOKEN_INDEX).sum()) == 1  # the conversation grew, one image token
+    assert chat.conv.messages[1][1] == "Region [0] is behind Region [1]" and len(chat.conv.messages) == 4
+    # a new first turn resets the session
+    answers2 = iter(["ok </s>"])
+    Stub.generate = lambda self, input_ids, images=None, depths=None, masks=None, **kw: torch.tensor([tok(next(answers2)).input_ids[1:]])
+    assert chat.ask("What is <region1> ?", img, segs) == "ok" and len(chat.user_turns) == 1

@@ -408,6 +408,20 @@ def test_argmax_bf16_first_index_on_ties(ops):
     wide[:, :1000] = x
     wide[:, 1000:] = 9.0  # beyond `cols`: must be ignored (strided rows)
     assert ops.argmax_bf16(wide.to(DEV)[:, :1000]).tolist() == [17, 999, 0]
+    # vocabulary-wide rows take the segmented kernel (one CTA per 4096 columns, 64-bit atomicMax of (value, ~index)): same answers,
+    # ties across segments -> lowest index, negative values, -inf, a NaN that must not win, an all-NaN row -> 0
+    V = 128259
+    g = torch.Generator().manual_seed(3)
+    y = (torch.randn(5, V + 5, generator=g) * 3).to(BF)
+    y[1, 70000] = y[1, 120] = 50.0
+    y[2] = -torch.rand(V + 5, generator=g).to(BF) - 1
+    y[3, 5] = float("nan")
+    y[4] = float("nan")
+    y[:, V:] = 99.0
+    ref = y[:, :V].float().nan_to_num(nan=float("-inf")).argmax(-1).tolist()
+    ref[4] = 0
+    got = ops.argmax_bf16(y.to(DEV)[:, :V]).tolist()
+    assert got == ref and got[1] == 120
 
 
 def _rope_tables(hd, theta, max_pos):
@@ -655,3 +669,31 @@ def test_mask_pool_odd_sides_and_ragged_channels(ops, side, C, M, R):
     out = ops.mask_pool(x.to(DEV), w)
     assert_close(out, ref, **BF16_CHAIN, what="odd-side mask_pool")
     assert torch.equal(ops.mask_pool(x.to(DEV), w), out)
+
+
+@pytest.mark.parametrize("nh,nkv", [(8, 2), (4, 4), (8, 1), (6, 2)])
+def test_attention_decode_batched_equals_per_sequence(ops, nh, nkv):
+    """Batched decode attention (one CTA per kv head and sequence, the GQA group served from one pass over K / V; group sizes without
+    a specialisation fall back to one CTA per query head) against the single-sequence kernel on every sequence: different lengths,
+    scattered pages, q read as a column slice of a fused qkv buffer."""
+    hd, page, B = 128, 16, 5
+    lens = [1, 17, 300, 64, 259]
+    n_pages = sum((n + page - 1) // page for n in lens) + 3
+    pages = rnd(n_pages, 2, page, nkv, hd, seed=31).to(DEV)
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(32)).tolist()
+    cap = max((n + page - 1) // page for n in lens) + 1
+    pts = torch.zeros(B, cap, dtype=torch.int32)
+    o = 0
+    for b, n in enumerate(lens):
+        k = (n + page - 1) // page
+        pts[b, :k] = torch.tensor(perm[o:o + k], dtype=torch.int32)
+        o += k
+    pts = pts.to(DEV)
+    qkv = rnd(B, (nh + 2 * nkv) * hd, seed=33).to(DEV)
+    pos = torch.tensor([n - 1 for n in lens], dtype=torch.int32, device=DEV)
+    out = torch.zeros(B, nh * hd, dtype=BF, device=DEV)
+    ops.attention_decode_batched(qkv[:, :nh * hd], out, pages, pts, page, pos, nh, nkv, hd, hd ** -0.5)
+    for b in range(B):
+        one = torch.zeros(nh * hd, dtype=BF, device=DEV)
+        ops.attention_decode(qkv[b, :nh * hd].contiguous(), one, pages, pts[b].contiguous(), page, pos[b:b + 1].contiguous(), nh, nkv, hd, hd ** -0.5)
+        assert_close(out[b], one, rel_rms=2e-3, rel_max=2e-2, what=f"batched decode attention seq {b}")
