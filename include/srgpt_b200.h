@@ -186,6 +186,17 @@ int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out
 int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed, const int* step, int step_offset,
                            long long* out_ids, const void* embed_table, void* next_x, int K, void* stream);
 
+/* ---- host preprocessing on the GPU (preprocess.cu; llava/mm_utils.py:421-542: process_images / process_regions) ----------
+ * The pinned image processor (transformers 4.37.2 SiglipImageProcessor) = Pillow BICUBIC resize of the uint8 image + rescale +
+ * normalise; masks = cv2 INTER_NEAREST.  Pillow's resampler is integer arithmetic over host-built coefficient tables
+ * (spatialrgpt_b200/preprocess.py, same double arithmetic as libImaging/Resample.c), so the results are bit-exact. */
+int srgpt_resample_u8(const void* in, void* out, int H, int W, int C, int axis, int out_size, const int* kk, const int* bounds, int ksize,
+                      void* stream);
+/* mean3 / std3: HOST arrays of 3 floats (passed by value to the kernel) */
+int srgpt_u8_to_normalized_chw(const void* in, float* out, int H, int W, int C, double scale, const float* mean3, const float* std3,
+                               int do_normalize, void* stream);
+int srgpt_resize_nearest_u8(const void* in, float* out, int H, int W, int Hout, int Wout, const int* ys, const int* xs, void* stream);
+
 /* ---- batched decode (B sequences, one new token each; llava_arch.py:549-611 pads, modeling_llama.py:540-562 un-pads: here
  * the rows are never padded).  The projections are srgpt_gemm_bf16 over the B rows (tall stream-K configuration: every weight is
  * streamed once for the whole batch), RoPE / KV append is srgpt_rope_kv_append_varlen_bf16 with one row per sequence. */

@@ -17,7 +17,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(PKG_DIR, "libsrgpt_b200.so")
 
-SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemv.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "region.cu", "sampling.cu", "tp_comm.cu", "layers.cu"]
+SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemv.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "region.cu", "sampling.cu", "tp_comm.cu", "preprocess.cu", "layers.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

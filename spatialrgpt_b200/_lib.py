@@ -55,6 +55,9 @@ SIGNATURES = {
     "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
     "srgpt_argmax_bf16": (ci, [vp, ci, ci, ci, vp, vp]),
     "srgpt_sample_top_p_f32": (ci, [vp, ci, vp, C.c_ulonglong, vp, ci, vp, vp, vp, ci, vp]),
+    "srgpt_resample_u8": (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
+    "srgpt_u8_to_normalized_chw": (ci, [vp, vp, ci, ci, ci, C.c_double, vp, vp, ci, vp]),
+    "srgpt_resize_nearest_u8": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp]),
     "srgpt_attention_decode_batched_bf16": (ci, [vp, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, ci, cf, vp]),
     "srgpt_decode_batch_advance": (ci, [vp, vp, vp, ci, vp, vp, vp, ci, vp, vp]),
     "srgpt_gemv_tp_bf16": (ci, [vp, vp, ci, vp, ci, ci, vp, cf, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]),

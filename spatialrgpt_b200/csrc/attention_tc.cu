@@ -719,9 +719,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
         const float alpha = ex2_approx((m_run - m_use) * sl);  // m_run = -inf -> 0
         m_run = m_new;
         const float msl = m_use * sl;
-        // ---- the previous tile's P V product, folded while the tensor pipe may still be busy with the other group
-        if (j > 0) fold(t - 1, alpha_prev);
-        alpha_prev = alpha;
         // ---- pass 2: P = 2^(s * scale - m) -> bf16 -> 128B-swizzled K-major tile, row sum; loads pipelined as in pass 1
         mbar_wait(bar(PP_EMPTY + g), (t & 1) ^ 1);
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -768,6 +765,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_vit_pp_kernel(const __grid_c
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(PP_FULL + g));
+        // ---- the PREVIOUS tile's P V product: issued a whole tile ago, so it is complete by now (folding it between the two passes
+        //      had the group spin on O_FULL for 12 % of the samples); P_g V(j) waits for this fold through O_EMPTY, ~200 clk
+        if (j > 0) fold(t - 1, alpha_prev);
+        alpha_prev = alpha;
       }
       // ---- last product of the item, normalisation, store (72 channels = nine 16-byte vectors per row)
       fold(t - 1, alpha_prev);

@@ -65,9 +65,14 @@ def process_image(image_file, data_args, image_folder=None, return_info: bool = 
     return pixel
 
 
-def process_images(images, image_processor, model_cfg):
-    """mm_utils.py:535-542: stacks when every image has the same shape, else returns a list."""
+def process_images(images, image_processor, model_cfg, device=None):
+    """mm_utils.py:535-542: stacks when every image has the same shape, else returns a list.  With ``device`` (a CUDA device) the
+    resize / rescale / normalise run in the sm_100a kernels of preprocess.py (bit-identical to the pinned Pillow-based processor) and
+    the result stays on the GPU - the CPU stage in front of TTFT disappears."""
     model_cfg.image_processor = image_processor
+    if device is not None and torch.device(device).type == "cuda":
+        from .preprocess import process_images_gpu
+        return process_images_gpu(images, image_processor, model_cfg, torch.device(device))
     out = [process_image(im, model_cfg, None) for im in images]
     if all(x.shape == out[0].shape for x in out):
         out = torch.stack(out, dim=0)
@@ -92,8 +97,12 @@ def _pad_to_square(a: np.ndarray) -> np.ndarray:
     return out
 
 
-def process_regions(masks: Sequence[np.ndarray], image_processor, data_args) -> torch.Tensor:
-    """mm_utils.py:477-532: uint8 region masks [H, W] -> float tensor [M, R, R]."""
+def process_regions(masks: Sequence[np.ndarray], image_processor, data_args, device=None) -> torch.Tensor:
+    """mm_utils.py:477-532: uint8 region masks [H, W] -> float tensor [M, R, R] (on ``device`` through the nearest-neighbour kernel
+    when a CUDA device is given and the aspect mode is "resize")."""
+    if device is not None and torch.device(device).type == "cuda" and getattr(data_args, "image_aspect_ratio", None) == "resize":
+        from .preprocess import process_regions_gpu
+        return process_regions_gpu(masks, image_processor, data_args, torch.device(device))
     import cv2
 
     mp = _mask_processor(image_processor)

@@ -327,6 +327,35 @@ def gemv(x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, norm_weight: Optiona
     return y
 
 
+# ---- host preprocessing on the GPU (preprocess.py) ---------------------------------------------------------------
+def resample_u8(img: torch.Tensor, axis: int, out_size: int, kk: torch.Tensor, bounds: torch.Tensor, ksize: int) -> torch.Tensor:
+    _need(img, torch.uint8, "resample_u8.img"); _need(kk, torch.int32, "resample_u8.kk"); _need(bounds, torch.int32, "resample_u8.bounds")
+    H, W, Cc = img.shape
+    out = torch.empty((out_size, W, Cc) if axis == 0 else (H, out_size, Cc), dtype=torch.uint8, device=img.device)
+    check(_lib.load().srgpt_resample_u8(_p(img), _p(out), H, W, Cc, axis, out_size, _p(kk), _p(bounds), ksize, _stream()), "srgpt_resample_u8")
+    return out
+
+
+def u8_to_normalized_chw(img: torch.Tensor, scale: float, mean, std, do_normalize: bool = True) -> torch.Tensor:
+    import ctypes
+    _need(img, torch.uint8, "u8_to_normalized_chw.img")
+    H, W, Cc = img.shape
+    out = torch.empty((Cc, H, W), dtype=torch.float32, device=img.device)
+    m3 = (ctypes.c_float * 3)(*([float(v) for v in mean] + [0.0] * 3)[:3])
+    s3 = (ctypes.c_float * 3)(*([float(v) for v in std] + [1.0] * 3)[:3])
+    check(_lib.load().srgpt_u8_to_normalized_chw(_p(img), _p(out), H, W, Cc, float(scale), m3, s3, 1 if do_normalize else 0, _stream()),
+          "srgpt_u8_to_normalized_chw")
+    return out
+
+
+def resize_nearest_u8(img: torch.Tensor, out_h: int, out_w: int, ys: torch.Tensor, xs: torch.Tensor) -> torch.Tensor:
+    _need(img, torch.uint8, "resize_nearest_u8.img"); _need(ys, torch.int32, "resize_nearest_u8.ys"); _need(xs, torch.int32, "resize_nearest_u8.xs")
+    H, W = img.shape
+    out = torch.empty((out_h, out_w), dtype=torch.float32, device=img.device)
+    check(_lib.load().srgpt_resize_nearest_u8(_p(img), _p(out), H, W, out_h, out_w, _p(ys), _p(xs), _stream()), "srgpt_resize_nearest_u8")
+    return out
+
+
 # ---- batched decode ----------------------------------------------------------------------------------------------
 def attention_decode_batched(q: torch.Tensor, out: torch.Tensor, kv_pages: torch.Tensor, page_tables: torch.Tensor, page_size: int, pos: torch.Tensor,
                              n_heads: int, n_kv_heads: int, head_dim: int, scale: float) -> torch.Tensor:

@@ -697,3 +697,51 @@ def test_attention_decode_batched_equals_per_sequence(ops, nh, nkv):
         one = torch.zeros(nh * hd, dtype=BF, device=DEV)
         ops.attention_decode(qkv[b, :nh * hd].contiguous(), one, pages, pts[b].contiguous(), page, pos[b:b + 1].contiguous(), nh, nkv, hd, hd ** -0.5)
         assert_close(out[b], one, rel_rms=2e-3, rel_max=2e-2, what=f"batched decode attention seq {b}")
+
+
+# ------------------------------------------------------------------------------------------ preprocessing on the GPU
+@pytest.mark.parametrize("H,W,oh,ow", [(40, 70, 56, 56), (480, 640, 448, 448), (100, 100, 448, 448), (1000, 750, 336, 336), (448, 448, 448, 448), (37, 91, 384, 384)])
+def test_gpu_bicubic_resize_is_pillow_exact(ops, H, W, oh, ow):
+    """f2: Pillow's BICUBIC resize (what the pinned SiglipImageProcessor of transformers 4.37.2 calls) reproduced bit for bit."""
+    from PIL import Image
+
+    from spatialrgpt_b200.preprocess import resize_bicubic_u8
+    a = np.random.RandomState(H + W).randint(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(a).resize((ow, oh), Image.BICUBIC))
+    got = resize_bicubic_u8(torch.from_numpy(a).to(DEV), oh, ow).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_gpu_process_images_and_regions_match_the_pinned_cpu_path():
+    import cv2
+    from PIL import Image
+    from transformers import SiglipImageProcessor
+    from types import SimpleNamespace
+
+    from spatialrgpt_b200 import mm_utils as M
+    proc = SiglipImageProcessor(size={"height": 448, "width": 448})
+    cfg = SimpleNamespace(image_aspect_ratio="resize", image_processor=proc)
+    rng = np.random.RandomState(5)
+    imgs = [Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8)) for (h, w) in ((480, 640), (333, 500))]
+    got = M.process_images(imgs, proc, cfg, device=DEV)
+    assert got.shape == (2, 3, 448, 448) and got.dtype == torch.float32 and got.is_cuda
+    for i, im in enumerate(imgs):
+        u8 = np.asarray(im.resize((448, 448), Image.BICUBIC))
+        pinned = ((u8.astype(np.float64) * proc.rescale_factor).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+        assert np.array_equal(got[i].cpu().numpy(), pinned.transpose(2, 0, 1))
+    # the installed transformers (torchvision backend) is within one 8-bit step of the pinned Pillow arithmetic
+    cpu = M.process_images(imgs, proc, cfg)
+    assert float((got.cpu() - cpu).abs().max()) <= 2.0 / 255 + 1e-6
+    # pad mode: expand2square with the mean colour, then the same resize
+    cfg_pad = SimpleNamespace(image_aspect_ratio="pad", image_processor=proc)
+    gp = M.process_images(imgs[:1], proc, cfg_pad, device=DEV)
+    sq = M._expand2square(imgs[0].convert("RGB"), tuple(int(x * 255) for x in proc.image_mean))
+    u8 = np.asarray(sq.resize((448, 448), Image.BICUBIC))
+    pinned = ((u8.astype(np.float64) * proc.rescale_factor).astype(np.float32) - np.float32(0.5)) / np.float32(0.5)
+    assert np.array_equal(gp[0].cpu().numpy(), pinned.transpose(2, 0, 1))
+    # regions: cv2 INTER_NEAREST
+    masks = [(rng.rand(480, 640) > 0.5).astype(np.uint8), (rng.rand(97, 211) > 0.7).astype(np.uint8)]
+    gr = M.process_regions(masks, proc, cfg, device=DEV)
+    assert gr.shape == (2, 448, 448) and gr.dtype == torch.float32
+    for i, m in enumerate(masks):
+        assert np.array_equal(gr[i].cpu().numpy(), cv2.resize(m, (448, 448), interpolation=cv2.INTER_NEAREST).astype(np.float32))
