@@ -46,6 +46,10 @@ __device__ __forceinline__ unsigned int seq_value(const int* epoch, const int* s
 
 // signal + wait: thread 0 of block 0 tells every peer, thread 0 of every block waits for every peer
 __device__ __forceinline__ void exchange_flags(const Peers& peers, int rank, int world, int idx, unsigned int seq) {
+  // programmatic dependent launch on both sides: the NEXT kernel (a weight-streaming GEMV) may start now and prefetch its rows
+  // during the NVLink round trip below; this kernel itself started early and now waits for the GEMV that wrote the partial sums
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       __threadfence_system();  // the partial written by the previous kernel of this stream is visible to the peers before the flag
@@ -142,9 +146,16 @@ extern "C" __attribute__((visibility("default"))) int srgpt_tp_allreduce_residua
   tp::Peers peers;
   SRGPT_CHECK_ARG(fill_peers(&peers, peer_bases, world) == 0 && rank >= 0 && rank < world && idx >= 0 && idx < tp::TP_FLAGS);
   SRGPT_CHECK_ARG(epoch && step && h && n > 0 && (n % 4) == 0 && (slot_off_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(h) & 7) == 0);
-  tp::allreduce_residual_kernel<<<ceil_div(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peers, rank, world, slot_off_bytes, idx, epoch, step,
-                                                                                                        reinterpret_cast<bf16*>(h), n);
-  SRGPT_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(n / 4, 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tp::allreduce_residual_kernel, peers, rank, world, slot_off_bytes, idx, epoch, step, reinterpret_cast<bf16*>(h), n));
   return SRGPT_OK;
 }
 
@@ -155,9 +166,16 @@ extern "C" __attribute__((visibility("default"))) int srgpt_tp_allgather_pick_to
   SRGPT_CHECK_ARG(fill_peers(&peers, peer_bases, world) == 0 && rank >= 0 && rank < world && idx >= 0 && idx < tp::TP_FLAGS);
   SRGPT_CHECK_ARG(epoch && out_ids && step && pos && (slot_off_bytes % 8) == 0);
   SRGPT_CHECK_ARG((embed_table == nullptr) == (next_x == nullptr));
-  tp::allgather_pick_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peers, rank, world, slot_off_bytes, idx, epoch,
-                                                                                 reinterpret_cast<const bf16*>(embed_table), reinterpret_cast<bf16*>(next_x), K, out_ids,
-                                                                                 step, pos);
-  SRGPT_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(256);
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tp::allgather_pick_kernel, peers, rank, world, slot_off_bytes, idx, epoch, reinterpret_cast<const bf16*>(embed_table),
+                                      reinterpret_cast<bf16*>(next_x), K, out_ids, step, pos));
   return SRGPT_OK;
 }

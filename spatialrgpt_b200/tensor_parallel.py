@@ -107,11 +107,6 @@ class TPLlamaDecoder(LlamaDecoder):
         H = d.hidden_size
         nbytes = int(lib.srgpt_tp_comm_bytes(self.world, n_slots, H))
         group = self.group if self.group is not None else dist.group.WORLD
-        if hasattr(symm_mem, "enable_symm_mem_for_group"):
-            try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-            except Exception:
-                pass
         buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=self.device)
         buf.zero_()
         hdl = symm_mem.rendezvous(buf, group)

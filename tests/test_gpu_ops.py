@@ -1,5 +1,7 @@
 """Op-level parity of every C-ABI kernel against plain fp32 torch / the CPU oracle.  Needs a B200."""
 import math
+
+import numpy as np
 import os
 
 import pytest

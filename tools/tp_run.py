@@ -103,8 +103,13 @@ def main():
             line.update({"tp1_ids_head": ref_ids[:16], "tp_ids_head": tp_ids[:16], "ids_equal_on_margin_safe_prefix": tp_ids[:safe] == ref_ids[:safe],
                          "margin_safe_prefix": safe, "ids_equal_32": tp_ids[:32] == ref_ids})
             print(json.dumps(line), flush=True)
+    # leave without tearing down NCCL / the captured graphs: with collectives captured in a CUDA graph (comm=nccl) the teardown was
+    # seen to hang on the 2-GPU box after all results were printed
+    sys.stdout.flush()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+    os._exit(0)
 
 
 if __name__ == "__main__":
