@@ -41,15 +41,19 @@ __device__ __forceinline__ float4 ld_peer_f4(const float4* p) {  // peer memory:
 }
 
 __device__ __forceinline__ unsigned int seq_value(const int* epoch, const int* step, int idx) {
-  return ((unsigned int)(*epoch & 0xFFF) << 20) | ((unsigned int)(*step & 0xFFF) << 8) | (unsigned int)(idx + 1);
+  const int e = *reinterpret_cast<const volatile int*>(epoch), st = *reinterpret_cast<const volatile int*>(step);  // never from a cached copy
+  return ((unsigned int)(e & 0xFFF) << 20) | ((unsigned int)(st & 0xFFF) << 8) | (unsigned int)(idx + 1);
 }
 
 // signal + wait: thread 0 of block 0 tells every peer, thread 0 of every block waits for every peer
-__device__ __forceinline__ void exchange_flags(const Peers& peers, int rank, int world, int idx, unsigned int seq) {
+__device__ __forceinline__ void exchange_flags(const Peers& peers, int rank, int world, int idx, const int* epoch, const int* step) {
   // programmatic dependent launch on both sides: the NEXT kernel (a weight-streaming GEMV) may start now and prefetch its rows
   // during the NVLink round trip below; this kernel itself started early and now waits for the GEMV that wrote the partial sums
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // only NOW are the step / epoch counters final (the previous step's token kernel increments *step; reading them before the wait
+  // made an early-started kernel signal a stale sequence value and its peer spin forever: found on the 2-GPU box in eager mode)
+  const unsigned int seq = seq_value(epoch, step, idx);
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       __threadfence_system();  // the partial written by the previous kernel of this stream is visible to the peers before the flag
@@ -71,7 +75,7 @@ __device__ __forceinline__ void exchange_flags(const Peers& peers, int rank, int
 __global__ void __launch_bounds__(256)
 allreduce_residual_kernel(const Peers peers, int rank, int world, long long slot_off_bytes, int idx, const int* __restrict__ epoch,
                           const int* __restrict__ step, bf16* __restrict__ h, int n) {
-  exchange_flags(peers, rank, world, idx, seq_value(epoch, step, idx));
+  exchange_flags(peers, rank, world, idx, epoch, step);
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256)
 allgather_pick_kernel(const Peers peers, int rank, int world, long long slot_off_bytes, int idx, const int* __restrict__ epoch, const bf16* __restrict__ embed_table,
                       bf16* __restrict__ next_x, int K, long long* __restrict__ out_ids, int* step, int* pos) {
   __shared__ int s_tok;
-  exchange_flags(peers, rank, world, idx, seq_value(epoch, step, idx));
+  exchange_flags(peers, rank, world, idx, epoch, step);
   if (threadIdx.x == 0) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;

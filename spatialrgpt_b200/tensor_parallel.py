@@ -119,6 +119,12 @@ class TPLlamaDecoder(LlamaDecoder):
         self.best_slot = self.slots[-1].view(torch.int32)[:2]
         self.kernels_per_decode_step = 6 * d.num_hidden_layers + 2
 
+    def _ensure_graph(self, seq: int, sample: bool = False) -> None:
+        had = (self._graph_sample if sample else self._graph) is not None
+        super()._ensure_graph(seq, sample)
+        if not had:  # the warm-up step before the capture ran real collectives with the current (epoch, step): retire those flag values
+            self.tp_epoch.add_(1)
+
     def _decode_loop(self, *args, **kwargs):
         self.tp_epoch.add_(1)  # a new request: flag values of the previous one can never match (tp_comm.cu seq_value)
         return super()._decode_loop(*args, **kwargs)
