@@ -1067,15 +1067,31 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int j = 0; j < 8; ++j)
               dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           } else {
-            for (int cc = cta + 1; cc <= c_last; ++cc) {  // fixed order: deterministic sums
-              const float4* src = reinterpret_cast<const float4*>(ws.partial + ((size_t)cc * MT + mt) * (BM * BN) + (size_t)trow * BN + c * 32);
+            // fixed order: deterministic sums.  The partials of up to four contributors are requested together (half a chunk = four
+            // 16-byte loads each) so the fix-up pays one L2 round trip per half chunk instead of one per contributor
+            for (int cc0 = cta + 1; cc0 <= c_last; cc0 += 4) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 v = __ldcg(src + j);
-                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
-                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
-                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
-                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+              for (int half = 0; half < 2; ++half) {
+                float4 v[4][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  const int cc = cc0 + b;
+                  const float4* src = reinterpret_cast<const float4*>(ws.partial + ((size_t)(cc <= c_last ? cc : cta + 1) * MT + mt) * (BM * BN) +
+                                                                      (size_t)trow * BN + c * 32 + half * 16);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[b][j] = (cc <= c_last) ? __ldcg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int q = half * 16 + 4 * j;
+                    r[q] = __float_as_uint(__uint_as_float(r[q]) + v[b][j].x);
+                    r[q + 1] = __float_as_uint(__uint_as_float(r[q + 1]) + v[b][j].y);
+                    r[q + 2] = __float_as_uint(__uint_as_float(r[q + 2]) + v[b][j].z);
+                    r[q + 3] = __float_as_uint(__uint_as_float(r[q + 3]) + v[b][j].w);
+                  }
+                }
               }
             }
             store_chunk<EPI>(r, p, row, col0);
