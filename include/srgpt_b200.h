@@ -8,7 +8,12 @@
  *
  * Conventions
  *   - plain C: device pointers as void*, sizes as int / long long, CUDA stream as void* (cudaStream_t).
- *   - all tensors are row-major; "bf16" means __nv_bfloat16; strides (ld*) are in ELEMENTS.
+ *   - all tensors are row-major; strides (ld*) are in ELEMENTS.
+ *   - element type: the library is built twice from the same sources.  libsrgpt_b200.so computes in bfloat16 (the dtype the
+ *     reference's eval scripts load the model in, llava/eval/eval_spatial.py:206-212); libsrgpt_b200_f16.so (-DSRGPT_ELEM_F16) in
+ *     IEEE half, the reference loader's default (llava/model/builder.py:62, llava/eval/eval_region_cls.py:316-317).  Both export the
+ *     SAME entry points: in the names and comments below "bf16" stands for "the 16-bit element type of the build" - __nv_bfloat16
+ *     or __half - and srgpt_elem_type() says which.  Accumulation is fp32 and the rounding points are identical in both builds.
  *   - every function is asynchronous on `stream`, allocates nothing, and returns 0 on success or a
  *     negative srgpt error code; the message is available from srgpt_last_error().  Nothing throws.
  *   - callable from any host thread; no global state except the last-error string (thread-local).
@@ -24,6 +29,8 @@ extern "C" {
 
 /* ---- library -------------------------------------------------------------------------------- */
 int srgpt_abi_version(void);
+/* 0 = bfloat16 build, 1 = IEEE half build (see "element type" above). */
+int srgpt_elem_type(void);
 const char* srgpt_last_error(void);
 /* sm count + compute capability of the current device; fails (<0) unless it is sm_100. */
 int srgpt_device_info(int* sm_count, int* cc_major, int* cc_minor);

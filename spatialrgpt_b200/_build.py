@@ -16,6 +16,10 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(PKG_DIR, "libsrgpt_b200.so")
+# the same sources compiled with IEEE half as the 16-bit element type (csrc/common.cuh): the reference loader's default dtype
+# (llava/model/builder.py:62)
+LIB_PATH_F16 = os.path.join(PKG_DIR, "libsrgpt_b200_f16.so")
+VARIANTS = {"bf16": (LIB_PATH, []), "f16": (LIB_PATH_F16, ["-DSRGPT_ELEM_F16"])}
 
 SOURCES = ["capi.cu", "gemm_tcgen05.cu", "gemv.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "region.cu", "sampling.cu", "tp_comm.cu", "preprocess.cu", "layers.cu"]
 NVCC_FLAGS = [
@@ -38,10 +42,13 @@ def _deps():
 
 
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > t for f in _deps() if os.path.exists(f))
+    for path, _ in VARIANTS.values():
+        if not os.path.exists(path):
+            return True
+        t = os.path.getmtime(path)
+        if any(os.path.getmtime(f) > t for f in _deps() if os.path.exists(f)):
+            return True
+    return False
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
@@ -65,25 +72,28 @@ def build(force: bool = False, verbose: bool = True) -> str:
 def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
 
-    def compile_one(src):
-        obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(job):
+        variant, src = job
+        obj = os.path.join(BUILD_DIR, f"{variant}_" + src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *VARIANTS[variant][1], "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"nvcc failed for {src} ({variant}):\n{r.stdout}\n{r.stderr}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
-    cmd = [nvcc, "-shared", "--cudart", "shared", "-o", tmp, *objs,
-           "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB_PATH)
-    if verbose:
-        print(f"[srgpt_b200] built {LIB_PATH}", file=sys.stderr)
+    jobs = [(v, s) for v in VARIANTS for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_one, jobs))
+    for vi, (variant, (path, _)) in enumerate(VARIANTS.items()):
+        tmp = f"{path}.{os.getpid()}.tmp"
+        cmd = [nvcc, "-shared", "--cudart", "shared", "-o", tmp, *objs[vi * len(SOURCES):(vi + 1) * len(SOURCES)],
+               "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed ({variant}):\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, path)
+        if verbose:
+            print(f"[srgpt_b200] built {path}", file=sys.stderr)
     return LIB_PATH
 
 

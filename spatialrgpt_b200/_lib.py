@@ -13,7 +13,8 @@ import threading
 from . import _build
 
 _lock = threading.Lock()
-_lib = None
+_libs = {}       # element type ("bf16" / "f16") -> typed CDLL
+_elem = "bf16"   # element type whose library load() returns; switched by ops.elem_dtype() around a model's calls
 
 
 class SrgptError(RuntimeError):
@@ -25,6 +26,7 @@ vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 # name -> (restype, argtypes); mirrors include/srgpt_b200.h one to one
 SIGNATURES = {
     "srgpt_abi_version": (ci, []),
+    "srgpt_elem_type": (ci, []),
     "srgpt_last_error": (C.c_char_p, []),
     "srgpt_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
     "srgpt_trace_begin": (ci, [vp, ci]),
@@ -84,23 +86,37 @@ class LlamaLayerWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("in_norm", "qkv_w", "o_w", "post_norm", "gateup_w", "down_w", "kv_pages")]
 
 
-def lib_path() -> str:
-    return _build.LIB_PATH
+def lib_path(elem: str = "bf16") -> str:
+    return _build.VARIANTS[elem][0]
 
 
-def load(build_if_missing: bool = True):
-    """Load (building first if the .so is missing/stale and nvcc is present) and type the library."""
-    global _lib
+def current_elem() -> str:
+    return _elem
+
+
+def set_elem(elem: str) -> str:
+    """Selects which build of the library (bf16 or f16 elements) ``load()`` hands out; returns the previous setting."""
+    global _elem
+    if elem not in _build.VARIANTS:
+        raise SrgptError(f"unsupported element type {elem!r} (have {sorted(_build.VARIANTS)})")
+    prev, _elem = _elem, elem
+    return prev
+
+
+def load(build_if_missing: bool = True, elem: str = None):
+    """Load (building first if the .so is missing/stale and nvcc is present) and type the library of the given (default: the
+    current) element type."""
+    elem = elem or _elem
     with _lock:
-        if _lib is not None:
-            return _lib
-        path = _build.LIB_PATH
+        if elem in _libs:
+            return _libs[elem]
+        path = lib_path(elem)
         if build_if_missing and _build.is_stale():
             try:
                 _build.build(verbose=False)
             except Exception as e:  # stale-but-present is still loadable; missing is fatal
                 if not os.path.exists(path):
-                    raise SrgptError(f"libsrgpt_b200.so is missing and could not be built: {e}") from e
+                    raise SrgptError(f"{os.path.basename(path)} is missing and could not be built: {e}") from e
         if not os.path.exists(path):
             raise SrgptError(f"{path} not found; run `python -c 'import __graft_entry__ as g; g.build()'`")
         try:
@@ -116,8 +132,10 @@ def load(build_if_missing: bool = True):
             fn.restype = res
             fn.argtypes = args
         if lib.srgpt_abi_version() != 1:
-            raise SrgptError("ABI version mismatch between _lib.py and libsrgpt_b200.so")
-        _lib = lib
+            raise SrgptError(f"ABI version mismatch between _lib.py and {os.path.basename(path)}")
+        if lib.srgpt_elem_type() != {"bf16": 0, "f16": 1}[elem]:
+            raise SrgptError(f"{path} was not built for {elem} elements")
+        _libs[elem] = lib
         return lib
 
 

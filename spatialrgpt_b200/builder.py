@@ -113,7 +113,7 @@ def read_checkpoint(model_path: str, load_tokenizer: bool = True):
         mm_use_im_start_end=bool(top.get("mm_use_im_start_end", False)),
         mm_use_im_patch_token=bool(top.get("mm_use_im_patch_token", True)),  # loader default True (builder.py:194)
         enable_region=enable_region, enable_depth=bool(top.get("enable_depth", False)),
-        model_dtype=top.get("model_dtype", "torch.bfloat16"),
+        model_dtype=top.get("model_dtype", "torch.float16"),  # llava_arch.py:74 default
         vision=_vision_config(vt_cfg), llama=_llama_dims(llm_cfg),
         mm_projector_type=mp_cfg.get("mm_projector_type", "mlp_downsample"),
         region_extractor_type=re_cfg.get("region_extractor_type", "regiongpt"))
@@ -181,7 +181,11 @@ def _resize_token_embeddings(cfg: LlavaConfig, llm_sd: Dict[str, torch.Tensor], 
 
 def load_pretrained_model(model_path: str, model_name: str, model_base: Optional[str] = None, load_8bit: bool = False,
                           load_4bit: bool = False, device_map: str = "auto", device: str = "cuda", **kwargs):
-    """Reference signature (builder.py:36-45) -> (tokenizer, model, image_processor, context_len)."""
+    """Reference signature (builder.py:36-45) -> (tokenizer, model, image_processor, context_len).
+
+    The model comes back in fp16 like the reference's (builder.py:62 sets torch_dtype = float16 unconditionally); callers that want
+    bf16 cast afterwards exactly as the reference's do (``model.to(dtype=torch.bfloat16)``, eval_spatial.py:221).  ``torch_dtype=``
+    (torch.float16 / torch.bfloat16) is an extension that loads straight into that dtype."""
     if load_8bit or load_4bit:
         raise NotImplementedError("bitsandbytes quantised loading is outside the hot path (builder.py:51-60)")
     if model_base is not None:
@@ -194,7 +198,10 @@ def load_pretrained_model(model_path: str, model_name: str, model_base: Optional
     cfg, sd, tokenizer, image_processor = read_checkpoint(model_path)
     dev = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
     max_seq = int(kwargs.pop("max_seq_len", min(cfg.llama.max_position_embeddings, 4096)))
-    model = LlavaLlamaModel(cfg, from_state_dicts(cfg, sd, dev), tokenizer=tokenizer, image_processor=image_processor,
+    dtype = kwargs.pop("torch_dtype", None) or torch.float16
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise NotImplementedError(f"torch_dtype {dtype}: the sm_100a kernels compute in torch.float16 or torch.bfloat16")
+    model = LlavaLlamaModel(cfg, from_state_dicts(cfg, sd, dev, dtype=dtype), tokenizer=tokenizer, image_processor=image_processor,
                             max_seq_len=max_seq)
     context_len = getattr(cfg.llama, "max_sequence_length", 2048) if hasattr(cfg.llama, "max_sequence_length") else 2048
     return tokenizer, model, image_processor, context_len

@@ -50,11 +50,11 @@ class RegionChat:
         prompt = self.conv.get_prompt()
         region_indices = [int(i) for turn in self.user_turns for i in re.findall(r"<region(\d+)>", turn)]
         model, dev = self.model, self.model.device
-        images = process_images([image], self.image_processor, model.config).to(dev, dtype=torch.bfloat16)
-        depths = process_images([depth_image], self.image_processor, model.config).to(dev, dtype=torch.bfloat16) if use_depth else None
+        images = process_images([image], self.image_processor, model.config).to(dev, dtype=model.dtype)
+        depths = process_images([depth_image], self.image_processor, model.config).to(dev, dtype=model.dtype) if use_depth else None
         masks: Optional[torch.Tensor] = None
         if len(seg_masks) > 0:
-            masks = process_regions(list(seg_masks), self.image_processor, model.config)[region_indices].to(dev, dtype=torch.bfloat16)
+            masks = process_regions(list(seg_masks), self.image_processor, model.config)[region_indices].to(dev, dtype=model.dtype)
         input_ids = tokenizer_image_token(prompt, self.tokenizer, IMAGE_TOKEN_INDEX, return_tensors="pt").unsqueeze(0).to(dev)
         stop = stop_string(self.conv_mode)
         out = model.generate(input_ids, images=[images], depths=None if depths is None else [depths], masks=[masks],

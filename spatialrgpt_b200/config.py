@@ -76,7 +76,7 @@ class LlavaConfig:
     s2_max_split_size: Optional[int] = None
     enable_region: bool = True
     enable_depth: bool = True
-    model_dtype: str = "torch.bfloat16"
+    model_dtype: str = "torch.float16"  # llava_arch.py:74; overwritten with the dtype the weights were loaded / cast to
     # ours (not in the reference): resolved sub-configs and special-token ids
     vision: VisionConfig = field(default_factory=VisionConfig)
     llama: LlamaDims = field(default_factory=LlamaDims)

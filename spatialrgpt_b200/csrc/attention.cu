@@ -36,7 +36,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
 }
 __device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." SRGPT_ELEM_PTX "." SRGPT_ELEM_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -437,7 +437,7 @@ attn_decode_kernel(const bf16* __restrict__ q, bf16* __restrict__ out, const bf1
       lt += s_l[i] * w;
       at += s_acc[i][threadIdx.x] * w;
     }
-    out[head * HD + threadIdx.x] = __float2bfloat16_rn(at / lt);
+    out[head * HD + threadIdx.x] = f2e(at / lt);
   }
   trace_mark(trace, 2);
 }
@@ -532,7 +532,7 @@ attn_decode_gqa_kernel(const bf16* __restrict__ q, int q_ld, bf16* __restrict__ 
         lt += s_l[i] * w;
         at += s_acc[i][threadIdx.x] * w;
       }
-      out[(size_t)b * o_ld + (kvh * GROUP + g) * HD + threadIdx.x] = __float2bfloat16_rn(at / lt);
+      out[(size_t)b * o_ld + (kvh * GROUP + g) * HD + threadIdx.x] = f2e(at / lt);
     }
   }
 }

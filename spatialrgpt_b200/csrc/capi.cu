@@ -68,6 +68,14 @@ extern "C" __attribute__((visibility("default"))) int srgpt_trace_end(void) {
 
 extern "C" __attribute__((visibility("default"))) int srgpt_abi_version(void) { return SRGPT_ABI_VERSION; }
 
+extern "C" __attribute__((visibility("default"))) int srgpt_elem_type(void) {
+#ifdef SRGPT_ELEM_F16
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 extern "C" __attribute__((visibility("default"))) const char* srgpt_last_error(void) { return g_last_error; }
 
 extern "C" __attribute__((visibility("default"))) int srgpt_device_info(int* sm_count_out, int* cc_major, int* cc_minor) {

@@ -1,6 +1,7 @@
 // Shared device/host helpers for the sm_100a kernels behind the srgpt C-ABI (include/srgpt_b200.h).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -48,17 +49,41 @@ bool pdl_enabled();                      // false when SRGPT_NO_PDL=1 (debug kno
 bool env_flag(const char* name);
 
 // ---- device helpers
+// The 16-bit element type of this build.  The library is compiled twice from the same sources: libsrgpt_b200.so computes in bfloat16
+// (the reference's eval default, llava/eval/eval_spatial.py:206-212) and libsrgpt_b200_f16.so (-DSRGPT_ELEM_F16) in IEEE half (the
+// loader default, llava/model/builder.py:62; llava/eval/eval_region_cls.py:316-317).  Every rounding point is the same in both - the
+// fp32 accumulators are rounded to the element type exactly where torch would materialise a tensor - so the kernels are written once
+// against the alias `bf16` and these helpers; only the conversions, the mma.sync / tcgen05 operand formats and the tensor-map data
+// type differ.  srgpt_elem_type() reports which build a loaded library is.
+#ifdef SRGPT_ELEM_F16
+typedef __half bf16;
+#define SRGPT_ELEM_PTX "f16"
+#define SRGPT_UMMA_FMT 0u  // tcgen05 kind::f16 operand format: 0 = f16, 1 = bf16
+#define SRGPT_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+__device__ __forceinline__ float e2f(bf16 x) { return __half2float(x); }
+__device__ __forceinline__ bf16 f2e(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+#else
 typedef __nv_bfloat16 bf16;
-
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
+#define SRGPT_ELEM_PTX "bf16"
+#define SRGPT_UMMA_FMT 1u
+#define SRGPT_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+__device__ __forceinline__ float e2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2e(float x) { return __float2bfloat16_rn(x); }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+#endif
+
+__device__ __forceinline__ float bf16_round(float x) { return e2f(f2e(x)); }
 
 // 8 bf16 (one 16-byte vector) -> 8 floats
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {

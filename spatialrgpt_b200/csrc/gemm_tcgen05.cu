@@ -118,7 +118,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
 __device__ __forceinline__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (SRGPT_UMMA_FMT << 7) | (SRGPT_UMMA_FMT << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct Params {
@@ -170,7 +170,7 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
         for (int t = 0; t < 8; ++t) v[j + t] += f[t];
       } else {
         for (int t = 0; t < 8; ++t)
-          if (col0 + j + t < p.N) v[j + t] += __bfloat162float(p.bias[col0 + j + t]);
+          if (col0 + j + t < p.N) v[j + t] += e2f(p.bias[col0 + j + t]);
       }
     }
   }
@@ -204,7 +204,7 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
           for (int t = 0; t < 8; ++t) v[j + t] = bf16_round(v[j + t]) + f[t];
         } else {
           for (int t = 0; t < 8; ++t)
-            if (col0 + j + t < p.N) v[j + t] = bf16_round(v[j + t]) + __bfloat162float(rp[j + t]);
+            if (col0 + j + t < p.N) v[j + t] = bf16_round(v[j + t]) + e2f(rp[j + t]);
         }
       }
     }
@@ -232,7 +232,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
       *reinterpret_cast<uint4*>(cp + 8) = pack8(o + 8);
     } else {
       for (int j = 0; j < 16; ++j)
-        if ((col0 >> 1) + j < ncols_out) cp[j] = __float2bfloat16_rn(o[j]);
+        if ((col0 >> 1) + j < ncols_out) cp[j] = f2e(o[j]);
     }
   } else {
     apply_epilogue<EPI>(v, p, row, col0, pre_res);
@@ -252,7 +252,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t* r, const Params& p, 
         for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(v + j);
       } else {
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+          if (col0 + j < p.N) cp[j] = f2e(v[j]);
       }
     }
   }
@@ -1157,7 +1157,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int k, int ld, 
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(tm, SRGPT_TMAP_DTYPE, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1178,7 +1178,7 @@ static int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, i
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(tm, SRGPT_TMAP_DTYPE, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled (output) failed: CUresult %d (rows=%d cols=%d ld=%d ptr=%p)", (int)r, rows, cols, ld, ptr);

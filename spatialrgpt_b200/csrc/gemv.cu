@@ -297,37 +297,37 @@ __global__ void __launch_bounds__(THREADS, PRE == 1 ? 3 : (PRE == 2 ? 2 : 1)) de
     } else if (MODE == SRGPT_GEMV_PLAIN) {
       float y0 = bf16_round(a0), y1 = bf16_round(a1);
       if (p.residual != nullptr) {
-        y0 += __bfloat162float(p.residual[r0]);
-        y1 += __bfloat162float(p.residual[r1]);
+        y0 += e2f(p.residual[r0]);
+        y1 += e2f(p.residual[r1]);
       }
       *reinterpret_cast<uint32_t*>(p.y + r0) = pack_bf16x2(y0, y1);
     } else if (MODE == SRGPT_GEMV_SWIGLU) {
       const float g = bf16_round(a0), u = bf16_round(a1);
-      p.y[pi] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
+      p.y[pi] = f2e(bf16_round(silu(g)) * u);
     } else if (MODE == SRGPT_GEMV_QKV_ROPE) {
       const int half = p.hd >> 1;
       const int head = pi / half, j = pi - head * half;
       float v0 = bf16_round(a0), v1 = bf16_round(a1);
       const int pos = *p.pos;
       if (head < p.n_heads + p.n_kv_heads) {
-        const float cs = __bfloat162float(p.cos_tab[(size_t)pos * half + j]);
-        const float sn = __bfloat162float(p.sin_tab[(size_t)pos * half + j]);
+        const float cs = e2f(p.cos_tab[(size_t)pos * half + j]);
+        const float sn = e2f(p.sin_tab[(size_t)pos * half + j]);
         const float o0 = bf16_round(bf16_round(v0 * cs) + bf16_round(-v1 * sn));
         const float o1 = bf16_round(bf16_round(v1 * cs) + bf16_round(v0 * sn));
         v0 = o0;
         v1 = o1;
       }
       if (head < p.n_heads) {
-        p.y[r0] = __float2bfloat16_rn(v0);
-        p.y[r1] = __float2bfloat16_rn(v1);
+        p.y[r0] = f2e(v0);
+        p.y[r1] = f2e(v1);
       } else {
         const int page = p.page_table[pos / p.page_size], slot = pos % p.page_size;
         const bool is_v = head >= p.n_heads + p.n_kv_heads;
         const int kh = head - p.n_heads - (is_v ? p.n_kv_heads : 0) + p.kv_head_off;
         const int kv_row = (p.kv_heads_total > 0 ? p.kv_heads_total : p.n_kv_heads) * p.hd;
         bf16* dst = p.kv_pages + (((size_t)page * 2 + (is_v ? 1 : 0)) * p.page_size + slot) * kv_row + kh * p.hd;
-        dst[j] = __float2bfloat16_rn(v0);
-        dst[j + half] = __float2bfloat16_rn(v1);
+        dst[j] = f2e(v0);
+        dst[j + half] = f2e(v1);
       }
     } else {  // MODE_LM: logits = lm_head(h).float() -> bf16 rounding first (modeling_llama.py:1044-1045)
       a0 = bf16_round(a0);
@@ -457,7 +457,7 @@ tp_pick_token_kernel(const int* __restrict__ best_all, int world, const bf16* __
 // h = bf16(bf16(sum of the ranks' partial dot products) + h): the rounding points of `residual + o_proj(x)` (modeling_llama.py:668,682)
 __global__ void __launch_bounds__(256) tp_residual_add_kernel(bf16* __restrict__ h, const float* __restrict__ partial, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) h[i] = __float2bfloat16_rn(bf16_round(partial[i]) + __bfloat162float(h[i]));
+  if (i < n) h[i] = f2e(bf16_round(partial[i]) + e2f(h[i]));
 }
 
 // ---- host side ------------------------------------------------------------------------------------

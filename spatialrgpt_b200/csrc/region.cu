@@ -74,9 +74,9 @@ mask_taps_kernel(const T* __restrict__ masks, bf16* __restrict__ w, float* __res
   float sum = 0.f;
   for (int l = split * per + threadIdx.x; l < l_end; l += blockDim.x) {
     const int oy = l / side, ox = l - oy * side;
-    const bf16 v = __float2bfloat16_rn(bilinear_tap(src, IH, IW, rscale, rscale, oy, ox));
+    const bf16 v = f2e(bilinear_tap(src, IH, IW, rscale, rscale, oy, ox));
     dst[feat_row(oy, ox, side, order)] = v;
-    sum += __bfloat162float(v);
+    sum += e2f(v);
   }
   const float total = block_sum(sum, red);
   if (threadIdx.x == 0) psum[((size_t)img * M + m) * MW_SPLITS + split] = total;
@@ -98,7 +98,7 @@ mask_normalise_kernel(const bf16* __restrict__ v, bf16* __restrict__ w, const fl
   const int l_end = min(L, (split + 1) * per);
   // rows are a permutation of l; normalising the contiguous range [split*per, l_end) of ROWS covers every row once
   for (int r = split * per + threadIdx.x; r < l_end; r += blockDim.x)
-    dst[r] = __float2bfloat16_rn(__fdiv_rn(__bfloat162float(src[r]), denorm));
+    dst[r] = f2e(__fdiv_rn(e2f(src[r]), denorm));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -204,7 +204,7 @@ mask_pool_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                      : "r"(tx + (c0 >> 6) * MP_X_BOX + bl * 128 + ((((c0 & 63) >> 3) ^ (bl & 7)) << 4)));
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
-          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." SRGPT_ELEM_PTX "." SRGPT_ELEM_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                        : "+f"(acc[nb][0]), "+f"(acc[nb][1]), "+f"(acc[nb][2]), "+f"(acc[nb][3])
                        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[2 * nb]), "r"(b[2 * nb + 1]));
       }
@@ -242,7 +242,7 @@ mask_pool_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ ou
     for (int k = 0; k < 8; ++k) s += v[k];
   }
   for (; r < R; ++r) s += p[(size_t)r * stride];
-  out[((size_t)img * M + m) * C + c] = __float2bfloat16_rn(s);
+  out[((size_t)img * M + m) * C + c] = f2e(s);
 }
 
 static void mask_pool_plan(int n_img, int L, int C, int* R, int* rows_per_cta, int* Q) {

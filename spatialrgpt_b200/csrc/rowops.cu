@@ -197,7 +197,7 @@ __global__ void patchify_kernel(const SrcT* __restrict__ img, bf16* __restrict__
       const int ky = r / ps, kx = r % ps;
       val = (float)img[(((size_t)n * 3 + c) * R + (py * ps + ky)) * R + (px * ps + kx)];
     }
-    A[(size_t)row * ldk + col] = __float2bfloat16_rn(val);
+    A[(size_t)row * ldk + col] = f2e(val);
   }
 }
 
@@ -218,7 +218,7 @@ __global__ void splice_kernel(const bf16* s0, const bf16* s1, const bf16* s2, co
 // argmax over fp32 rows, first index on ties
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float argmax_load(const float* p) { return *p; }
-__device__ __forceinline__ float argmax_load(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float argmax_load(const bf16* p) { return e2f(*p); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_kernel(const T* __restrict__ x, int ldx, int cols, long long* __restrict__ out) {

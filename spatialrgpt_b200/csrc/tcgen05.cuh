@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace srgpt {
 namespace tc {
 
@@ -111,9 +113,9 @@ constexpr uint64_t UMMA_DESC_SW128 = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4
 constexpr uint64_t UMMA_DESC_SW32 = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 __device__ __forceinline__ uint64_t umma_desc(uint64_t flavour, uint32_t smem_addr) { return flavour | (uint64_t)((smem_addr & 0x3FFFF) >> 4); }
 
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, M x N tile; *_mn = 1 selects an MN-major operand
+// kind::f16 instruction descriptor: D = f32, A = B = the build's element type (bf16 / f16), M x N tile; *_mn = 1 selects an MN-major operand
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn = 0, int b_mn = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (SRGPT_UMMA_FMT << 7) | (SRGPT_UMMA_FMT << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -141,7 +143,7 @@ inline int encode_tmap_bf16(CUtensorMap* tm, const void* ptr, int ndim, const cu
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return -1;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)ndim, const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(tm, SRGPT_TMAP_DTYPE, (cuuint32_t)ndim, const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }

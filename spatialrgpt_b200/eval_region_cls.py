@@ -161,9 +161,9 @@ def eval_model(args, loader=None, seed: Optional[int] = None) -> int:
         for line in data:
             input_ids, images, masks = build_sample(line, tokenizer, image_processor, model.config, args.conv_mode, args.dataset, args.prompt_type,
                                                     args.image_folder, rng)
-            # the reference feeds fp16 here (316-317); this path computes in bf16 (DESIGN.md "fp16")
-            output_ids = model.generate(input_ids.unsqueeze(0).to(dev), images=images.to(dev, dtype=torch.bfloat16),
-                                        masks=[masks.to(dev, dtype=torch.bfloat16)], do_sample=args.temperature > 0, temperature=args.temperature,
+            # fp16 end to end, as the reference runs this script (builder.py:62 load, inputs cast at 316-317)
+            output_ids = model.generate(input_ids.unsqueeze(0).to(dev), images=images.to(dev, dtype=model.dtype),
+                                        masks=[masks.to(dev, dtype=model.dtype)], do_sample=args.temperature > 0, temperature=args.temperature,
                                         top_p=args.top_p, num_beams=args.num_beams, max_new_tokens=64, use_cache=True,
                                         pad_token_id=getattr(tokenizer, "pad_token_id", None))
             text = clean_output(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0], stop)

@@ -221,8 +221,8 @@ def answer_questions(line: Dict[str, Any], model, tokenizer, image_processor, im
                      num_beams: int = 1) -> List[Dict[str, Any]]:
     """All question turns of one annotation (the conversation accumulates, as in the reference) -> JSONL records."""
     dev = model.device
-    images_tensor = process_images([image], image_processor, model.config).to(dev, dtype=torch.bfloat16)
-    depths_tensor = None if depth is None else process_images([depth], image_processor, model.config).to(dev, dtype=torch.bfloat16)
+    images_tensor = process_images([image], image_processor, model.config).to(dev, dtype=model.dtype)
+    depths_tensor = None if depth is None else process_images([depth], image_processor, model.config).to(dev, dtype=model.dtype)
     conv = conv_templates[conv_mode].copy()
     stop = stop_string(conv_mode)
     conversations = line["conversations"]
@@ -235,7 +235,7 @@ def answer_questions(line: Dict[str, Any], model, tokenizer, image_processor, im
         conv.append_message(conv.roles[1], None)
         input_ids = tokenizer_image_token(conv.get_prompt(), tokenizer, IMAGE_TOKEN_INDEX, return_tensors="pt").unsqueeze(0).to(dev)
         output_ids = model.generate(input_ids, images=images_tensor, depths=depths_tensor,
-                                    masks=None if masks is None else [masks.to(dev, dtype=torch.bfloat16)],
+                                    masks=None if masks is None else [masks.to(dev, dtype=model.dtype)],
                                     do_sample=temperature > 0, temperature=temperature, top_p=top_p, num_beams=num_beams,
                                     max_new_tokens=max_new_tokens, use_cache=True)
         pred = clean_output(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0], stop)
@@ -253,6 +253,7 @@ def eval_model(args, depth_predictor: Optional[Callable[[np.ndarray], torch.Tens
     model_path = os.path.expanduser(args.model_path)
     model_name = get_model_name_from_path(model_path)
     tokenizer, model, image_processor, _ = loader(model_path, model_name, getattr(args, "model_base", None))
+    model.to(dtype=torch.bfloat16)  # eval_spatial.py:221: the loader returns fp16, this script computes in bf16
     if depth_predictor is None:
         depth_predictor = get_depth_predictor(getattr(args, "depth_predictor", None))
     if depth_predictor is None and getattr(model.config, "enable_depth", False):

@@ -22,26 +22,26 @@ from .weights import LlamaW
 PAGE_SIZE = 16
 
 
-def build_rope_tables(dims: LlamaDims, max_pos: int, device) -> (torch.Tensor, torch.Tensor):
+def build_rope_tables(dims: LlamaDims, max_pos: int, device, dtype: torch.dtype = torch.bfloat16) -> (torch.Tensor, torch.Tensor):
     """cos/sin exactly as LlamaRotaryEmbedding.forward computes them (modeling_llama.py:86,117-130):
-    fp32 inv_freq, fp32 outer product, cos/sin in fp32, cast to bf16.  Host-side table build (once)."""
+    fp32 inv_freq, fp32 outer product, cos/sin in fp32, cast to the model dtype.  Host-side table build (once)."""
     hd = dims.head_dim
     inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
     t = torch.arange(max_pos, dtype=torch.int64).float()
     freqs = t[:, None] * inv_freq[None, :]
-    return freqs.cos().to(torch.bfloat16).to(device).contiguous(), freqs.sin().to(torch.bfloat16).to(device).contiguous()
+    return freqs.cos().to(dtype).to(device).contiguous(), freqs.sin().to(dtype).to(device).contiguous()
 
 
 class PagedKVCache:
     """KV pages for all layers: [layers, n_pages, 2 (k,v), PAGE_SIZE, n_kv_heads, head_dim] bf16, a free list
     and per-sequence page tables (int32, device) of fixed capacity so decode graphs stay valid."""
 
-    def __init__(self, dims: LlamaDims, n_pages: int, max_seqs: int, max_pages_per_seq: int, device):
+    def __init__(self, dims: LlamaDims, n_pages: int, max_seqs: int, max_pages_per_seq: int, device, dtype: torch.dtype = torch.bfloat16):
         self.dims = dims
         self.n_pages = n_pages
         self.max_pages_per_seq = max_pages_per_seq
         self.pages = torch.zeros((dims.num_hidden_layers, n_pages, 2, PAGE_SIZE, dims.num_key_value_heads, dims.head_dim),
-                                 dtype=torch.bfloat16, device=device)
+                                 dtype=dtype, device=device)
         # +1 spare column (a measured-and-dropped decode-attention variant read the page id of row pos+1; kept so tables stay 16-byte padded)
         self.page_tables = torch.zeros((max_seqs, max_pages_per_seq + 1), dtype=torch.int32, device=device)
         self.free: List[int] = list(range(n_pages - 1, -1, -1))
@@ -94,9 +94,10 @@ class LlamaDecoder:
         dev = w.embed.device
         self.device = dev
         self.max_seq_len = max_seq_len
-        self.cos, self.sin = build_rope_tables(dims, max_seq_len, dev)
+        self.dtype = w.embed.dtype  # torch.bfloat16 or torch.float16: selects the build of the kernels (ops.elem_dtype)
+        self.cos, self.sin = build_rope_tables(dims, max_seq_len, dev, self.dtype)
         ppseq = (max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE
-        self.cache = PagedKVCache(dims, kv_pages if kv_pages is not None else ppseq * max_seqs, max_seqs, ppseq, dev)
+        self.cache = PagedKVCache(dims, kv_pages if kv_pages is not None else ppseq * max_seqs, max_seqs, ppseq, dev, self.dtype)
         # the decode graph reads the page table of the sequence being decoded from this fixed buffer
         self.active_pt = torch.zeros(ppseq + 1, dtype=torch.int32, device=dev)
         H, nh, hd, I = dims.hidden_size, dims.num_attention_heads, dims.head_dim, dims.intermediate_size
@@ -104,10 +105,10 @@ class LlamaDecoder:
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)       # position of the token being processed
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)      # number of generated tokens so far
         self.out_ids = torch.zeros(max_new_tokens_cap, dtype=torch.int64, device=dev)
-        self.h = torch.zeros(H, dtype=torch.bfloat16, device=dev)      # residual stream of the current token
-        self.q_buf = torch.zeros(nh * hd, dtype=torch.bfloat16, device=dev)
-        self.attn_buf = torch.zeros(nh * hd, dtype=torch.bfloat16, device=dev)
-        self.act_buf = torch.zeros(I, dtype=torch.bfloat16, device=dev)
+        self.h = torch.zeros(H, dtype=self.dtype, device=dev)      # residual stream of the current token
+        self.q_buf = torch.zeros(nh * hd, dtype=self.dtype, device=dev)
+        self.attn_buf = torch.zeros(nh * hd, dtype=self.dtype, device=dev)
+        self.act_buf = torch.zeros(I, dtype=self.dtype, device=dev)
         self.lm_ws = ops.lm_head_workspace(dims.vocab_size, dev)
         self.scale = hd ** -0.5
         self._layer_array = ops.make_llama_layer_array(w.layers, [self.cache.layer(l) for l in range(dims.num_hidden_layers)])
@@ -120,6 +121,7 @@ class LlamaDecoder:
         self.sample_seed = 0
 
     # ---------------------------------------------------------------------------------------------
+    @ops.in_own_dtype
     def ensure_capacity(self, n_seqs: int, tokens_per_seq: int) -> None:
         """Grow the paged cache so `n_seqs` sequences of `tokens_per_seq` tokens fit at once (batched prefill).
         Re-allocation drops all cached sequences and the captured decode graph (page addresses change)."""
@@ -138,9 +140,10 @@ class LlamaDecoder:
         n_pages_old, n_seqs_old = c.n_pages, len(c.owned)
         self.cache = None
         del c
-        self.cache = PagedKVCache(d, max(need_pages, n_pages_old), max(n_seqs, n_seqs_old), (self.max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE, self.device)
+        self.cache = PagedKVCache(d, max(need_pages, n_pages_old), max(n_seqs, n_seqs_old), (self.max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE, self.device, self.dtype)
         self._layer_array = ops.make_llama_layer_array(self.w.layers, [self.cache.layer(l) for l in range(d.num_hidden_layers)])
 
+    @ops.in_own_dtype
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         """Embedding gather through the splice kernel (source 0 only)."""
         flat = ids.reshape(-1).to(device=self.device, dtype=torch.int32)
@@ -150,6 +153,7 @@ class LlamaDecoder:
                 raise IndexError(f"token id {lo if lo < 0 else hi} is outside the token table [0, {self.w.embed.shape[0]})")
         return ops.splice_rows(self.w.embed, None, None, None, torch.zeros_like(flat), flat)
 
+    @ops.in_own_dtype
     def prefill_hidden(self, inputs_embeds: torch.Tensor, seq: int = 0, start_pos: int = 0) -> torch.Tensor:
         """Run all layers over one sequence's prompt rows [S, H]; fills the KV cache; returns the
         final-layer residual stream [S, H] (before the final norm)."""
@@ -160,11 +164,12 @@ class LlamaDecoder:
         self.cache.reserve(seq, start_pos + S)
         sp = torch.tensor([start_pos], dtype=torch.int32, device=self.device)
         pt = self.cache.page_tables[seq]
-        x = inputs_embeds.to(torch.bfloat16).contiguous().clone()
+        x = inputs_embeds.to(self.dtype).contiguous().clone()
         if start_pos != 0:
             raise NotImplementedError("chunked prefill (prompt attention over cached pages) is a next-round item")
         return ops.llama_prefill_layers(x, self._layer_array, d.num_hidden_layers, d, self.cos, self.sin, sp, pt, PAGE_SIZE)
 
+    @ops.in_own_dtype
     def prefill_packed(self, packed_embeds: torch.Tensor, seq_lens: List[int]) -> torch.Tensor:
         """Prefill `len(seq_lens)` prompts packed back to back ([sum S_b, H]) into sequence slots 0..B-1 in ONE pass:
         every GEMM runs over all rows, attention / RoPE / KV append per sequence (the unpadded varlen path of
@@ -177,10 +182,11 @@ class LlamaDecoder:
             raise RuntimeError(f"prompt of {max(seq_lens)} tokens exceeds max_seq_len {self.max_seq_len}")
         cu = torch.tensor([0] + list(torch.tensor(seq_lens).cumsum(0).tolist()), dtype=torch.int32).to(self.device)
         sp = torch.zeros(B, dtype=torch.int32, device=self.device)
-        x = packed_embeds.to(torch.bfloat16).contiguous().clone()
+        x = packed_embeds.to(self.dtype).contiguous().clone()
         return ops.llama_prefill_layers(x, self._layer_array, d.num_hidden_layers, d, self.cos, self.sin, sp, self.cache.page_tables[:B],
                                         PAGE_SIZE, cu_seqlens=cu, max_seqlen=max(seq_lens))
 
+    @ops.in_own_dtype
     def first_tokens(self, hidden_packed: torch.Tensor, seq_lens: List[int], return_logits: bool = False):
         """Greedy first token of every packed sequence: final norm + lm_head over the B last rows as one GEMM
         (bf16 logits, modeling_llama.py:1044-1045), argmax with the lowest index on ties."""
@@ -194,8 +200,9 @@ class LlamaDecoder:
     def _logits_buffer(self, rows: int) -> torch.Tensor:
         """bf16 [rows, V] view with a 16-byte-aligned row stride (V = 128259 is odd; the GEMM stores 16-byte vectors)."""
         V = self.dims.vocab_size
-        return torch.empty((rows, (V + 7) // 8 * 8), dtype=torch.bfloat16, device=self.device)[:, :V]
+        return torch.empty((rows, (V + 7) // 8 * 8), dtype=self.dtype, device=self.device)[:, :V]
 
+    @ops.in_own_dtype
     def logits_all(self, hidden: torch.Tensor) -> torch.Tensor:
         """lm_head over every row -> fp32 logits [S, V] (LlamaForCausalLM.forward semantics, 1044-1045)."""
         hn = ops.rmsnorm(hidden, self.w.norm, self.dims.rms_norm_eps)
@@ -255,6 +262,7 @@ class LlamaDecoder:
         return True
 
     @torch.no_grad()
+    @ops.in_own_dtype
     def generate_from_embeds(self, inputs_embeds: torch.Tensor, max_new_tokens: int, eos_token_ids=None, stopping_fn=None,
                              use_graph: bool = True, return_logits: bool = False, seq: int = 0, sampling=None):
         """Greedy (or, with ``sampling=dict(temperature, top_p, seed)``, nucleus-sampled) decoding started from prompt
@@ -360,7 +368,7 @@ class LlamaDecoder:
             return st
         d, dev = self.dims, self.device
         H, nh, nkv, hd, I, V = d.hidden_size, d.num_attention_heads, d.num_key_value_heads, d.head_dim, d.intermediate_size, d.vocab_size
-        z = lambda *shape, dtype=torch.bfloat16: torch.zeros(shape, dtype=dtype, device=dev)  # noqa: E731
+        z = lambda *shape, dtype=self.dtype: torch.zeros(shape, dtype=dtype, device=dev)  # noqa: E731
         st = dict(B=B, cache=self.cache, graph=None, h=z(B, H), xn=z(B, H), qkv=z(B, (nh + 2 * nkv) * hd), attn=z(B, nh * hd), act=z(B, I),
                   logits=z(B, (V + 7) // 8 * 8), pos=z(B, dtype=torch.int32), step=z(1, dtype=torch.int32), ids=z(B, dtype=torch.int64),
                   out=z(self.out_ids.numel() * B, dtype=torch.int64), ticket=z(1, dtype=torch.int32),
@@ -460,6 +468,7 @@ class LlamaDecoder:
         return [res[b, : (stopped[b] if stopped[b] is not None else n)].clone() for b in range(B)]
 
     @torch.no_grad()
+    @ops.in_own_dtype
     def generate_batch(self, packed_embeds: torch.Tensor, seq_lens: List[int], max_new_tokens: int, eos_token_ids=None,
                        stopping_fn=None, use_graph: bool = True, return_logits: bool = False, sampling=None):
         """Decoding of B prompts: ONE packed prefill pass (tensor-core bound, all prompts share every GEMM), one lm_head GEMM for the

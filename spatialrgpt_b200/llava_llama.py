@@ -41,13 +41,27 @@ class LlavaLlamaModel:
         (tensor_parallel.py, BASELINE config c5); encoders and the prompt prefill stay replicated."""
         # fail loudly when the CUDA extension or a B200 is missing: there is no CPU path
         from . import _lib
-        _lib.load()
-        if not torch.cuda.is_available():
-            raise _lib.SrgptError("spatialrgpt_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
-        _lib.device_info()
         self.config = config
         self.weights = weights
+        if self.dtype not in (torch.bfloat16, torch.float16):
+            raise _lib.SrgptError(f"weights are {self.dtype}: the kernels compute in torch.bfloat16 or torch.float16")
+        with ops.elem_dtype(self.dtype):
+            _lib.load()
+            if not torch.cuda.is_available():
+                raise _lib.SrgptError("spatialrgpt_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+            _lib.device_info()
         self.tokenizer = tokenizer
+        self._image_processor = image_processor
+        self._max_seq_len = max_seq_len
+        self._tensor_parallel = tensor_parallel
+        self.training = False
+        config.model_dtype = str(self.dtype)
+        self._build_modules()
+
+    @ops.in_own_dtype
+    def _build_modules(self) -> None:
+        config, weights, image_processor, max_seq_len, tensor_parallel = (self.config, self.weights, self._image_processor, self._max_seq_len,
+                                                                          self._tensor_parallel)
         self.vision_tower = VisionTower(config, weights.vision, image_processor)
         self.mm_projector = MultimodalProjector(config, weights.projector)
         self.region_extractor = RegionExtractor(config, weights.region) if (config.enable_region and weights.region is not None) else None
@@ -57,7 +71,6 @@ class LlavaLlamaModel:
                                       group=tensor_parallel[2] if len(tensor_parallel) > 2 else None, max_seq_len=max_seq_len)
         else:
             self.llm = LlamaDecoder(config.llama, weights.llama, max_seq_len=max_seq_len)
-        self.training = False
 
     # ---- accessors (llava_arch.py:252-278) -----------------------------------------------------------
     def get_llm(self):
@@ -84,7 +97,9 @@ class LlavaLlamaModel:
 
     @property
     def dtype(self):
-        return torch.bfloat16
+        """torch.bfloat16 or torch.float16 - the dtype of the weights, which is also the compute dtype (the matching build of the
+        kernels is selected around every public call, ops.elem_dtype)."""
+        return self.weights.dtype
 
     def eval(self):
         return self
@@ -97,11 +112,18 @@ class LlavaLlamaModel:
         for x in a:
             if isinstance(x, torch.dtype):
                 dt = x
-        if dt is not None and dt not in (torch.bfloat16,):
-            raise NotImplementedError("the sm_100a path computes in bf16 (eval_spatial.py:221); fp16 is a next-round item")
+        if dt is not None and dt != self.dtype:
+            # nn.Module.to(dtype): cast the weights and rebuild what is derived from them (rope tables, KV cache, decode graphs).
+            # The reference's eval does exactly this after an fp16 load: model.to(dtype=torch.bfloat16) (eval_spatial.py:221).
+            if dt not in (torch.bfloat16, torch.float16):
+                raise NotImplementedError(f"the sm_100a path computes in torch.bfloat16 or torch.float16, not {dt}")
+            self.weights.to(dt)
+            self.config.model_dtype = str(dt)
+            self._build_modules()
         return self
 
     # ---- encoders ---------------------------------------------------------------------------------
+    @ops.in_own_dtype
     def encode_images(self, images: torch.Tensor) -> torch.Tensor:
         """llava_arch.py:307-310 (tower -> projector, no regions)."""
         return self.mm_projector(self.vision_tower(images))
@@ -174,6 +196,7 @@ class LlavaLlamaModel:
         return image_features, mask_embeds, depth_embeds
 
     # ---- embedding splice (llava_arch.py:333-650) -----------------------------------------------------
+    @ops.in_own_dtype
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
                                              masks=None, depths=None, _packed_only: bool = False):
         if images is None or (input_ids is not None and input_ids.shape[1] == 1):
@@ -231,7 +254,7 @@ class LlavaLlamaModel:
 
         max_len = max(x.shape[0] for x in new_embeds)
         left = getattr(cfg.llama, "tokenizer_padding_side", "right") == "left"
-        out = torch.zeros((B, max_len, H), dtype=torch.bfloat16, device=dev)
+        out = torch.zeros((B, max_len, H), dtype=self.dtype, device=dev)
         lab_out = torch.full((B, max_len), IGNORE_INDEX, dtype=torch.int64)
         am_out = torch.zeros((B, max_len), dtype=torch.bool)
         pos_out = torch.zeros((B, max_len), dtype=torch.int64)
@@ -250,6 +273,7 @@ class LlavaLlamaModel:
 
     # ---- forward: logits for every position (llava_llama.py:100-192) ----------------------------------
     @torch.no_grad()
+    @ops.in_own_dtype
     def forward(self, input_ids=None, images=None, masks=None, depths=None, attention_mask=None, position_ids=None,
                 past_key_values=None, seqlens_in_batch=None, inputs_embeds=None, labels=None, use_cache=None, **kwargs):
         if past_key_values is not None:
@@ -292,6 +316,7 @@ class LlavaLlamaModel:
 
     # ---- generate (llava_llama.py:194-213) --------------------------------------------------------------
     @torch.no_grad()
+    @ops.in_own_dtype
     def generate(self, input_ids: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
                  depths: Optional[torch.Tensor] = None, masks: Optional[List[torch.Tensor]] = None,
                  attention_mask: Optional[torch.Tensor] = None, **generation_kwargs):

@@ -63,15 +63,16 @@ class VisionTower:
     def num_patches(self):
         return self.vc.grid ** 2
 
+    @ops.in_own_dtype
     def forward(self, images: torch.Tensor) -> torch.Tensor:
-        """images [N, 3, R, R] (fp32 or bf16, on the device) -> [N, T, D] bf16."""
+        """images [N, 3, R, R] (fp32 or the model dtype, on the device) -> [N, T, D] in the model dtype."""
         if isinstance(images, (list, tuple)):  # vision_encoder.py:116-125
             return [self.forward(im.unsqueeze(0) if im.dim() == 3 else im) for im in images]
         vc, w = self.vc, self.w
         if images.dim() != 4 or images.shape[-1] != vc.image_size or images.shape[-2] != vc.image_size:
             raise ValueError(f"expected images [N, 3, {vc.image_size}, {vc.image_size}], got {tuple(images.shape)}")
         images = images.to(device=self.device)
-        if images.dtype not in (torch.float32, torch.bfloat16):
+        if images.dtype not in (torch.float32, self.dtype):
             images = images.float()
         images = images.contiguous()
         N, T, D, nh, hd = images.shape[0], vc.grid ** 2, vc.hidden_size, vc.num_attention_heads, vc.head_dim

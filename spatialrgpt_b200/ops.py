@@ -26,6 +26,46 @@ GEMV_PLAIN, GEMV_SWIGLU, GEMV_QKV_ROPE = range(3)
 ORDER_ROWMAJOR, ORDER_NESTED = 0, 2
 
 BF16 = torch.bfloat16
+F16 = torch.float16
+_ELEM_NAMES = {torch.bfloat16: "bf16", torch.float16: "f16"}
+_ELEM_DTYPES = {v: k for k, v in _ELEM_NAMES.items()}
+
+
+def ELEM() -> torch.dtype:
+    """The 16-bit element type the ops currently compute in (which build of the library ``_lib.load()`` hands out)."""
+    return _ELEM_DTYPES[_lib.current_elem()]
+
+
+class elem_dtype:
+    """``with ops.elem_dtype(torch.float16): ...`` - route the ops through the IEEE-half build of the kernels (the reference loader's
+    default dtype, llava/model/builder.py:62) instead of the bfloat16 one.  The models wrap their public entry points in this with their
+    own dtype, so a bf16 and an fp16 model can live in one process (one thread at a time: the setting is process-wide)."""
+
+    def __init__(self, dtype: torch.dtype):
+        if dtype not in _ELEM_NAMES:
+            raise SrgptError(f"unsupported compute dtype {dtype}: the kernels are built for torch.bfloat16 and torch.float16")
+        self.name = _ELEM_NAMES[dtype]
+
+    def __enter__(self):
+        self.prev = _lib.set_elem(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.set_elem(self.prev)
+        return False
+
+
+def in_own_dtype(fn):
+    """Method decorator: run the method with the kernels of ``self.dtype`` (torch.bfloat16 / torch.float16)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with elem_dtype(self.dtype):
+            return fn(self, *a, **k)
+
+    return wrapped
+
 
 # number of OUR kernels launched through this module (bench.py's `gpu_launches`); CUDA-graph replays
 # are added by the decoder (kernels_per_decode_step per replay)
@@ -55,19 +95,19 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> int:
 
 # workspace of the short-prompt GEMM configuration (include/srgpt_b200.h: srgpt_gemm_set_workspace): owned here, one per process,
 # registered on the first GEMM call on a device (the library keeps only the pointer)
-_GEMM_WS = None
+_GEMM_WS = {}  # element type -> buffer (each build of the library keeps its own registration)
 
 
 def _ensure_gemm_workspace(device) -> None:
-    global _GEMM_WS
-    if _GEMM_WS is not None:
+    elem = _lib.current_elem()
+    if elem in _GEMM_WS:
         return
     lib = _lib.load()
     n = int(lib.srgpt_gemm_workspace_bytes())
-    _GEMM_WS = torch.zeros(n + 1024, dtype=torch.uint8, device=device)
-    off = (-_GEMM_WS.data_ptr()) % 1024
+    ws = _GEMM_WS[elem] = torch.zeros(n + 1024, dtype=torch.uint8, device=device)
+    off = (-ws.data_ptr()) % 1024
     torch.cuda.synchronize(device)  # the zero fill is complete before any kernel polls the flags
-    check(lib.srgpt_gemm_set_workspace(_GEMM_WS.data_ptr() + off, n), "srgpt_gemm_set_workspace")
+    check(lib.srgpt_gemm_set_workspace(ws.data_ptr() + off, n), "srgpt_gemm_set_workspace")
     global LAUNCHES
     LAUNCHES -= 1
 
@@ -77,7 +117,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          epilogue: int = EPI_NONE, out: Optional[torch.Tensor] = None, out_fp32: bool = False,
          res_row_mod: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores."""
-    _need(a, BF16, "gemm.a"); _need(w, BF16, "gemm.w")
+    _need(a, ELEM(), "gemm.a"); _need(w, ELEM(), "gemm.w")
     _ensure_gemm_workspace(a.device)
     lda, ldw = _rowmajor2d(a, "gemm.a"), _rowmajor2d(w, "gemm.w")
     M, K = a.shape
@@ -86,18 +126,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         raise SrgptError(f"gemm: K mismatch {K} vs {K2}")
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
     if out is None:
-        out = torch.empty((M, n_out), dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+        out = torch.empty((M, n_out), dtype=torch.float32 if out_fp32 else ELEM(), device=a.device)
     else:
-        _need(out, torch.float32 if out_fp32 else BF16, "gemm.out")
+        _need(out, torch.float32 if out_fp32 else ELEM(), "gemm.out")
         if out.shape != (M, n_out):
             raise SrgptError(f"gemm.out: expected {(M, n_out)}, got {tuple(out.shape)}")
     ldc = _rowmajor2d(out, "gemm.out")
     ldr = 0
     if residual is not None:
-        _need(residual, BF16, "gemm.residual")
+        _need(residual, ELEM(), "gemm.residual")
         ldr = _rowmajor2d(residual, "gemm.residual")
     if bias is not None:
-        _need(bias, BF16, "gemm.bias")
+        _need(bias, ELEM(), "gemm.bias")
     check(_lib.load().srgpt_gemm_bf16(_p(a), lda, _p(w), ldw, _p(out), ldc, M, N, K, _p(bias), _p(residual), ldr,
                                       res_row_mod, epilogue, 1 if out_fp32 else 0, _stream()), "srgpt_gemm_bf16")
     return out
@@ -105,11 +145,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, act: int = 0,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need(x, BF16, "layernorm.x")
+    _need(x, ELEM(), "layernorm.x")
     ldx = _rowmajor2d(x, "layernorm.x")
     rows, cols = x.shape
     if out is None:
-        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+        out = torch.empty((rows, cols), dtype=ELEM(), device=x.device)
     check(_lib.load().srgpt_layernorm_bf16(_p(x), ldx, _p(weight), _p(bias), _p(out), _rowmajor2d(out, "layernorm.out"),
                                            rows, cols, eps, act, _stream()), "srgpt_layernorm_bf16")
     return out
@@ -117,7 +157,7 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
 
 def downsample_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
     """x [n, side*side, C] -> [n, ceil(side/2)^2, 4C] (DownSampleBlock + LayerNorm)."""
-    _need(x, BF16, "downsample_layernorm.x")
+    _need(x, ELEM(), "downsample_layernorm.x")
     if x.dim() != 3 or not x.is_contiguous():
         raise SrgptError("downsample_layernorm: expected contiguous [n, side*side, C]")
     n, hw, c = x.shape
@@ -125,18 +165,18 @@ def downsample_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tens
     if side * side != hw:
         raise SrgptError(f"downsample_layernorm: {hw} tokens is not a square grid")
     half = (side + 1) // 2
-    out = torch.empty((n, half * half, 4 * c), dtype=BF16, device=x.device)
+    out = torch.empty((n, half * half, 4 * c), dtype=ELEM(), device=x.device)
     check(_lib.load().srgpt_downsample_layernorm_bf16(_p(x), _p(weight), _p(bias), _p(out), n, side, c, eps, _stream()),
           "srgpt_downsample_layernorm_bf16")
     return out
 
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need(x, BF16, "rmsnorm.x")
+    _need(x, ELEM(), "rmsnorm.x")
     ldx = _rowmajor2d(x, "rmsnorm.x")
     rows, cols = x.shape
     if out is None:
-        out = torch.empty((rows, cols), dtype=BF16, device=x.device)
+        out = torch.empty((rows, cols), dtype=ELEM(), device=x.device)
     check(_lib.load().srgpt_rmsnorm_bf16(_p(x), ldx, _p(weight), _p(out), _rowmajor2d(out, "rmsnorm.out"), rows, cols, eps,
                                          _stream()), "srgpt_rmsnorm_bf16")
     return out
@@ -145,28 +185,28 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[tor
 def patchify(images: torch.Tensor, patch: int, ldk: int) -> torch.Tensor:
     if not images.is_cuda or images.dim() != 4 or images.shape[1] != 3 or not images.is_contiguous():
         raise SrgptError("patchify: expected a contiguous CUDA tensor [n, 3, R, R]")
-    if images.dtype not in (torch.float32, BF16):
+    if images.dtype not in (torch.float32, ELEM()):
         raise SrgptError(f"patchify: unsupported dtype {images.dtype}")
     n, _, R, R2 = images.shape
     if R != R2:
         raise SrgptError("patchify: square images only")
     P = R // patch
-    out = torch.empty((n * P * P, ldk), dtype=BF16, device=images.device)
-    check(_lib.load().srgpt_patchify_bf16(_p(images), 1 if images.dtype == BF16 else 0, _p(out), n, R, patch, ldk, _stream()),
+    out = torch.empty((n * P * P, ldk), dtype=ELEM(), device=images.device)
+    check(_lib.load().srgpt_patchify_bf16(_p(images), 1 if images.dtype == ELEM() else 0, _p(out), n, R, patch, ldk, _stream()),
           "srgpt_patchify_bf16")
     return out
 
 
 def splice_rows(src0: torch.Tensor, src1, src2, src3, src_id: torch.Tensor, src_row: torch.Tensor) -> torch.Tensor:
-    _need(src0, BF16, "splice.src0"); _need(src_id, torch.int32, "splice.src_id"); _need(src_row, torch.int32, "splice.src_row")
+    _need(src0, ELEM(), "splice.src0"); _need(src_id, torch.int32, "splice.src_id"); _need(src_row, torch.int32, "splice.src_row")
     cols = src0.shape[-1]
     rows = src_id.numel()
     for s in (src1, src2, src3):
         if s is not None:
-            _need(s, BF16, "splice.src")
+            _need(s, ELEM(), "splice.src")
             if s.shape[-1] != cols or not s.is_contiguous():
                 raise SrgptError("splice: all sources must be contiguous with the same width")
-    out = torch.empty((rows, cols), dtype=BF16, device=src0.device)
+    out = torch.empty((rows, cols), dtype=ELEM(), device=src0.device)
     check(_lib.load().srgpt_splice_rows_bf16(_p(src0), _p(src1), _p(src2), _p(src3), _p(src_id), _p(src_row), _p(out), rows,
                                              cols, _stream()), "srgpt_splice_rows_bf16")
     return out
@@ -177,7 +217,7 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
     """masks [n_img, M, IH, IW] (fp32 or bf16) -> normalised bf16 pooling weights [n_img, M, side*side]."""
     if not masks.is_cuda or masks.dim() != 4 or not masks.is_contiguous():
         raise SrgptError("mask_weights: expected a contiguous CUDA tensor [n_img, M, IH, IW]")
-    if masks.dtype not in (torch.float32, BF16):
+    if masks.dtype not in (torch.float32, ELEM()):
         raise SrgptError(f"mask_weights: unsupported dtype {masks.dtype}")
     n, M, IH, IW = masks.shape
     # base_extractor.py:53-57: scale_factor = (L / (IH*IW)) ** 0.5 in Python doubles; ATen then uses
@@ -189,16 +229,16 @@ def mask_weights(masks: torch.Tensor, side: int, order: int) -> torch.Tensor:
     lib = _lib.load()
     L = side * side
     ld = (L + 7) // 8 * 8  # rows padded to 16 bytes (include/srgpt_b200.h); the returned view hides the pad
-    w = torch.empty((n, M, ld), dtype=BF16, device=masks.device)[:, :, :L]
+    w = torch.empty((n, M, ld), dtype=ELEM(), device=masks.device)[:, :, :L]
     ws = torch.empty(lib.srgpt_mask_weights_workspace(n, M, side), dtype=torch.uint8, device=masks.device)
-    check(lib.srgpt_mask_weights(_p(masks), 1 if masks.dtype == BF16 else 0, _p(w), _p(ws), n, M, IH, IW, side, rscale, order,
+    check(lib.srgpt_mask_weights(_p(masks), 1 if masks.dtype == ELEM() else 0, _p(w), _p(ws), n, M, IH, IW, side, rscale, order,
                                  _stream()), "srgpt_mask_weights")
     return w
 
 
 def mask_pool(x: torch.Tensor, w: torch.Tensor, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [n_img, L, C] bf16, w [n_img, M, L] bf16 -> [n_img, M, C] bf16."""
-    _need(x, BF16, "mask_pool.x"); _need(w, BF16, "mask_pool.w")
+    _need(x, ELEM(), "mask_pool.x"); _need(w, ELEM(), "mask_pool.w")
     if x.dim() != 3 or w.dim() != 3 or not x.is_contiguous():
         raise SrgptError("mask_pool: expected contiguous x [n, L, C] and w [n, M, L]")
     n, L, Cc = x.shape
@@ -211,24 +251,24 @@ def mask_pool(x: torch.Tensor, w: torch.Tensor, workspace: Optional[torch.Tensor
     need = _lib.load().srgpt_mask_pool_workspace(n, M, L, Cc)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=x.device)
-    out = torch.empty((n, M, Cc), dtype=BF16, device=x.device)
+    out = torch.empty((n, M, Cc), dtype=ELEM(), device=x.device)
     check(_lib.load().srgpt_mask_pool_bf16(_p(x), _p(w), _p(out), _p(workspace), n, M, L, Cc, _stream()), "srgpt_mask_pool_bf16")
     return out
 
 
 def adaptive_avgpool(x: torch.Tensor, side: int, out_side: int, order: int) -> torch.Tensor:
-    _need(x, BF16, "adaptive_avgpool.x")
+    _need(x, ELEM(), "adaptive_avgpool.x")
     n, L, Cc = x.shape
     if L != side * side or not x.is_contiguous():
         raise SrgptError("adaptive_avgpool: expected contiguous [n, side*side, C]")
-    y = torch.empty((n, out_side * out_side, Cc), dtype=BF16, device=x.device)
+    y = torch.empty((n, out_side * out_side, Cc), dtype=ELEM(), device=x.device)
     check(_lib.load().srgpt_adaptive_avgpool_bf16(_p(x), _p(y), n, side, out_side, Cc, order, _stream()),
           "srgpt_adaptive_avgpool_bf16")
     return y
 
 
 def reorder_rows(x: torch.Tensor, side: int, from_order: int, to_order: int) -> torch.Tensor:
-    _need(x, BF16, "reorder_rows.x")
+    _need(x, ELEM(), "reorder_rows.x")
     n, L, Cc = x.shape
     if L != side * side or not x.is_contiguous():
         raise SrgptError("reorder_rows: expected contiguous [n, side*side, C]")
@@ -253,12 +293,12 @@ def attention_prefill(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: 
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q/k/v: 2-D row-major views [batch*seqlen, heads*head_dim] (may be column slices of a fused qkv buffer)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
-        _need(t, BF16, f"attention_prefill.{nm}")
+        _need(t, ELEM(), f"attention_prefill.{nm}")
     q_ld, k_ld, v_ld = _rowmajor2d(q, "q"), _rowmajor2d(k, "k"), _rowmajor2d(v, "v")
     if k_ld != v_ld:
         raise SrgptError("attention_prefill: k and v must share a row stride")
     if out is None:
-        out = torch.empty((batch * seqlen, n_heads * head_dim), dtype=BF16, device=q.device)
+        out = torch.empty((batch * seqlen, n_heads * head_dim), dtype=ELEM(), device=q.device)
     check(_lib.load().srgpt_attention_prefill_bf16(_p(q), _p(k), _p(v), _p(out), q_ld, k_ld, _rowmajor2d(out, "out"), batch,
                                                    seqlen, n_heads, n_kv_heads, head_dim, scale, 1 if causal else 0, _stream()),
           "srgpt_attention_prefill_bf16")
@@ -269,12 +309,12 @@ def attention_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
                              n_heads: int, n_kv_heads: int, head_dim: int, scale: float, causal: bool) -> torch.Tensor:
     """Packed sequences: rows [cu_seqlens[b], cu_seqlens[b+1]) belong to sequence b (modeling_llama.py:540-562)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
-        _need(t, BF16, f"attention_prefill_varlen.{nm}")
+        _need(t, ELEM(), f"attention_prefill_varlen.{nm}")
     _need(cu_seqlens, torch.int32, "attention_prefill_varlen.cu_seqlens")
     q_ld, k_ld, v_ld = _rowmajor2d(q, "q"), _rowmajor2d(k, "k"), _rowmajor2d(v, "v")
     if k_ld != v_ld:
         raise SrgptError("attention_prefill_varlen: k and v must share a row stride")
-    out = torch.empty((q.shape[0], n_heads * head_dim), dtype=BF16, device=q.device)
+    out = torch.empty((q.shape[0], n_heads * head_dim), dtype=ELEM(), device=q.device)
     check(_lib.load().srgpt_attention_prefill_varlen_bf16(_p(q), _p(k), _p(v), _p(out), q_ld, k_ld, _rowmajor2d(out, "out"),
                                                           cu_seqlens.numel() - 1, _p(cu_seqlens), max_seqlen, q.shape[0], n_heads, n_kv_heads,
                                                           head_dim, scale, 1 if causal else 0, _stream()),
@@ -285,7 +325,7 @@ def attention_prefill_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, 
 def rope_kv_append_varlen(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
                           start_pos: torch.Tensor, kv_pages: torch.Tensor, page_tables: torch.Tensor, page_size: int,
                           cu_seqlens: torch.Tensor) -> None:
-    _need(qkv, BF16, "rope_kv_append_varlen.qkv")
+    _need(qkv, ELEM(), "rope_kv_append_varlen.qkv")
     if not qkv.is_contiguous() or qkv.shape[1] != (n_heads + 2 * n_kv_heads) * head_dim:
         raise SrgptError("rope_kv_append_varlen: qkv must be contiguous [rows, (nh + 2 nkv) * hd]")
     for t, nm in ((start_pos, "start_pos"), (page_tables, "page_tables"), (cu_seqlens, "cu_seqlens")):
@@ -301,7 +341,7 @@ def rope_kv_append_varlen(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head
 def rope_kv_append(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int, cos_tab: torch.Tensor,
                    sin_tab: torch.Tensor, start_pos: torch.Tensor, kv_pages: torch.Tensor, page_table: torch.Tensor,
                    page_size: int) -> None:
-    _need(qkv, BF16, "rope_kv_append.qkv")
+    _need(qkv, ELEM(), "rope_kv_append.qkv")
     if not qkv.is_contiguous() or qkv.shape[1] != (n_heads + 2 * n_kv_heads) * head_dim:
         raise SrgptError("rope_kv_append: qkv must be contiguous [rows, (nh + 2 nkv) * hd]")
     _need(start_pos, torch.int32, "rope_kv_append.start_pos"); _need(page_table, torch.int32, "rope_kv_append.page_table")
@@ -361,7 +401,7 @@ def attention_decode_batched(q: torch.Tensor, out: torch.Tensor, kv_pages: torch
                              n_heads: int, n_kv_heads: int, head_dim: int, scale: float) -> torch.Tensor:
     """q [B, >= n_heads*hd] (row-strided view, e.g. the q columns of a fused qkv buffer), out [B, n_heads*hd], page_tables [>= B, cap],
     pos int32 [B] = position of every sequence's newest row."""
-    _need(q, BF16, "attention_decode_batched.q"); _need(out, BF16, "attention_decode_batched.out")
+    _need(q, ELEM(), "attention_decode_batched.q"); _need(out, ELEM(), "attention_decode_batched.out")
     _need(page_tables, torch.int32, "attention_decode_batched.page_tables"); _need(pos, torch.int32, "attention_decode_batched.pos")
     B = q.shape[0]
     check(_lib.load().srgpt_attention_decode_batched_bf16(_p(q), _rowmajor2d(q, "q"), _p(out), _rowmajor2d(out, "out"), _p(kv_pages), _p(page_tables),
@@ -471,7 +511,7 @@ def argmax_f32(x: torch.Tensor) -> torch.Tensor:
 
 
 def argmax_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _need(x, BF16, "argmax_bf16.x")
+    _need(x, ELEM(), "argmax_bf16.x")
     ldx = _rowmajor2d(x, "argmax_bf16.x")
     rows, cols = x.shape
     if out is None:
@@ -506,14 +546,14 @@ def make_llama_layer_array(layers, kv_pages_per_layer):
 
 def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: int, D: int, heads: int, I: int, eps: float) -> torch.Tensor:
     """n_layers SigLIP encoder layers in place on x [n_img*T, D]."""
-    _need(x, BF16, "siglip_layers.x")
+    _need(x, ELEM(), "siglip_layers.x")
     _ensure_gemm_workspace(x.device)
     M = n_img * T
     dev = x.device
-    ws_h = torch.empty((M, D), dtype=BF16, device=dev)
-    ws_qkv = torch.empty((M, 3 * D), dtype=BF16, device=dev)
-    ws_attn = torch.empty((M, D), dtype=BF16, device=dev)
-    ws_mlp = torch.empty((M, I), dtype=BF16, device=dev)
+    ws_h = torch.empty((M, D), dtype=ELEM(), device=dev)
+    ws_qkv = torch.empty((M, 3 * D), dtype=ELEM(), device=dev)
+    ws_attn = torch.empty((M, D), dtype=ELEM(), device=dev)
+    ws_mlp = torch.empty((M, I), dtype=ELEM(), device=dev)
     import ctypes
     check(_lib.load().srgpt_siglip_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
                                                _p(ws_attn), _p(ws_mlp), n_img, T, D, heads, I, eps, _stream()), "srgpt_siglip_layers_bf16")
@@ -526,7 +566,7 @@ def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos,
     """All decoder layers over the prompt rows x [S, H] in place (K/V appended to the paged cache).  One prompt
     (page_table [cap], start_pos [1]) or, with cu_seqlens [n_seqs+1], n_seqs prompts packed back to back
     (page_table [n_seqs, cap], start_pos [n_seqs])."""
-    _need(x, BF16, "llama_prefill_layers.x")
+    _need(x, ELEM(), "llama_prefill_layers.x")
     _ensure_gemm_workspace(x.device)
     n_seqs, pt_stride = 1, 0
     if cu_seqlens is not None:
@@ -538,10 +578,10 @@ def llama_prefill_layers(x: torch.Tensor, layer_array, n_layers: int, dims, cos,
     S, H = x.shape
     nh, nkv, hd, I = dims.num_attention_heads, dims.num_key_value_heads, dims.head_dim, dims.intermediate_size
     dev = x.device
-    ws_h = torch.empty((S, H), dtype=BF16, device=dev)
-    ws_qkv = torch.empty((S, (nh + 2 * nkv) * hd), dtype=BF16, device=dev)
-    ws_attn = torch.empty((S, nh * hd), dtype=BF16, device=dev)
-    ws_act = torch.empty((S, I), dtype=BF16, device=dev)
+    ws_h = torch.empty((S, H), dtype=ELEM(), device=dev)
+    ws_qkv = torch.empty((S, (nh + 2 * nkv) * hd), dtype=ELEM(), device=dev)
+    ws_attn = torch.empty((S, nh * hd), dtype=ELEM(), device=dev)
+    ws_act = torch.empty((S, I), dtype=ELEM(), device=dev)
     import ctypes
     check(_lib.load().srgpt_llama_prefill_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
                                                       _p(ws_attn), _p(ws_act), S, H, nh, nkv, hd, I, dims.rms_norm_eps, _p(cos), _p(sin),

@@ -90,7 +90,7 @@ class MaskPooling:
     @staticmethod
     def _prep(mask: torch.Tensor, device) -> torch.Tensor:
         m = mask.detach().to(device=device)
-        if m.dtype not in (torch.float32, torch.bfloat16):
+        if m.dtype not in (torch.float32, ops.ELEM()):
             m = m.float()  # base_extractor.py:55
         return m.contiguous()
 
@@ -106,6 +106,11 @@ class RegionExtractor:
         self.mask_pooling = MaskPooling()
         self.C = cfg.vision.hidden_size
 
+    @property
+    def dtype(self):
+        return self.w.rgb_w.dtype
+
+    @ops.in_own_dtype
     def feature_refinement_nested(self, tower_features: torch.Tensor):
         """[N, T, C] -> (hres in nested order [N, 16T, C], lres [N, 729, C] row-major)."""
         N, T, C = tower_features.shape
@@ -119,6 +124,7 @@ class RegionExtractor:
         lres = ops.adaptive_avgpool(hres, 4 * P, ADA_POOL, ops.ORDER_NESTED)
         return hres, lres
 
+    @ops.in_own_dtype
     def feature_refinement(self, tower_features: torch.Tensor):
         """Reference signature/layout (base_extractor.py:137-147): hres flattened row-major (H W)."""
         hres, lres = self.feature_refinement_nested(tower_features)
@@ -136,6 +142,7 @@ class RegionExtractor:
                 out[i] = part
         return out
 
+    @ops.in_own_dtype
     def forward(self, image_features: torch.Tensor, depth_features: Optional[torch.Tensor], masks, hres_order: int = ops.ORDER_ROWMAJOR):
         """base_extractor.py:167-173.  ``image_features`` = hres (row-major by default, like the reference)."""
         w = self.w

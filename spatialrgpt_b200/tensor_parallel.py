@@ -72,9 +72,9 @@ class TPLlamaDecoder(LlamaDecoder):
         self.nkv_local = dims.num_key_value_heads // world
         self.kv_off = rank * self.nkv_local
         hd = dims.head_dim
-        self.q_local = torch.zeros(self.nh_local * hd, dtype=torch.bfloat16, device=dev)
-        self.attn_local = torch.zeros(self.nh_local * hd, dtype=torch.bfloat16, device=dev)
-        self.act_local = torch.zeros(dims.intermediate_size // world, dtype=torch.bfloat16, device=dev)
+        self.q_local = torch.zeros(self.nh_local * hd, dtype=self.dtype, device=dev)
+        self.attn_local = torch.zeros(self.nh_local * hd, dtype=self.dtype, device=dev)
+        self.act_local = torch.zeros(dims.intermediate_size // world, dtype=self.dtype, device=dev)
         self.partial = torch.zeros(dims.hidden_size, dtype=torch.float32, device=dev)
         # vocabulary-parallel lm_head: contiguous row blocks, the last rank takes the remainder
         V = dims.vocab_size

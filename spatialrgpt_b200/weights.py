@@ -128,6 +128,28 @@ class ModelWeights:
         walk(self)
         return total
 
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.llama.embed.dtype
+
+    def to(self, dtype: torch.dtype) -> "ModelWeights":
+        """In-place cast of every floating-point weight (what ``model.to(dtype=...)`` does to the reference's modules,
+        llava/eval/eval_spatial.py:221); the kernel layouts (padding, interleaving, fused qkv) are dtype independent."""
+        def walk(o):
+            if isinstance(o, torch.Tensor):
+                return o.to(dtype) if o.is_floating_point() else o
+            if isinstance(o, list):
+                return [walk(x) for x in o]
+            if isinstance(o, tuple):
+                return tuple(walk(x) for x in o)
+            if hasattr(o, "__dataclass_fields__"):
+                for k in o.__dataclass_fields__:
+                    setattr(o, k, walk(getattr(o, k)))
+            return o
+
+        walk(self)
+        return self
+
 
 def _deconv_as_gemm(w: torch.Tensor) -> torch.Tensor:
     """ConvTranspose2d weight [Cin, Cout, 2, 2] -> [(di*2+dj)*Cout + co, Cin]."""
@@ -139,13 +161,14 @@ def interleave_rows(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     return torch.stack((gate, up), dim=1).reshape(2 * gate.shape[0], gate.shape[1]).contiguous()
 
 
-def from_state_dicts(cfg: LlavaConfig, sd: Dict[str, Dict[str, torch.Tensor]], device, n_tower_layers: Optional[int] = None) -> ModelWeights:
+def from_state_dicts(cfg: LlavaConfig, sd: Dict[str, Dict[str, torch.Tensor]], device, n_tower_layers: Optional[int] = None,
+                     dtype: torch.dtype = BF16) -> ModelWeights:
     """sd = {"vision_tower": ..., "region_extractor": ..., "mm_projector": ..., "llm": ...} with the
-    reference's key names; tensors may live on the CPU in any float dtype."""
+    reference's key names; tensors may live on the CPU in any float dtype.  ``dtype``: torch.bfloat16 or torch.float16."""
     dev = torch.device(device)
 
     def g(d, k):
-        return d[k].to(device=dev, dtype=BF16)
+        return d[k].to(device=dev, dtype=dtype)
 
     v, vc = sd["vision_tower"], cfg.vision
     D = vc.hidden_size
@@ -213,7 +236,8 @@ def from_state_dicts(cfg: LlavaConfig, sd: Dict[str, Dict[str, torch.Tensor]], d
     return ModelWeights(vision, region, projector, llama)
 
 
-def random_init(cfg: LlavaConfig, device, seed: int = 0, std: float = 0.02, n_tower_layers: Optional[int] = None) -> ModelWeights:
+def random_init(cfg: LlavaConfig, device, seed: int = 0, std: float = 0.02, n_tower_layers: Optional[int] = None,
+                dtype: torch.dtype = BF16) -> ModelWeights:
     """Seeded synthetic weights generated directly on the device in the kernel layouts (no 16 GB
     host staging for the 8B benchmarks; there are no checkpoints offline).  Same distributions as
     the test fixtures' weight generator but NOT the same values — parity tests go through
@@ -222,13 +246,13 @@ def random_init(cfg: LlavaConfig, device, seed: int = 0, std: float = 0.02, n_to
     gen = torch.Generator(device=dev).manual_seed(seed)
 
     def rn(*shape, s=std):
-        return (torch.randn(*shape, generator=gen, device=dev, dtype=torch.float32) * s).to(BF16)
+        return (torch.randn(*shape, generator=gen, device=dev, dtype=torch.float32) * s).to(dtype)
 
     def nw(n):
-        return (1.0 + 0.1 * torch.randn(n, generator=gen, device=dev)).to(BF16)
+        return (1.0 + 0.1 * torch.randn(n, generator=gen, device=dev)).to(dtype)
 
     def nb(n):
-        return (0.05 * torch.randn(n, generator=gen, device=dev)).to(BF16)
+        return (0.05 * torch.randn(n, generator=gen, device=dev)).to(dtype)
 
     vc, lc = cfg.vision, cfg.llama
     D, I, T = vc.hidden_size, vc.intermediate_size, vc.grid * vc.grid
