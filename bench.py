@@ -160,7 +160,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = baseline_config("c2")
-    model = LlavaLlamaModel(cfg, random_init(cfg, dev, seed=0, n_tower_layers=cfg.vision.num_hidden_layers - 1), max_seq_len=1024)
+    wdtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
+    from spatialrgpt_b200 import _lib
+    _lib.set_elem({"bf16": "bf16", "fp16": "f16"}[args.dtype])  # process-wide: the per-kernel timing below calls ops.* directly
+    model = LlavaLlamaModel(cfg, random_init(cfg, dev, seed=0, n_tower_layers=cfg.vision.num_hidden_layers - 1, dtype=wdtype), max_seq_len=1024)
     nums = algorithmic_numbers(cfg)
     hbm_peak, tensor_peak, peak_src, tensor_sustained = load_peaks()
 
@@ -325,7 +328,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": round(n_tok / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "requests_per_step_per_gpu": 1, "new_tokens": NEW_TOKENS, "parallelism": f"replicas x{world}",
                    "l2": "working set per step (16 GB of weights) exceeds the 126 MB L2; no flush needed",
                    "ttft_flops": nums["flops_ttft"]},
@@ -478,6 +481,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-c3", action="store_true", help="skip the batch-32 prefill-only measurement (config c3)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="compute dtype: bf16 (how the reference's eval_spatial.py runs the model; the graded default) or fp16 (the loader default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -487,7 +492,7 @@ def main():
             # convenience: re-launch under torchrun, one rank per GPU
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
-                   "--steps", str(args.steps), "--warmup", str(args.warmup)]
+                   "--steps", str(args.steps), "--warmup", str(args.warmup), "--dtype", args.dtype]
             sys.exit(subprocess.call(cmd))
         run_ours(args)
 

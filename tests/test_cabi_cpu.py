@@ -23,11 +23,13 @@ def test_header_declares_the_expected_groups():
         assert must in syms
 
 
-def test_library_loads_and_exports_every_declared_symbol():
+@pytest.mark.parametrize("elem", ["bf16", "f16"])
+def test_library_loads_and_exports_every_declared_symbol(elem):
+    """Both builds of the kernels (bfloat16 / IEEE half elements, csrc/common.cuh) export the same C-ABI."""
     from spatialrgpt_b200 import _lib
-    lib = _lib.load()
-    assert lib.srgpt_abi_version() == 1
-    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True, check=True).stdout
+    lib = _lib.load(elem=elem)
+    assert lib.srgpt_abi_version() == 1 and lib.srgpt_elem_type() == {"bf16": 0, "f16": 1}[elem]
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path(elem)], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r"\sT\s+(srgpt_[a-z0-9_]+)", out))
     declared = set(declared_symbols())
     assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
@@ -55,6 +57,21 @@ def test_host_argument_validation_needs_no_gpu():
     assert rc == -1 and "invalid argument" in _lib.last_error()
     assert lib.srgpt_mask_pool_workspace(0, 1, 1, 8) == -1
     assert lib.srgpt_lm_head_workspace(128259) > 0
+
+
+def test_element_type_switch_selects_the_build():
+    import torch
+
+    from spatialrgpt_b200 import _lib, ops
+    assert ops.ELEM() == torch.bfloat16 and _lib.load().srgpt_elem_type() == 0
+    with ops.elem_dtype(torch.float16):
+        assert ops.ELEM() == torch.float16 and _lib.load().srgpt_elem_type() == 1
+        with ops.elem_dtype(torch.bfloat16):
+            assert _lib.load().srgpt_elem_type() == 0
+        assert _lib.load().srgpt_elem_type() == 1
+    assert ops.ELEM() == torch.bfloat16
+    with pytest.raises(_lib.SrgptError):
+        ops.elem_dtype(torch.float32)
 
 
 def test_product_path_never_imports_the_oracle():

@@ -65,6 +65,11 @@ class _StubModel:
         self.device = torch.device("cpu")
         self.config = SimpleNamespace(image_aspect_ratio="resize")
         self.calls = []
+        self.dtype = torch.float16  # what the loader hands out (builder.py:62)
+
+    def to(self, dtype=None, **kw):
+        self.dtype = dtype or self.dtype
+        return self
 
     def generate(self, input_ids, images=None, depths=None, masks=None, **kw):
         self.calls.append(dict(ids=input_ids.clone(), images=images, depths=depths, masks=masks, kw=kw))
@@ -141,9 +146,11 @@ def test_region_cls_driver_end_to_end_with_a_stub_model(tmp_path):
 
     class Stub:
         device = torch.device("cpu")
+        dtype = torch.float16  # this script runs the model as loaded (eval_region_cls.py:316-317)
         config = SimpleNamespace(image_aspect_ratio="resize", mm_use_im_start_end=False)
 
         def generate(self, input_ids, images=None, masks=None, **kw):
+            assert images.dtype == torch.float16 and masks[0].dtype == torch.float16
             seen.append((input_ids.clone(), tuple(images.shape), tuple(masks[0].shape), kw))
             return torch.tensor([[tok._id("dog"), tok._id("</s>")]])
 
@@ -175,6 +182,7 @@ def test_region_chat_follow_up_flow_with_a_stub_model():
 
     class Stub:
         device = torch.device("cpu")
+        dtype = torch.bfloat16
         config = SimpleNamespace(image_aspect_ratio="resize", mm_use_im_start_end=False)
 
         def generate(self, input_ids, images=None, depths=None, masks=None, **kw):

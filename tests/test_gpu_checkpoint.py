@@ -30,6 +30,7 @@ def test_load_pretrained_model_then_generate(tmp_path):
     tokenizer, model, image_processor, context_len = load_pretrained_model(root, "SpatialRGPT-tiny", None)
     assert context_len == 2048 and model.config.llm_mask_token_id == tokenizer.convert_tokens_to_ids("<mask>")
     assert model.config.llama.vocab_size == len(tokenizer)
+    assert model.dtype == torch.float16  # builder.py:62: the loader hands out fp16 ...
 
     # ---- the caller's flow (eval_spatial.py:196-237)
     rng = np.random.RandomState(3)
@@ -39,8 +40,8 @@ def test_load_pretrained_model_then_generate(tmp_path):
     region[0][10:50, 20:70] = 1
     region[1][40:85, 60:110] = 1
     model.config.image_processor = image_processor
-    images = process_images([image], image_processor, model.config).to(model.device, dtype=torch.bfloat16)
-    depths = process_images([depth], image_processor, model.config).to(model.device, dtype=torch.bfloat16)
+    images32 = process_images([image], image_processor, model.config)
+    depths32 = process_images([depth], image_processor, model.config)
     masks = process_regions(region, image_processor, model.config)
     conv = conv_templates["llava_v1"].copy()
     conv.append_message(conv.roles[0], "<image>\n how far is <mask> <depth> from <mask> <depth> ?")
@@ -49,9 +50,18 @@ def test_load_pretrained_model_then_generate(tmp_path):
     assert int((input_ids == IMAGE_TOKEN_INDEX).sum()) == 1 and int((input_ids == model.config.llm_mask_token_id).sum()) == 2
     stopping = KeywordsStoppingCriteria(["</s>"], tokenizer, input_ids)
     n_new = 10
-    out = model.generate(input_ids.to(model.device), images=images, depths=depths, masks=[masks.to(model.device, dtype=torch.bfloat16)],
-                         do_sample=False, temperature=0, max_new_tokens=n_new, use_cache=True, stopping_criteria=[stopping])
+
+    def run():
+        dev, dt = model.device, model.dtype
+        return model.generate(input_ids.to(dev), images=images32.to(dev, dtype=dt), depths=depths32.to(dev, dtype=dt), masks=[masks.to(dev, dtype=dt)],
+                              do_sample=False, temperature=0, max_new_tokens=n_new, use_cache=True, stopping_criteria=[stopping])
+
+    got16 = run()[0].tolist()               # ... which is how eval_region_cls.py:316-317 runs it
+    model.to(dtype=torch.bfloat16)          # ... and eval_spatial.py:221 casts to bf16 before generating
+    assert model.dtype == torch.bfloat16
+    out = run()
     got = out[0].tolist()
+    images, depths = images32.to(torch.bfloat16), depths32.to(torch.bfloat16)
 
     # ---- the oracle on the weights the loader actually read (token tables resized to len(tokenizer))
     cfg2, sd2, _, _ = builder.read_checkpoint(root)
@@ -65,5 +75,6 @@ def test_load_pretrained_model_then_generate(tmp_path):
     safe = int((margin > 2 * tol).long().cumprod(0).sum())
     assert safe >= 1
     assert got[:safe] == ref_ids.tolist()[:safe], (got, ref_ids.tolist(), margin.tolist())
+    assert got16[:safe] == ref_ids.tolist()[:safe], (got16, ref_ids.tolist(), margin.tolist())
     text = tokenizer.batch_decode(out, skip_special_tokens=True)[0]
     assert isinstance(text, str)
