@@ -300,14 +300,17 @@ class LlamaDecoder:
         self.active_pt.copy_(self.cache.page_tables[seq])
         need_host_check = bool(eos) or stopping_fn is not None
         return_logits = logits is not None
+        graph = None
         if use_graph and not return_logits:
-            self._ensure_graph(seq)
+            self._ensure_graph(seq, sample)
+            graph = self._graph_sample if sample else self._graph
+
         def launch_step(k: int) -> None:
-            if use_graph and not return_logits:
-                self._graph.replay()
-                ops.LAUNCHES += self.kernels_per_decode_step
+            if graph is not None:
+                graph.replay()
+                ops.LAUNCHES += self.kernels_per_decode_step + (1 if sample else 0)
             else:
-                self._decode_step_launch(seq, None if logits is None else logits[k])
+                self._decode_step_launch(seq, None if logits is None else logits[k], sample)
 
         if not need_host_check:
             while n < max_new_tokens:

@@ -128,10 +128,19 @@ def test_fp16_stages_and_tokens_match_reference_fixture(golden_dir, name):
     with __import__("spatialrgpt_b200").ops.elem_dtype(F16):  # module-level call outside generate(): select the build explicitly
         me, de = model.get_region_extractor()(hres, dfeat, md)
         feats = model.get_mm_projector()(lres)
-    assert_close(me[0], g["mask_embeds"], **F16_STAGE, what="mask_embeds")
+    # A region that is empty AFTER the bilinear resize (tiny_nodepth's 1-pixel mask) is where fp16 differs from bf16 in the reference
+    # itself: denorm = sum + 1e-8 (base_extractor.py:66) rounds to 0 in fp16 (1e-8 is below half the smallest subnormal), so the row is
+    # 0/0 = NaN, while bf16 keeps 1e-8 and gives 0.  The kernels reproduce that (the oracle in fp16 mode shows the same rows).
+    o_me = O.mask_pooling(g["hres"].to(F16), [m.to(F16) for m in masks])[0]
+    nan_rows = torch.isnan(o_me.float()).any(-1)
+    assert torch.equal(torch.isnan(me[0].float()).any(-1).cpu(), nan_rows), "NaN rows differ from the fp16 oracle"
+    assert_close(me[0][~nan_rows.to(DEV)], g["mask_embeds"][~nan_rows], **F16_STAGE, what="mask_embeds")
     if depth_on:
-        assert_close(de[0], g["depth_embeds"], **F16_STAGE, what="depth_embeds")
+        assert_close(de[0][~nan_rows.to(DEV)], g["depth_embeds"][~nan_rows], **F16_STAGE, what="depth_embeds")
     assert_close(feats, g["image_features"], **F16_STAGE, what="image_features")
+    if bool(nan_rows.any()):
+        assert name == "tiny_nodepth"
+        return  # NaN embeddings poison the prompt (in the reference too): nothing meaningful to compare downstream
 
     ids, logits = model.generate(input_ids.to(DEV), images=imd, depths=dd, masks=md, do_sample=False, max_new_tokens=n_new,
                                  use_cache=True, output_logits=True)

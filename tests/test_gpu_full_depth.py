@@ -24,4 +24,6 @@ def test_c2_full_depth_matches_oracle_fixture(golden_dir):
         with open(os.environ["SRGPT_FULL_DEPTH_REPORT"], "w") as f:
             json.dump(report, f, indent=1)
     assert not fails, fails
-    assert report["steps_compared_vs_fp32"] >= 3 and report["steps_equal_to_bf16_oracle"] >= 3, "should follow the oracles for several tokens"
+    # `fails` already holds the id rule (ids must agree wherever the oracle's margin exceeds 4 x the rms noise).  Near-ties are free to
+    # flip with any change of summation order: step 2 of the fixture has a margin of 0.11 logits under an rms noise of 0.2.
+    assert report["steps_compared_vs_fp32"] >= 3 and report["steps_equal_to_bf16_oracle"] >= report["steps_id_must_agree_bf16"]

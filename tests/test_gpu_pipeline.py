@@ -277,8 +277,19 @@ def test_generate_with_sampling(golden_dir):
     s2 = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, **args)[0].tolist()
     s3 = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, use_cuda_graph=False, **args)[0].tolist()
     assert s1 == s2 == s3 and len(s1) == n_new
-    draws = {tuple(model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=s, **args)[0].tolist()) for s in range(6)}
-    assert len(draws) > 1, "six seeds at temperature 1.5 should not all give the same continuation"
+    draws = [model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=s, **args)[0].tolist() for s in range(6)]
+    assert len({tuple(d) for d in draws}) > 1, "six seeds at temperature 1.5 should not all give the same continuation"
+    # EVERY step is sampled, not just the first one: among draws that share a first token the continuations still differ, and each
+    # token lies inside the top-k / top-p support of the logits the model produced for that step
+    top_k = 4
+    by_step = [set() for _ in range(n_new)]
+    for s in range(12):
+        out, lg = model.generate(ids, do_sample=True, temperature=2.0, top_p=1.0, top_k=top_k, seed=100 + s, output_logits=True, **args)
+        toks = out[0].tolist()
+        for k, t in enumerate(toks):
+            by_step[k].add(t)
+            assert t in lg[0, k].topk(top_k).indices.tolist(), f"step {k}: token {t} outside the top-{top_k} of its own logits"
+    assert sum(len(b) > 1 for b in by_step[1:]) >= (n_new - 1) // 2, f"later steps are not being sampled: {[len(b) for b in by_step]}"
     stop_at = s1[2]
     cut = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, eos_token_id=stop_at, **args)[0].tolist()
     assert cut == s1[: s1.index(stop_at) + 1]

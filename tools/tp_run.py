@@ -3,7 +3,7 @@
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/tp_run.py [--check] [--bench]
 
---check  tiny GQA model (fixture sizes): generate() with TP = N must give exactly the ids of the TP-1 decoder on the same weights,
+--check  tiny GQA model (fixture sizes; widened to 2N / N heads for N > 2): generate() with TP = N must give exactly the ids of the TP-1 decoder on the same weights,
          for the CUDA-graph and the eager decode loop, with EOS handling.
 --bench  c5: Llama-3-8B dims, SigLIP@448 px, 8 mask regions, depth ON, 512 greedy tokens: tokens/s at TP = N next to the TP-1
          decoder of the same process, the ids of both (must agree on the TP-1 margin-safe prefix), NVLink bytes per token.
@@ -43,6 +43,8 @@ def main():
         from tests.golden.make_golden import CASES
         from tests.test_gpu_pipeline import build_model
         kw, n_regions, t_text, kind, n_new, _ = CASES["tiny_masks_gqa"]
+        if world > 2:  # the fixture model has 4 / 2 heads: widen it so that every rank owns at least one KV head (head_dim stays 128)
+            kw = {**kw, "hidden": 256 * world, "heads": 2 * world, "kv_heads": world, "inter": 128 * world}
         oc, sd, ref_model = build_model(kw, 7)
         tp_model = LlavaLlamaModel(ref_model.config, ref_model.weights, max_seq_len=512, tensor_parallel=(rank, world))
         ids, im, de, mk = O.synth_request(oc, n_regions, t_text, seed=1234, kind=kind)
