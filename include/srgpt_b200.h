@@ -56,7 +56,8 @@ enum {
   SRGPT_EPI_BIAS_GELU_TANH = 2, /* C = gelu_tanh(bf16(acc + bias))   (SigLIP fc1)                 */
   SRGPT_EPI_BIAS_GELU_ERF = 3,  /* C = gelu_erf(bf16(acc + bias))    (deconv #2, mm_projector)    */
   SRGPT_EPI_BIAS_RESIDUAL = 4,  /* C = bf16(acc + bias) + residual[row (% res_row_mod), n]        */
-  SRGPT_EPI_SWIGLU = 5          /* W rows interleaved (gate_i, up_i): C[:, i] = silu(g) * u; C has N/2 cols */
+  SRGPT_EPI_SWIGLU = 5,         /* W rows interleaved (gate_i, up_i): C[:, i] = silu(g) * u; C has N/2 cols */
+  SRGPT_EPI_BIAS_QUICK_GELU = 6 /* C = x * sigmoid(1.702 x), x = bf16(acc + bias)   (CLIP fc1, HF QuickGELUActivation) */
 };
 /* Optional workspace of the short-prompt ("tall stream-K") configuration: M <= 384 rows, all rows in one CTA, the (n-tile,
  * k-block) units balanced over the SMs, split tiles combined through fp32 partials in this buffer.  The caller owns the memory
@@ -86,6 +87,10 @@ int srgpt_rmsnorm_bf16(const void* x, int ldx, const void* weight, void* y, int 
  * (HF SiglipVisionEmbeddings; call site siglip_encoder.py:11-16).  images: [n, 3, R, R] fp32 or
  * bf16 (src_is_bf16) -> A: [n*(R/ps)^2, ldk] bf16, column = c*ps*ps + ky*ps + kx, zero padded to ldk. */
 int srgpt_patchify_bf16(const void* images, int src_is_bf16, void* A, int n, int R, int ps, int ldk, void* stream);
+/* CLIP embeddings (HF CLIPVisionEmbeddings.forward; call site clip_encoder.py:11): out [n_img, T + 1, D] =
+ * cat([class_embedding, patch_embeds[n]]) + position_embedding, one element-type add per value like torch's. */
+int srgpt_clip_embed_bf16(const void* patch_embeds, const void* class_embedding, const void* position_embedding, void* out,
+                          int n_img, int T, int D, void* stream);
 /* Embedding splice (llava_arch.py:434-539): out[r,:] = src[src_id[r]][src_row[r],:] for the four
  * sources (0 = token embedding table, 1 = image features, 2 = mask embeds, 3 = depth embeds).
  * The (src_id,src_row) plan is built on the host from input_ids. */
@@ -187,10 +192,11 @@ int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* s
 int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream);
 /* Temperature + nucleus (top-p) sampling of one token from fp32 logits [V] (sampling.cu): replaces HF's TemperatureLogitsWarper /
  * TopKLogitsWarper / TopPLogitsWarper / multinomial behind do_sample=True (llava/eval/eval_spatial.py:231-236, llava/eval/model_vqa.py:72-78).
- * params = device float[3] {temperature, top_p, top_k (0 = off)}; the draw is a counter-based generator of (seed, *step + step_offset).
+ * params = device float[3] {temperature, top_p, top_k (0 = off)}; seed = device u64; the draw is a counter-based generator of
+ * (*seed, *step + step_offset) - both read at run time, so a captured decode graph serves every request.
  * Writes out_ids[*step + step_offset] and, when given, next_x[K] = embed_table[token].  Call it right after
  * srgpt_lm_head_argmax_bf16 / srgpt_llama_decode_step_bf16 (which advanced *step) with step_offset = -1. */
-int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed, const int* step, int step_offset,
+int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, const unsigned long long* seed, const int* step, int step_offset,
                            long long* out_ids, const void* embed_table, void* next_x, int K, void* stream);
 
 /* ---- host preprocessing on the GPU (preprocess.cu; llava/mm_utils.py:421-542: process_images / process_regions) ----------
@@ -262,6 +268,11 @@ typedef struct {
 /* n_layers SigLIP encoder layers in place on x [n_img*T, D] (HF SiglipEncoderLayer; call site vision_encoder.py:119-130). */
 int srgpt_siglip_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
                              void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps, void* stream);
+/* The same pre-LN encoder layer with the MLP activation as a parameter (fc1_epilogue = SRGPT_EPI_BIAS_GELU_TANH: SigLIP,
+ * SRGPT_EPI_BIAS_QUICK_GELU: CLIP (HF CLIPEncoderLayer; call site clip_encoder.py:11, vision_encoder.py:119-130),
+ * SRGPT_EPI_BIAS_GELU_ERF: hidden_act "gelu").  T counts ALL rows of an image (CLIP: patches + the class token). */
+int srgpt_vit_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv, void* ws_attn,
+                          void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps, int fc1_epilogue, void* stream);
 /* n_layers Llama decoder layers over the prompt rows x [S, H] in place, appending K/V to the paged cache
  * (LlamaDecoderLayer.forward, modeling_llama.py:623-684).  n_seqs == 1, cu_seqlens == NULL: one prompt of S rows.
  * Otherwise S is the total row count of n_seqs prompts packed back to back (cu_seqlens int32 [n_seqs+1] on the

@@ -52,6 +52,9 @@ class OracleConfig:
     v_inter: int = 4304
     v_eps: float = 1e-6
     select_layer: int = -2  # scripts/srgpt/*/3_sft.sh:29
+    v_type: str = "siglip"  # "clip": HF CLIPVisionModel behind CLIPVisionTower (clip_encoder.py:8-13)
+    v_act: str = "gelu_pytorch_tanh"  # CLIP: "quick_gelu"
+    select_feature: str = "cls_patch"  # CLIP: "patch" (vision_encoder.py:28-31)
     # llm (Llama)
     hidden: int = 4096
     layers: int = 32
@@ -111,8 +114,14 @@ def make_weights(cfg: OracleConfig, seed: int = 0, std: float = 0.02, nontrivial
     D, I = cfg.v_hidden, cfg.v_inter
     vt: Dict[str, torch.Tensor] = {}
     vt["vision_model.embeddings.patch_embedding.weight"] = rn(D, 3, cfg.patch_size, cfg.patch_size)
-    vt["vision_model.embeddings.patch_embedding.bias"] = rn(D)
-    vt["vision_model.embeddings.position_embedding.weight"] = rn(cfg.grid * cfg.grid, D)
+    if cfg.v_type == "clip":  # HF CLIPVisionEmbeddings / CLIPVisionTransformer parameter names (bias-free conv, "pre_layrnorm" sic)
+        vt["vision_model.embeddings.class_embedding"] = rn(D)
+        vt["vision_model.embeddings.position_embedding.weight"] = rn(cfg.grid * cfg.grid + 1, D)
+        vt["vision_model.pre_layrnorm.weight"] = norm_w(D)
+        vt["vision_model.pre_layrnorm.bias"] = norm_b(D)
+    else:
+        vt["vision_model.embeddings.patch_embedding.bias"] = rn(D)
+        vt["vision_model.embeddings.position_embedding.weight"] = rn(cfg.grid * cfg.grid, D)
     for i in range(cfg.v_layers):
         p = f"vision_model.encoder.layers.{i}."
         vt[p + "layer_norm1.weight"] = norm_w(D)
@@ -178,10 +187,62 @@ def gelu_tanh(x: torch.Tensor) -> torch.Tensor:
     return F.gelu(x, approximate="tanh")
 
 
+def quick_gelu(x: torch.Tensor) -> torch.Tensor:
+    """HF ``QuickGELUActivation`` (transformers 4.37.2 activations.py): three ops in the tensor's dtype."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def clip_tower_forward(cfg: OracleConfig, w: Dict[str, torch.Tensor], images: torch.Tensor,
+                       dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """``CLIPVisionTower`` (clip_encoder.py:8-13) through ``VisionTower.forward`` + ``feature_select`` (vision_encoder.py:26-34,
+    115-132).  The arithmetic is third-party: HF ``CLIPVisionModel`` (transformers 4.37.2, modeling_clip.py) - bias-free patch
+    convolution, class token, position embedding, ``pre_layrnorm``, pre-LN encoder layers whose attention scales q BEFORE q k^T
+    (``q_proj(x) * scale``) and takes the softmax in the tensor's dtype, ``quick_gelu`` MLP; ``hidden_states[select_layer]`` with
+    the class-token row dropped for "patch"."""
+    W = lambda k: w[k].to(dtype)  # noqa: E731
+    x = images.to(dtype)
+    N = x.shape[0]
+    D, ps = cfg.v_hidden, cfg.patch_size
+    x = F.conv2d(x, W("vision_model.embeddings.patch_embedding.weight"), None, stride=ps)
+    x = x.flatten(2).transpose(1, 2)
+    cls = W("vision_model.embeddings.class_embedding").expand(N, 1, -1)
+    x = torch.cat([cls, x], dim=1) + W("vision_model.embeddings.position_embedding.weight")[None]
+    x = F.layer_norm(x, (D,), W("vision_model.pre_layrnorm.weight"), W("vision_model.pre_layrnorm.bias"), cfg.v_eps)
+    nh, hd = cfg.v_heads, cfg.v_head_dim
+    scale = hd ** -0.5
+    act = {"quick_gelu": quick_gelu, "gelu": F.gelu, "gelu_pytorch_tanh": gelu_tanh}[cfg.v_act]
+    for i in range(cfg.n_tower_layers):
+        p = f"vision_model.encoder.layers.{i}."
+        r = x
+        h = F.layer_norm(x, (D,), W(p + "layer_norm1.weight"), W(p + "layer_norm1.bias"), cfg.v_eps)
+        q = F.linear(h, W(p + "self_attn.q_proj.weight"), W(p + "self_attn.q_proj.bias")) * scale
+        k = F.linear(h, W(p + "self_attn.k_proj.weight"), W(p + "self_attn.k_proj.bias"))
+        v = F.linear(h, W(p + "self_attn.v_proj.weight"), W(p + "self_attn.v_proj.bias"))
+        q = q.view(N, -1, nh, hd).transpose(1, 2)
+        k = k.view(N, -1, nh, hd).transpose(1, 2)
+        v = v.view(N, -1, nh, hd).transpose(1, 2)
+        att = F.softmax(torch.matmul(q, k.transpose(-1, -2)), dim=-1)
+        o = torch.matmul(att, v).transpose(1, 2).reshape(N, -1, D)
+        o = F.linear(o, W(p + "self_attn.out_proj.weight"), W(p + "self_attn.out_proj.bias"))
+        x = r + o
+        r = x
+        h = F.layer_norm(x, (D,), W(p + "layer_norm2.weight"), W(p + "layer_norm2.bias"), cfg.v_eps)
+        h = act(F.linear(h, W(p + "mlp.fc1.weight"), W(p + "mlp.fc1.bias")))
+        h = F.linear(h, W(p + "mlp.fc2.weight"), W(p + "mlp.fc2.bias"))
+        x = r + h
+    if cfg.select_feature == "patch":
+        x = x[:, 1:]
+    elif cfg.select_feature != "cls_patch":
+        raise ValueError(f"Unexpected select feature: {cfg.select_feature}")  # vision_encoder.py:33
+    return x
+
+
 def vision_tower_forward(cfg: OracleConfig, w: Dict[str, torch.Tensor], images: torch.Tensor,
                          dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``VisionTower.forward`` + ``feature_select`` (vision_encoder.py:26-34,115-132):
     SigLIP forward, returns ``hidden_states[select_layer]`` with all T tokens ("cls_patch")."""
+    if cfg.v_type == "clip":
+        return clip_tower_forward(cfg, w, images, dtype)
     W = lambda k: w[k].to(dtype)  # noqa: E731
     x = images.to(dtype)
     N = x.shape[0]

@@ -38,6 +38,7 @@ SIGNATURES = {
     "srgpt_downsample_layernorm_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, vp]),
     "srgpt_rmsnorm_bf16": (ci, [vp, ci, vp, vp, ci, ci, ci, cf, vp]),
     "srgpt_patchify_bf16": (ci, [vp, ci, vp, ci, ci, ci, ci, vp]),
+    "srgpt_clip_embed_bf16": (ci, [vp, vp, vp, vp, ci, ci, ci, vp]),
     "srgpt_splice_rows_bf16": (ci, [vp, vp, vp, vp, vp, vp, vp, ci, ci, vp]),
     "srgpt_mask_weights_workspace": (cll, [ci, ci, ci]),
     "srgpt_mask_weights": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, ci, vp]),
@@ -56,7 +57,7 @@ SIGNATURES = {
     "srgpt_lm_head_argmax_bf16": (ci, [vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp, vp, vp]),
     "srgpt_argmax_f32": (ci, [vp, ci, ci, vp, vp]),
     "srgpt_argmax_bf16": (ci, [vp, ci, ci, ci, vp, vp]),
-    "srgpt_sample_top_p_f32": (ci, [vp, ci, vp, C.c_ulonglong, vp, ci, vp, vp, vp, ci, vp]),
+    "srgpt_sample_top_p_f32": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
     "srgpt_resample_u8": (ci, [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
     "srgpt_u8_to_normalized_chw": (ci, [vp, vp, ci, ci, ci, C.c_double, vp, vp, ci, vp]),
     "srgpt_resize_nearest_u8": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "srgpt_tp_allreduce_residual_bf16": (ci, [vp, ci, ci, cll, ci, vp, vp, vp, ci, vp]),
     "srgpt_tp_allgather_pick_token": (ci, [vp, ci, ci, cll, ci, vp, vp, vp, ci, vp, vp, vp, vp]),
     "srgpt_siglip_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]),
+    "srgpt_vit_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, ci, vp]),
     "srgpt_llama_prefill_layers_bf16": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, ci, vp, ci, ci, vp]),
     "srgpt_llama_decode_step_bf16": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, ci, vp, vp, ci, vp, vp, vp, vp,
                                           vp, vp]),

@@ -62,7 +62,15 @@ def _sub_path(root: str, top: Dict[str, Any], key: str) -> str:
 
 
 def _vision_config(d: Dict[str, Any]) -> VisionConfig:
-    d = d.get("vision_config", d)  # a full SiglipConfig nests the vision part
+    arch = " ".join(d.get("architectures") or []).lower()
+    d = d.get("vision_config", d)  # a full SiglipConfig / CLIPConfig nests the vision part
+    mt = d.get("model_type") or ""
+    is_clip = ("clip" in arch or "clip" in mt) and "siglip" not in (arch + mt)  # multimodal_encoder/builder.py:38-47 keys on the architecture name
+    if is_clip:
+        return VisionConfig(image_size=d.get("image_size", 224), patch_size=d.get("patch_size", 32), hidden_size=d.get("hidden_size", 768),
+                            num_hidden_layers=d.get("num_hidden_layers", 12), num_attention_heads=d.get("num_attention_heads", 12),
+                            intermediate_size=d.get("intermediate_size", 3072), layer_norm_eps=d.get("layer_norm_eps", 1e-5),
+                            hidden_act=d.get("hidden_act", "quick_gelu"), model_type="clip_vision_model")
     return VisionConfig(image_size=d.get("image_size", 384), patch_size=d.get("patch_size", 14), hidden_size=d.get("hidden_size", 1152),
                         num_hidden_layers=d.get("num_hidden_layers", 27), num_attention_heads=d.get("num_attention_heads", 16),
                         intermediate_size=d.get("intermediate_size", 4304), layer_norm_eps=d.get("layer_norm_eps", 1e-6),

@@ -11,7 +11,9 @@ from typing import Any, Dict, Optional
 
 @dataclass
 class VisionConfig:
-    """SigLIP vision transformer (HF ``SiglipVisionConfig`` field names)."""
+    """SigLIP or CLIP vision transformer (HF ``SiglipVisionConfig`` / ``CLIPVisionConfig`` field names).  ``model_type``
+    "clip_vision_model" adds the class token, the pre-layernorm and the bias-free patch convolution of HF CLIPVisionModel
+    (clip_encoder.py:8-13)."""
     image_size: int = 448
     patch_size: int = 14
     hidden_size: int = 1152
@@ -20,10 +22,20 @@ class VisionConfig:
     intermediate_size: int = 4304
     layer_norm_eps: float = 1e-6
     hidden_act: str = "gelu_pytorch_tanh"
+    model_type: str = "siglip_vision_model"
 
     @property
     def grid(self) -> int:
         return self.image_size // self.patch_size
+
+    @property
+    def is_clip(self) -> bool:
+        return "clip" in self.model_type and "siglip" not in self.model_type
+
+    @property
+    def tokens(self) -> int:
+        """Rows per image inside the encoder (CLIP: patches + the class token)."""
+        return self.grid * self.grid + (1 if self.is_clip else 0)
 
     @property
     def head_dim(self) -> int:

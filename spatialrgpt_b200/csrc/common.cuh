@@ -160,6 +160,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.0f + t);
 }
+// CLIP's "quick_gelu" (HF QuickGELUActivation: input * torch.sigmoid(1.702 * input)) - three element-type torch ops, so the
+// product 1.702 x and the sigmoid are each rounded to the element type before the final multiply (x is already rounded)
+__device__ __forceinline__ float quick_gelu(float x) {
+  const float t = bf16_round(1.702f * x);
+  const float s = bf16_round(1.0f / (1.0f + __expf(-t)));
+  return x * s;
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 }  // namespace srgpt

@@ -180,6 +180,9 @@ __device__ __forceinline__ void apply_epilogue(float* v /*32 accumulators*/, con
   } else if (EPI == SRGPT_EPI_BIAS_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(bf16_round(v[j]));
+  } else if (EPI == SRGPT_EPI_BIAS_QUICK_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(bf16_round(v[j]));
   } else if (EPI == SRGPT_EPI_BIAS_RESIDUAL) {
     if (RES_STAGED) {
       // all 32 columns come from the TMA-loaded residual tile (columns beyond N were zero-filled and are clipped by the store)
@@ -1496,7 +1499,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
   SRGPT_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0);  // 16-byte global strides for TMA
   SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
   SRGPT_CHECK_ARG((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-  SRGPT_CHECK_ARG(epilogue >= SRGPT_EPI_NONE && epilogue <= SRGPT_EPI_SWIGLU);
+  SRGPT_CHECK_ARG(epilogue >= SRGPT_EPI_NONE && epilogue <= SRGPT_EPI_BIAS_QUICK_GELU);
   if (epilogue == SRGPT_EPI_SWIGLU) {
     SRGPT_CHECK_ARG((N % 2) == 0 && !out_fp32 && ldc >= N / 2 && (ldc % 8) == 0);
   } else {
@@ -1527,6 +1530,7 @@ extern "C" __attribute__((visibility("default"))) int srgpt_gemm_bf16(const void
     case SRGPT_EPI_BIAS_GELU_ERF: return gemm::launch<SRGPT_EPI_BIAS_GELU_ERF>(A, lda, W, ldw, p, st);
     case SRGPT_EPI_BIAS_RESIDUAL: return gemm::launch<SRGPT_EPI_BIAS_RESIDUAL>(A, lda, W, ldw, p, st);
     case SRGPT_EPI_SWIGLU: return gemm::launch<SRGPT_EPI_SWIGLU>(A, lda, W, ldw, p, st);
+    case SRGPT_EPI_BIAS_QUICK_GELU: return gemm::launch<SRGPT_EPI_BIAS_QUICK_GELU>(A, lda, W, ldw, p, st);
   }
   return SRGPT_ERR_INVALID;
 }

@@ -16,11 +16,12 @@ using namespace srgpt;
 static inline const char* cptr(const void* p, size_t byte_off) { return reinterpret_cast<const char*>(p) + byte_off; }
 static inline char* mptr(void* p, size_t byte_off) { return reinterpret_cast<char*>(p) + byte_off; }
 
-extern "C" __attribute__((visibility("default"))) int srgpt_siglip_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
-                                                                                 void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps,
-                                                                                 void* stream) {
+extern "C" __attribute__((visibility("default"))) int srgpt_vit_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
+                                                                              void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps,
+                                                                              int fc1_epilogue, void* stream) {
   SRGPT_CHECK_ARG(x && layers && ws_h && ws_qkv && ws_attn && ws_mlp && n_layers >= 0 && n_img > 0 && T > 0 && D > 0 && heads > 0 && I > 0);
   SRGPT_CHECK_ARG(D % heads == 0);
+  SRGPT_CHECK_ARG(fc1_epilogue == SRGPT_EPI_BIAS_GELU_TANH || fc1_epilogue == SRGPT_EPI_BIAS_GELU_ERF || fc1_epilogue == SRGPT_EPI_BIAS_QUICK_GELU);
   const int M = n_img * T, hd = D / heads;
   const float scale = 1.0f / sqrtf((float)hd);
   for (int l = 0; l < n_layers; ++l) {
@@ -31,10 +32,16 @@ extern "C" __attribute__((visibility("default"))) int srgpt_siglip_layers_bf16(v
                                            heads, heads, hd, scale, 0, stream));
     SRGPT_TRY(srgpt_gemm_bf16(ws_attn, D, w.out_w, D, x, D, M, D, D, w.out_b, x, D, 0, SRGPT_EPI_BIAS_RESIDUAL, 0, stream));
     SRGPT_TRY(srgpt_layernorm_bf16(x, D, w.ln2_w, w.ln2_b, ws_h, D, M, D, eps, 0, stream));
-    SRGPT_TRY(srgpt_gemm_bf16(ws_h, D, w.fc1_w, D, ws_mlp, I, M, I, D, w.fc1_b, nullptr, 0, 0, SRGPT_EPI_BIAS_GELU_TANH, 0, stream));
+    SRGPT_TRY(srgpt_gemm_bf16(ws_h, D, w.fc1_w, D, ws_mlp, I, M, I, D, w.fc1_b, nullptr, 0, 0, fc1_epilogue, 0, stream));
     SRGPT_TRY(srgpt_gemm_bf16(ws_mlp, I, w.fc2_w, I, x, D, M, D, I, w.fc2_b, x, D, 0, SRGPT_EPI_BIAS_RESIDUAL, 0, stream));
   }
   return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_siglip_layers_bf16(void* x, const srgpt_siglip_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,
+                                                                                 void* ws_attn, void* ws_mlp, int n_img, int T, int D, int heads, int I, float eps,
+                                                                                 void* stream) {
+  return srgpt_vit_layers_bf16(x, layers, n_layers, ws_h, ws_qkv, ws_attn, ws_mlp, n_img, T, D, heads, I, eps, SRGPT_EPI_BIAS_GELU_TANH, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int srgpt_llama_prefill_layers_bf16(void* x, const srgpt_llama_layer_weights* layers, int n_layers, void* ws_h, void* ws_qkv,

@@ -202,6 +202,26 @@ __global__ void patchify_kernel(const SrcT* __restrict__ img, bf16* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// CLIP embeddings: out[n, 0] = cls + pos[0]; out[n, 1 + t] = patch[n, t] + pos[1 + t]   (one element-type add, like torch's)
+// ---------------------------------------------------------------------------------------------
+__global__ void clip_embed_kernel(const bf16* __restrict__ patch, const bf16* __restrict__ cls, const bf16* __restrict__ pos,
+                                  bf16* __restrict__ out, int T, int D) {
+  const int row = blockIdx.x;  // n * (T + 1) + s
+  const int n = row / (T + 1), s = row % (T + 1);
+  const uint4* a = reinterpret_cast<const uint4*>(s == 0 ? cls : patch + ((size_t)n * T + (s - 1)) * D);
+  const uint4* b = reinterpret_cast<const uint4*>(pos + (size_t)s * D);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * D);
+  for (int c = threadIdx.x; c < (D >> 3); c += blockDim.x) {
+    float fa[8], fb[8];
+    unpack8(a[c], fa);
+    unpack8(b[c], fb);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) fa[t] += fb[t];
+    dst[c] = pack8(fa);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // splice: out[r,:] = src[src_id[r]][src_row[r],:]
 // ---------------------------------------------------------------------------------------------
 __global__ void splice_kernel(const bf16* s0, const bf16* s1, const bf16* s2, const bf16* s3, const int* __restrict__ src_id,
@@ -377,6 +397,18 @@ extern "C" __attribute__((visibility("default"))) int srgpt_patchify_bf16(const 
     patchify_kernel<bf16><<<rows, 128, 0, st>>>(reinterpret_cast<const bf16*>(images), reinterpret_cast<bf16*>(A), R, ps, ldk);
   else
     patchify_kernel<float><<<rows, 128, 0, st>>>(reinterpret_cast<const float*>(images), reinterpret_cast<bf16*>(A), R, ps, ldk);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int srgpt_clip_embed_bf16(const void* patch_embeds, const void* class_embedding, const void* position_embedding,
+                                                                               void* out, int n_img, int T, int D, void* stream) {
+  SRGPT_CHECK_ARG(patch_embeds && class_embedding && position_embedding && out && n_img > 0 && T > 0 && D > 0 && (D % 8) == 0);
+  SRGPT_CHECK_ARG(((reinterpret_cast<uintptr_t>(patch_embeds) | reinterpret_cast<uintptr_t>(class_embedding) | reinterpret_cast<uintptr_t>(position_embedding) |
+                    reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  clip_embed_kernel<<<n_img * (T + 1), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(patch_embeds), reinterpret_cast<const bf16*>(class_embedding), reinterpret_cast<const bf16*>(position_embedding),
+      reinterpret_cast<bf16*>(out), T, D);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

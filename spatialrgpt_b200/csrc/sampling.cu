@@ -45,9 +45,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   return x ^ (x >> 31);
 }
 
-// params = {temperature, top_p, top_k (0 = off)} in device memory, so one captured CUDA graph serves any setting
+// params = {temperature, top_p, top_k (0 = off)} and the seed live in device memory, so one captured CUDA graph serves any request
 __global__ void __launch_bounds__(THREADS)
-sample_top_p_kernel(const float* __restrict__ logits, int V, const float* __restrict__ params, unsigned long long seed, const int* __restrict__ step,
+sample_top_p_kernel(const float* __restrict__ logits, int V, const float* __restrict__ params, const unsigned long long* __restrict__ seed_ptr, const int* __restrict__ step,
                     int step_offset, long long* __restrict__ out_ids, const bf16* __restrict__ embed_table, bf16* __restrict__ next_x, int K) {
   __shared__ float red[32];
   __shared__ float s_scan[THREADS];
@@ -111,7 +111,7 @@ sample_top_p_kernel(const float* __restrict__ logits, int V, const float* __rest
 
   // draw
   const unsigned long long ctr = (unsigned long long)(*step + step_offset);
-  const unsigned long long r = splitmix64(seed ^ splitmix64(ctr));
+  const unsigned long long r = splitmix64(*seed_ptr ^ splitmix64(ctr));
   const float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f) * mass;  // (0, mass)
   float local = 0.f;
   for (int i = lo; i < hi; ++i) {
@@ -177,12 +177,13 @@ sample_top_p_kernel(const float* __restrict__ logits, int V, const float* __rest
 using namespace srgpt;
 
 // Overwrites out_ids[*step + step_offset] (and, when given, next_x = embed_table[token]) with a token sampled from
-// softmax(logits / temperature) restricted to its top-p nucleus.  `params` = device float[3] {temperature, top_p, top_k (0 = off)}.
+// softmax(logits / temperature) restricted to its top-p nucleus.  `params` = device float[3] {temperature, top_p, top_k (0 = off)},
+// `seed` = device u64 (read at run time: a captured graph must not freeze the seed of the request it was captured under).
 // Called right after srgpt_lm_head_argmax_bf16 (which already advanced *step): step_offset = -1.
-extern "C" __attribute__((visibility("default"))) int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, unsigned long long seed,
+extern "C" __attribute__((visibility("default"))) int srgpt_sample_top_p_f32(const float* logits, int V, const float* params, const unsigned long long* seed,
                                                                              const int* step, int step_offset, long long* out_ids,
                                                                              const void* embed_table, void* next_x, int K, void* stream) {
-  SRGPT_CHECK_ARG(logits && params && step && out_ids && V > 0);
+  SRGPT_CHECK_ARG(logits && params && seed && step && out_ids && V > 0);
   SRGPT_CHECK_ARG((embed_table == nullptr) == (next_x == nullptr));
   SRGPT_CHECK_ARG(embed_table == nullptr || ((K % 8) == 0 && K > 0 && (reinterpret_cast<uintptr_t>(embed_table) & 15) == 0 &&
                                              (reinterpret_cast<uintptr_t>(next_x) & 15) == 0));

@@ -119,6 +119,7 @@ class LlamaDecoder:
         self.sample_params = torch.tensor([1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
         self.sample_logits: Optional[torch.Tensor] = None
         self.sample_seed = 0
+        self.sample_seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)  # device copy: the captured graph reads the seed at run time
 
     # ---------------------------------------------------------------------------------------------
     @ops.in_own_dtype
@@ -218,7 +219,7 @@ class LlamaDecoder:
                               self.sin, self.pos, self.active_pt, PAGE_SIZE, w.norm, w.lm_head, w.embed, self.lm_ws,
                               self.out_ids, self.step, logits_out)
         if sample:  # replaces the greedy id / next embedding row the finalize kernel just wrote (step already advanced)
-            ops.sample_top_p(logits_out, self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
+            ops.sample_top_p(logits_out, self.sample_params, self.sample_seed_dev, self.step, -1, self.out_ids, w.embed, self.h)
 
     def _sample_buffer(self) -> torch.Tensor:
         if self.sample_logits is None:
@@ -258,8 +259,12 @@ class LlamaDecoder:
             raise ValueError(f"sampling needs temperature > 0, 0 < top_p <= 1 and top_k >= 0, got temperature={t}, top_p={p}, top_k={k}")
         self.sample_params.copy_(torch.tensor([t, p, float(k)], dtype=torch.float32))
         seed = sampling.get("seed")
-        self.sample_seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self._set_seed(int(torch.initial_seed() if seed is None else seed))
         return True
+
+    def _set_seed(self, seed: int) -> None:
+        self.sample_seed = seed & 0x7FFFFFFFFFFFFFFF
+        self.sample_seed_dev.copy_(torch.tensor([self.sample_seed], dtype=torch.int64))
 
     @torch.no_grad()
     @ops.in_own_dtype
@@ -292,7 +297,7 @@ class LlamaDecoder:
         ops.lm_head_argmax(hidden[S - 1], w.lm_head, w.norm, d.rms_norm_eps, self.lm_ws, self.out_ids, self.step, self.pos,
                            embed_table=w.embed, next_x=self.h, logits_out=first_logits)
         if sample:
-            ops.sample_top_p(first_logits, self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
+            ops.sample_top_p(first_logits, self.sample_params, self.sample_seed_dev, self.step, -1, self.out_ids, w.embed, self.h)
         return self._decode_loop(seq, 1, max_new_tokens, eos, stopping_fn, use_graph, logits, sample)
 
     def _decode_loop(self, seq: int, n: int, max_new_tokens: int, eos, stopping_fn, use_graph: bool, logits, sample: bool = False):
@@ -513,8 +518,8 @@ class LlamaDecoder:
             self.pos.fill_(seq_lens[b])
             self.step.fill_(1)
             if sample:  # re-draw the first token of this sequence from its logits row (a different draw per sequence: the seed moves)
-                self.sample_seed = (self.sample_seed + 0x9E3779B97F4A7C15 * (b + 1)) & 0x7FFFFFFFFFFFFFFF
-                ops.sample_top_p(lg[b].float().contiguous(), self.sample_params, self.sample_seed, self.step, -1, self.out_ids, w.embed, self.h)
+                self._set_seed(self.sample_seed + 0x9E3779B97F4A7C15 * (b + 1))
+                ops.sample_top_p(lg[b].float().contiguous(), self.sample_params, self.sample_seed_dev, self.step, -1, self.out_ids, w.embed, self.h)
             r = self._decode_loop(b, 1, max_new_tokens, eos, stopping_fn, use_graph, logits, sample)
             if return_logits:
                 outs.append(r[0]); all_logits.append(r[1])

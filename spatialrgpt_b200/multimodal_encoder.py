@@ -1,8 +1,9 @@
-"""Vision tower: SigLIP forward on the sm_100a kernels.
+"""Vision tower: SigLIP / CLIP forward on the sm_100a kernels.
 
 Mirrors ``VisionTower.forward`` + ``feature_select`` (llava/model/multimodal_encoder/
-vision_encoder.py:26-34,115-132) and ``SiglipVisionTower`` (siglip_encoder.py:7-17): returns
-``hidden_states[select_layer]`` with all T patch tokens ("cls_patch"; SigLIP has no CLS token).
+vision_encoder.py:26-34,115-132), ``SiglipVisionTower`` (siglip_encoder.py:7-17) and ``CLIPVisionTower``
+(clip_encoder.py:8-13): returns ``hidden_states[select_layer]`` - all rows for "cls_patch" (SigLIP has no
+class token), the rows after the class token for "patch" (CLIP; vision_encoder.py:28-29).
 Only the layers that output depends on are executed (select_layer=-2 -> L-1 layers; the reference
 runs all L layers, the post-layernorm and the pooling head and throws them away).
 """
@@ -34,8 +35,12 @@ class VisionTower:
         self.select_feature = cfg.mm_vision_select_feature
         if self.select_feature not in ("cls_patch", "patch"):
             raise ValueError(f"Unexpected select feature: {self.select_feature}")  # vision_encoder.py:33
-        if self.select_feature == "patch":
-            raise NotImplementedError("'patch' drops a CLS token; SigLIP has none (CLIP tower is a next-round item)")
+        acts = {"gelu_pytorch_tanh": ops.EPI_BIAS_GELU_TANH, "quick_gelu": ops.EPI_BIAS_QUICK_GELU, "gelu": ops.EPI_BIAS_GELU_ERF}
+        if self.vc.hidden_act not in acts:
+            raise NotImplementedError(f"vision hidden_act {self.vc.hidden_act!r} (have {sorted(acts)})")
+        self._fc1_epilogue = acts[self.vc.hidden_act]
+        if self.vc.is_clip and (w.cls_emb is None or w.pre_ln_w is None):
+            raise ValueError("a CLIP tower needs class_embedding and pre_layrnorm weights")
         self.n_layers = tower_layers_needed(self.vc.num_hidden_layers, self.select_layer)
         if len(w.layers) < self.n_layers:
             raise ValueError(f"need {self.n_layers} vision layers, weights hold {len(w.layers)}")
@@ -77,9 +82,18 @@ class VisionTower:
         images = images.contiguous()
         N, T, D, nh, hd = images.shape[0], vc.grid ** 2, vc.hidden_size, vc.num_attention_heads, vc.head_dim
         a = ops.patchify(images, vc.patch_size, patch_ldk(vc.patch_size))
-        x = ops.gemm(a, w.patch_w, bias=w.patch_b, residual=w.pos_emb, epilogue=ops.EPI_BIAS_RESIDUAL, res_row_mod=T)
-        ops.siglip_layers(x, self._layer_array, self.n_layers, N, T, D, nh, vc.intermediate_size, vc.layer_norm_eps)
-        return x.view(N, T, D)
+        if vc.is_clip:
+            # CLIPVisionEmbeddings: bias-free convolution, class token prepended, position embedding added; then pre_layrnorm
+            x = ops.clip_embed(ops.gemm(a, w.patch_w), w.cls_emb, w.pos_emb, N, T)
+            x = ops.layernorm(x, w.pre_ln_w, w.pre_ln_b, vc.layer_norm_eps, out=x)
+            T += 1
+        else:
+            x = ops.gemm(a, w.patch_w, bias=w.patch_b, residual=w.pos_emb, epilogue=ops.EPI_BIAS_RESIDUAL, res_row_mod=T)
+        ops.siglip_layers(x, self._layer_array, self.n_layers, N, T, D, nh, vc.intermediate_size, vc.layer_norm_eps, self._fc1_epilogue)
+        x = x.view(N, T, D)
+        if self.select_feature == "patch":  # vision_encoder.py:28-29: drop row 0 (a plain strided device copy)
+            x = x[:, 1:].contiguous()
+        return x
 
     __call__ = forward
 

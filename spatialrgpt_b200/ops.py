@@ -21,7 +21,7 @@ def check(rc: int, what: str) -> None:
     _check_rc(rc, what)
     LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GELU_ERF, EPI_BIAS_RESIDUAL, EPI_SWIGLU = range(6)
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU_TANH, EPI_BIAS_GELU_ERF, EPI_BIAS_RESIDUAL, EPI_SWIGLU, EPI_BIAS_QUICK_GELU = range(7)
 GEMV_PLAIN, GEMV_SWIGLU, GEMV_QKV_ROPE = range(3)
 ORDER_ROWMAJOR, ORDER_NESTED = 0, 2
 
@@ -489,16 +489,20 @@ def lm_head_argmax(x: torch.Tensor, w: torch.Tensor, norm_weight: Optional[torch
                                                 _stream()), "srgpt_lm_head_argmax_bf16")
 
 
-def sample_top_p(logits: torch.Tensor, params: torch.Tensor, seed: int, step: torch.Tensor, step_offset: int, out_ids: torch.Tensor,
+def sample_top_p(logits: torch.Tensor, params: torch.Tensor, seed, step: torch.Tensor, step_offset: int, out_ids: torch.Tensor,
                  embed_table: Optional[torch.Tensor] = None, next_x: Optional[torch.Tensor] = None) -> None:
     """One token from softmax(logits / T) restricted to its top-p nucleus -> out_ids[step + step_offset] (and next_x = embed row).
-    ``params`` = device float32 [temperature, top_p, top_k (0 = off)]; ``step`` = device int32 [1]."""
+    ``params`` = device float32 [temperature, top_p, top_k (0 = off)]; ``step`` = device int32 [1]; ``seed`` = device int64 [1]
+    (read by the kernel at run time - graph-capturable), or a Python int for one-off eager calls."""
+    if not isinstance(seed, torch.Tensor):
+        seed = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=logits.device)
+    _need(seed, torch.int64, "sample_top_p.seed")
     _need(logits, torch.float32, "sample_top_p.logits"); _need(params, torch.float32, "sample_top_p.params")
     _need(step, torch.int32, "sample_top_p.step"); _need(out_ids, torch.int64, "sample_top_p.out_ids")
     if logits.dim() != 1 or not logits.is_contiguous() or params.numel() < 3:
         raise SrgptError("sample_top_p: logits must be a contiguous fp32 vector [V] and params [temperature, top_p, top_k]")
     K = 0 if embed_table is None else embed_table.shape[1]
-    check(_lib.load().srgpt_sample_top_p_f32(_p(logits), logits.numel(), _p(params), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(step), step_offset,
+    check(_lib.load().srgpt_sample_top_p_f32(_p(logits), logits.numel(), _p(params), _p(seed), _p(step), step_offset,
                                              _p(out_ids), _p(embed_table), _p(next_x), K, _stream()), "srgpt_sample_top_p_f32")
 
 
@@ -544,8 +548,21 @@ def make_llama_layer_array(layers, kv_pages_per_layer):
     return arr
 
 
-def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: int, D: int, heads: int, I: int, eps: float) -> torch.Tensor:
-    """n_layers SigLIP encoder layers in place on x [n_img*T, D]."""
+def clip_embed(patch_embeds: torch.Tensor, class_embedding: torch.Tensor, position_embedding: torch.Tensor, n_img: int, T: int) -> torch.Tensor:
+    """[n_img*T, D] patch embeddings -> [n_img*(T+1), D]: class token prepended, position embedding added (CLIPVisionEmbeddings)."""
+    _need(patch_embeds, ELEM(), "clip_embed.patch_embeds")
+    D = patch_embeds.shape[1]
+    if patch_embeds.shape[0] != n_img * T or not patch_embeds.is_contiguous() or tuple(position_embedding.shape) != (T + 1, D):
+        raise SrgptError(f"clip_embed: patch embeds {tuple(patch_embeds.shape)}, position embedding {tuple(position_embedding.shape)}, n_img {n_img}, T {T}")
+    out = torch.empty((n_img * (T + 1), D), dtype=ELEM(), device=patch_embeds.device)
+    check(_lib.load().srgpt_clip_embed_bf16(_p(patch_embeds), _p(class_embedding), _p(position_embedding), _p(out), n_img, T, D, _stream()),
+          "srgpt_clip_embed_bf16")
+    return out
+
+
+def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: int, D: int, heads: int, I: int, eps: float,
+                  fc1_epilogue: int = EPI_BIAS_GELU_TANH) -> torch.Tensor:
+    """n_layers pre-LN ViT encoder layers (SigLIP; CLIP with fc1_epilogue=EPI_BIAS_QUICK_GELU) in place on x [n_img*T, D]."""
     _need(x, ELEM(), "siglip_layers.x")
     _ensure_gemm_workspace(x.device)
     M = n_img * T
@@ -555,8 +572,8 @@ def siglip_layers(x: torch.Tensor, layer_array, n_layers: int, n_img: int, T: in
     ws_attn = torch.empty((M, D), dtype=ELEM(), device=dev)
     ws_mlp = torch.empty((M, I), dtype=ELEM(), device=dev)
     import ctypes
-    check(_lib.load().srgpt_siglip_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
-                                               _p(ws_attn), _p(ws_mlp), n_img, T, D, heads, I, eps, _stream()), "srgpt_siglip_layers_bf16")
+    check(_lib.load().srgpt_vit_layers_bf16(_p(x), ctypes.cast(layer_array, ctypes.c_void_p), n_layers, _p(ws_h), _p(ws_qkv),
+                                            _p(ws_attn), _p(ws_mlp), n_img, T, D, heads, I, eps, fc1_epilogue, _stream()), "srgpt_vit_layers_bf16")
     _count(7 * n_layers)
     return x
 

@@ -54,9 +54,12 @@ class VisionLayerW:
 @dataclass
 class VisionW:
     patch_w: torch.Tensor  # [D, ldk]
-    patch_b: torch.Tensor
-    pos_emb: torch.Tensor  # [T, D]
+    patch_b: Optional[torch.Tensor]  # None for CLIP (bias-free convolution)
+    pos_emb: torch.Tensor  # [T, D]  (CLIP: [T + 1, D], row 0 = the class token's position)
     layers: List[VisionLayerW] = field(default_factory=list)
+    cls_emb: Optional[torch.Tensor] = None   # CLIP: class_embedding [D]
+    pre_ln_w: Optional[torch.Tensor] = None  # CLIP: pre_layrnorm
+    pre_ln_b: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -173,11 +176,17 @@ def from_state_dicts(cfg: LlavaConfig, sd: Dict[str, Dict[str, torch.Tensor]], d
     v, vc = sd["vision_tower"], cfg.vision
     D = vc.hidden_size
     pw = g(v, "vision_model.embeddings.patch_embedding.weight").reshape(D, -1)
-    vision = VisionW(patch_w=_pad_cols(pw, patch_ldk(vc.patch_size)),
-                     patch_b=g(v, "vision_model.embeddings.patch_embedding.bias").contiguous(),
-                     pos_emb=g(v, "vision_model.embeddings.position_embedding.weight").contiguous())
-    if vision.pos_emb.shape[0] != vc.grid * vc.grid:
-        raise ValueError(f"position embedding has {vision.pos_emb.shape[0]} rows, expected {vc.grid ** 2} "
+    if vc.is_clip:  # HF CLIPVisionModel: no conv bias, class token, pre_layrnorm (sic)
+        vision = VisionW(patch_w=_pad_cols(pw, patch_ldk(vc.patch_size)), patch_b=None,
+                         pos_emb=g(v, "vision_model.embeddings.position_embedding.weight").contiguous(),
+                         cls_emb=g(v, "vision_model.embeddings.class_embedding").reshape(-1).contiguous(),
+                         pre_ln_w=g(v, "vision_model.pre_layrnorm.weight"), pre_ln_b=g(v, "vision_model.pre_layrnorm.bias"))
+    else:
+        vision = VisionW(patch_w=_pad_cols(pw, patch_ldk(vc.patch_size)),
+                         patch_b=g(v, "vision_model.embeddings.patch_embedding.bias").contiguous(),
+                         pos_emb=g(v, "vision_model.embeddings.position_embedding.weight").contiguous())
+    if vision.pos_emb.shape[0] != vc.tokens:
+        raise ValueError(f"position embedding has {vision.pos_emb.shape[0]} rows, expected {vc.tokens} "
                          f"(the reference resizes it at training time, vision_encoder.py:36-113)")
     nl = vc.num_hidden_layers if n_tower_layers is None else n_tower_layers
     for i in range(nl):
@@ -256,7 +265,11 @@ def random_init(cfg: LlavaConfig, device, seed: int = 0, std: float = 0.02, n_to
 
     vc, lc = cfg.vision, cfg.llama
     D, I, T = vc.hidden_size, vc.intermediate_size, vc.grid * vc.grid
-    vision = VisionW(patch_w=_pad_cols(rn(D, 3 * vc.patch_size ** 2), patch_ldk(vc.patch_size)), patch_b=rn(D), pos_emb=rn(T, D))
+    if vc.is_clip:
+        vision = VisionW(patch_w=_pad_cols(rn(D, 3 * vc.patch_size ** 2), patch_ldk(vc.patch_size)), patch_b=None, pos_emb=rn(T + 1, D),
+                         cls_emb=rn(D), pre_ln_w=nw(D), pre_ln_b=nb(D))
+    else:
+        vision = VisionW(patch_w=_pad_cols(rn(D, 3 * vc.patch_size ** 2), patch_ldk(vc.patch_size)), patch_b=rn(D), pos_emb=rn(T, D))
     nl = vc.num_hidden_layers if n_tower_layers is None else n_tower_layers
     for _ in range(nl):
         vision.layers.append(VisionLayerW(nw(D), nb(D), rn(3 * D, D, s=2 * std), rn(3 * D), rn(D, D, s=2 * std), rn(D),

@@ -247,9 +247,61 @@ def run_projector_kats():
     print(f"proj_kats -> {path}: {[k for k in arrays if '__w__' in k]}")
 
 
+CLIP_CASE = dict(image_size=56, v_hidden=128, v_layers=4, v_heads=2, v_inter=256, v_eps=1e-5, v_type="clip", v_act="quick_gelu",
+                 select_feature="patch", hidden=256, layers=2, heads=2, kv_heads=1, inter=384, vocab=512, rope_theta=10000.0,
+                 mask_token_id=510, depth_token_id=511)
+CLIP_WEIGHT_SEED = 11
+
+
+@torch.no_grad()
+def run_clip_kat():
+    """The reference's ``VisionTower.forward`` + ``feature_select("patch")`` (vision_encoder.py:26-34,115-132) over stock HF
+    ``CLIPVisionModel`` - what ``CLIPVisionTower`` (clip_encoder.py:8-13) wraps - in fp32, on the oracle's seeded CLIP weights."""
+    ref_shim.install()
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+
+    from llava.model.multimodal_encoder.vision_encoder import VisionTower
+
+    cfg = O.OracleConfig(**CLIP_CASE)
+    sd = O.make_weights(cfg, seed=CLIP_WEIGHT_SEED)
+    vcfg = CLIPVisionConfig(hidden_size=cfg.v_hidden, intermediate_size=cfg.v_inter, num_hidden_layers=cfg.v_layers,
+                            num_attention_heads=cfg.v_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
+                            layer_norm_eps=cfg.v_eps, hidden_act="quick_gelu")
+    vcfg._attn_implementation = "eager"
+    clip = CLIPVisionModel(vcfg).float().eval()
+    missing, unexpected = clip.load_state_dict({k: v.float() for k, v in sd["vision_tower"].items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all("post_layernorm" in k or "position_ids" in k for k in missing), missing
+
+    class Tower(VisionTower):
+        def __init__(self):
+            super().__init__("synthetic", SimpleNamespace(mm_vision_select_layer=cfg.select_layer, mm_vision_select_feature="patch"))
+            self.vision_tower = clip
+            self.is_loaded = True
+
+        @property
+        def dtype(self):
+            return torch.float32
+
+        @property
+        def device(self):
+            return torch.device("cpu")
+
+    g = torch.Generator().manual_seed(77)
+    images = torch.randn(3, 3, cfg.image_size, cfg.image_size, generator=g).to(torch.bfloat16).float()
+    feats = Tower()(images)
+    assert feats.shape == (3, cfg.grid ** 2, cfg.v_hidden)
+    path = os.path.join(HERE, "clip_tower.npz")
+    np.savez_compressed(path, images=images.numpy(), tower_features=feats.numpy(), weight_seed=np.int64(CLIP_WEIGHT_SEED))
+    print(f"clip_tower -> {path}: features {tuple(feats.shape)}, rms {float(feats.pow(2).mean().sqrt()):.4f}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["clip"]:
+        run_clip_kat()
+        sys.exit(0)
     if sys.argv[1:] == ["proj"]:  # only the projector-type fixture (the others regenerate bit-identically but take minutes)
         run_projector_kats()
         sys.exit(0)
@@ -257,3 +309,4 @@ if __name__ == "__main__":
         run_case(n)
     run_maskpool_kats()
     run_projector_kats()
+    run_clip_kat()

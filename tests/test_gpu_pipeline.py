@@ -293,3 +293,76 @@ def test_generate_with_sampling(golden_dir):
     stop_at = s1[2]
     cut = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, eos_token_id=stop_at, **args)[0].tolist()
     assert cut == s1[: s1.index(stop_at) + 1]
+
+
+# ---- CLIP tower (clip_encoder.py:8-13; a6 / f4) ----------------------------------------------------------------------------------
+def _clip_model(dtype=torch.bfloat16, seed=None):
+    from spatialrgpt_b200 import LlavaConfig, LlamaDims, VisionConfig
+    from spatialrgpt_b200.llava_llama import LlavaLlamaModel
+    from spatialrgpt_b200.weights import from_state_dicts
+    from tests.golden.make_golden import CLIP_CASE, CLIP_WEIGHT_SEED
+
+    oc = O.OracleConfig(**CLIP_CASE)
+    cfg = LlavaConfig(
+        vision=VisionConfig(image_size=oc.image_size, patch_size=oc.patch_size, hidden_size=oc.v_hidden, num_hidden_layers=oc.v_layers,
+                            num_attention_heads=oc.v_heads, intermediate_size=oc.v_inter, layer_norm_eps=oc.v_eps, hidden_act=oc.v_act,
+                            model_type="clip_vision_model"),
+        llama=LlamaDims(hidden_size=oc.hidden, num_hidden_layers=oc.layers, num_attention_heads=oc.heads, num_key_value_heads=oc.kv_heads,
+                        head_dim=oc.head_dim, intermediate_size=oc.inter, vocab_size=oc.vocab, rope_theta=oc.rope_theta, rms_norm_eps=oc.rms_eps),
+        enable_region=True, enable_depth=True, mm_vision_select_layer=oc.select_layer, mm_vision_select_feature="patch")
+    cfg.llm_mask_token_id, cfg.llm_depth_token_id = oc.mask_token_id, oc.depth_token_id
+    sd = O.make_weights(oc, seed=CLIP_WEIGHT_SEED if seed is None else seed)
+    return oc, sd, LlavaLlamaModel(cfg, from_state_dicts(cfg, sd, DEV, dtype=dtype), max_seq_len=512)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_clip_tower_matches_reference_fixture(golden_dir, dtype):
+    """CLIP tower on the CUDA path (bias-free patch GEMM, class token + position embedding kernel, pre_layrnorm, head_dim-64
+    attention, quick_gelu GEMM epilogue, "patch" select) against the reference's VisionTower over HF CLIPVisionModel."""
+    g = load_npz(os.path.join(golden_dir, "clip_tower.npz"))
+    oc, sd, model = _clip_model(dtype)
+    out = model.get_vision_tower()(g["images"].to(DEV))
+    assert out.dtype == dtype and tuple(out.shape) == tuple(g["tower_features"].shape)
+    tol = BF16_STAGE if dtype == torch.bfloat16 else dict(rel_rms=1.25e-2, rel_max=1.5e-1)
+    assert_close(out, g["tower_features"], **tol, what=f"clip tower {dtype}")
+    # no worse than the oracle run in the same dtype (the reference's own arithmetic)
+    from tests.util import err_stats
+    o = O.vision_tower_forward(oc, sd["vision_tower"], g["images"], dtype)
+    _, e_cuda, rr = err_stats(out, g["tower_features"])
+    _, e_orac, _ = err_stats(o, g["tower_features"])
+    print(f"clip {dtype}: rel rms err cuda {e_cuda / rr:.5f}, oracle {e_orac / rr:.5f}")
+    assert e_cuda <= 1.5 * e_orac + 1e-4 * rr
+
+
+def test_quick_gelu_gemm_epilogue_against_torch():
+    from spatialrgpt_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    for (M, N, K) in [(77, 256, 128), (1154, 4096, 1024), (2308, 1024, 1024)]:
+        a = (torch.randn(M, K, generator=gen, device=DEV)).to(torch.bfloat16)
+        w = (torch.randn(N, K, generator=gen, device=DEV) * K ** -0.5).to(torch.bfloat16)
+        b = (torch.randn(N, generator=gen, device=DEV) * 0.1).to(torch.bfloat16)
+        x = (a.float() @ w.float().t() + b.float()).to(torch.bfloat16)
+        ref = (x * torch.sigmoid(1.702 * x)).float()  # HF QuickGELUActivation on a bf16 tensor
+        assert_close(ops.gemm(a, w, bias=b, epilogue=ops.EPI_BIAS_QUICK_GELU), ref, **BF16_CHAIN, what=f"quick_gelu {M}x{N}x{K}")
+
+
+def test_clip_pipeline_generate_matches_oracle():
+    """generate() end to end with a CLIP tower (regions + depth on) against the CPU oracle on the same weights."""
+    from tests.golden.make_golden import CLIP_WEIGHT_SEED
+    oc, sd, model = _clip_model()
+    input_ids, images, depths, masks = O.synth_request(oc, 2, 24, seed=3, kind="mask")  # 4 leading tokens with margins >= 0.45 sigma
+    n_new = 8
+    ref_ids, enc = O.generate(oc, sd, input_ids, images, depths, masks, n_new, return_all=True)
+    ids, logits = model.generate(input_ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=[m.to(DEV) for m in masks],
+                                 do_sample=False, max_new_tokens=n_new, output_logits=True)
+    sigma = float(enc["logits"].std())
+    n_cmp = 1
+    while n_cmp < n_new and ids[0, :n_cmp].tolist() == ref_ids[:n_cmp].tolist():
+        n_cmp += 1
+    err = (logits[0, :n_cmp].cpu() - enc["logits"][:n_cmp]).abs().max().item()
+    assert err <= 0.06 * sigma, f"logit error {err:.4f} > 0.06 sigma ({sigma:.3f})"
+    top2 = enc["logits"].topk(2, -1).values
+    safe = int(((top2[:, 0] - top2[:, 1]) > 0.12 * sigma).long().cumprod(0).sum())
+    assert safe >= 4 and ids[0, :safe].tolist() == ref_ids[:safe].tolist()
+    assert model.generate(input_ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=[m.to(DEV) for m in masks],
+                          do_sample=False, max_new_tokens=n_new)[0].tolist() == ids[0].tolist()  # CUDA-graph decode

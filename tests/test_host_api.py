@@ -182,6 +182,29 @@ def test_read_checkpoint_with_tokenizer_registers_special_tokens(tmp_path):
     assert not cfg.mm_use_im_patch_token and tok.convert_tokens_to_ids("<im_patch>") in (None, tok.unk_token_id)
 
 
+def test_clip_checkpoint_reads_back_as_a_clip_tower(tmp_path):
+    """multimodal_encoder/builder.py:38-47 picks the tower class from the vision config's architecture name; a checkpoint whose
+    vision_tower/ holds a CLIPVisionModel parses as a CLIP tower ("patch" select, quick_gelu, class token + pre_layrnorm weights)."""
+    from oracle import srgpt_oracle as O
+    from spatialrgpt_b200 import builder
+    from spatialrgpt_b200.weights import from_state_dicts
+    from tests.golden.make_golden import CLIP_CASE
+    from tests.util import write_synthetic_checkpoint
+
+    oc = O.OracleConfig(**CLIP_CASE)
+    sd = O.make_weights(oc, seed=2)
+    root = str(tmp_path / "ckpt_clip")
+    write_synthetic_checkpoint(root, oc, sd)
+    cfg, got, tok, proc = builder.read_checkpoint(root)
+    v = cfg.vision
+    assert v.is_clip and v.hidden_act == "quick_gelu" and v.layer_norm_eps == 1e-5 and v.tokens == v.grid ** 2 + 1
+    assert cfg.mm_vision_select_feature == "patch"
+    w = from_state_dicts(cfg, got, "cpu")
+    assert w.vision.patch_b is None and w.vision.cls_emb.shape == (oc.v_hidden,) and w.vision.pos_emb.shape == (v.tokens, oc.v_hidden)
+    assert torch.equal(w.vision.pre_ln_w, sd["vision_tower"]["vision_model.pre_layrnorm.weight"])
+    assert len(w.vision.layers) == oc.v_layers
+
+
 def test_bench_algorithmic_numbers_match_the_survey():
     """bench.py's FLOP / byte model of config c2 equals SURVEY.md §8(d): 5.58 TFLOP per request to the first token,
     15.01 GB streamed per decoded token, 131072 B of KV per cached token, 234.9 MB for the gate/up GEMV."""

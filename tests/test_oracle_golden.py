@@ -8,7 +8,7 @@ import torch
 
 from oracle import srgpt_oracle as O
 from tests.golden.make_golden import CASES
-from tests.util import load_npz
+from tests.util import BF16_STAGE, assert_close, load_npz
 
 
 def _load(golden_dir, name):
@@ -90,6 +90,24 @@ def test_depth_to_u8x3():
     assert out.shape == (6, 8, 3) and out.dtype == torch.uint8
     assert out.min() == 0 and out.max() == 255
     assert torch.equal(out[..., 0], out[..., 2])
+
+
+def test_clip_tower_matches_reference_module(golden_dir):
+    """The oracle's CLIP branch (clip_encoder.py:8-13 over HF CLIPVisionModel) against the reference's VisionTower.forward +
+    feature_select("patch") run on the same seeded weights (fixture by ``make_golden.py clip``): the class token is dropped,
+    hidden_states[-2] is selected, fp32 agrees to rounding and the bf16 / fp16 modes track it."""
+    from tests.golden.make_golden import CLIP_CASE
+    g = load_npz(os.path.join(golden_dir, "clip_tower.npz"))
+    oc = O.OracleConfig(**CLIP_CASE)
+    sd = O.make_weights(oc, seed=int(g["weight_seed"]))
+    out = O.vision_tower_forward(oc, sd["vision_tower"], g["images"])
+    assert out.shape == g["tower_features"].shape == (3, oc.grid ** 2, oc.v_hidden)
+    assert torch.allclose(out, g["tower_features"], rtol=1e-5, atol=1e-5)
+    assert_close(O.vision_tower_forward(oc, sd["vision_tower"], g["images"], torch.bfloat16), g["tower_features"], **BF16_STAGE, what="clip bf16")
+    assert_close(O.vision_tower_forward(oc, sd["vision_tower"], g["images"], torch.float16), g["tower_features"], rel_rms=1.25e-2, rel_max=1.5e-1,
+                 what="clip fp16")
+    with pytest.raises(ValueError):
+        O.vision_tower_forward(O.OracleConfig(**{**CLIP_CASE, "select_feature": "nope"}), sd["vision_tower"], g["images"])
 
 
 @pytest.mark.parametrize("ptype", ["linear", "mlp2x_gelu", "mlp3x_gelu", "identity"])

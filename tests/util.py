@@ -51,7 +51,7 @@ def write_synthetic_checkpoint(root, oc, sd, n_words=200, generation_eos=None, p
     from transformers import PreTrainedTokenizerFast, SiglipImageProcessor
 
     top = {"architectures": ["LlavaLlamaModel"], "model_type": "llava_llama", "enable_region": True, "enable_depth": bool(oc.enable_depth),
-           "mm_vision_select_layer": oc.select_layer, "mm_vision_select_feature": "cls_patch", "image_aspect_ratio": "resize",
+           "mm_vision_select_layer": oc.select_layer, "mm_vision_select_feature": getattr(oc, "select_feature", "cls_patch"), "image_aspect_ratio": "resize",
            "mm_use_im_start_end": False, "mm_use_im_patch_token": False, "model_dtype": "torch.bfloat16"}
     subs = {
         "llm": {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": oc.hidden, "num_hidden_layers": oc.layers,
@@ -60,7 +60,10 @@ def write_synthetic_checkpoint(root, oc, sd, n_words=200, generation_eos=None, p
                 "bos_token_id": 1, "eos_token_id": 2, "tokenizer_padding_side": "right"},
         "vision_tower": {"model_type": "siglip_vision_model", "image_size": oc.image_size, "patch_size": oc.patch_size, "hidden_size": oc.v_hidden,
                          "num_hidden_layers": oc.v_layers, "num_attention_heads": oc.v_heads, "intermediate_size": oc.v_inter,
-                         "layer_norm_eps": oc.v_eps, "hidden_act": "gelu_pytorch_tanh"},
+                         "layer_norm_eps": oc.v_eps, "hidden_act": "gelu_pytorch_tanh"} if getattr(oc, "v_type", "siglip") != "clip" else
+                        {"architectures": ["CLIPVisionModel"], "model_type": "clip_vision_model", "image_size": oc.image_size,
+                         "patch_size": oc.patch_size, "hidden_size": oc.v_hidden, "num_hidden_layers": oc.v_layers,
+                         "num_attention_heads": oc.v_heads, "intermediate_size": oc.v_inter, "layer_norm_eps": oc.v_eps, "hidden_act": oc.v_act},
         "mm_projector": {"mm_projector_type": projector_type},
         "region_extractor": {"region_extractor_type": "regiongpt"},
     }
