@@ -502,7 +502,10 @@ static int launch_pre(const Params& p, int npairs, cudaStream_t st) {
     const char* v = getenv("SRGPT_GEMV_L2PF");
     return (v != nullptr && v[0] != 0) ? atoi(v) : 0;
   }();
-  q.l2pf = l2pf;
+  // 1: every GEMV (measured slower, see the kernel); 2: only o_proj, whose CTAs are resident while the latency-bound decode
+  // attention leaves HBM idle (its 33 MB fit L2 many times over); 3: o_proj and the qkv GEMV
+  const bool small_plain = MODE == SRGPT_GEMV_PLAIN && p.residual != nullptr && (long long)p.N * p.K <= (32LL << 20);
+  q.l2pf = (l2pf == 1 || (l2pf >= 2 && small_plain) || (l2pf == 3 && MODE == SRGPT_GEMV_QKV_ROPE)) ? 1 : 0;
   SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_gemv_kernel<MODE, PRE>, q));
   return SRGPT_OK;
 }

@@ -288,7 +288,7 @@ def test_generate_with_sampling(golden_dir):
         toks = out[0].tolist()
         for k, t in enumerate(toks):
             by_step[k].add(t)
-            assert t in lg[0, k].topk(top_k).indices.tolist(), f"step {k}: token {t} outside the top-{top_k} of its own logits"
+            assert t in lg[0][k].topk(top_k).indices.tolist(), f"step {k}: token {t} outside the top-{top_k} of its own logits"
     assert sum(len(b) > 1 for b in by_step[1:]) >= (n_new - 1) // 2, f"later steps are not being sampled: {[len(b) for b in by_step]}"
     stop_at = s1[2]
     cut = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, eos_token_id=stop_at, **args)[0].tolist()
@@ -359,7 +359,7 @@ def test_clip_pipeline_generate_matches_oracle():
     n_cmp = 1
     while n_cmp < n_new and ids[0, :n_cmp].tolist() == ref_ids[:n_cmp].tolist():
         n_cmp += 1
-    err = (logits[0, :n_cmp].cpu() - enc["logits"][:n_cmp]).abs().max().item()
+    err = (logits[0][:n_cmp].cpu() - enc["logits"][:n_cmp]).abs().max().item()
     assert err <= 0.06 * sigma, f"logit error {err:.4f} > 0.06 sigma ({sigma:.3f})"
     top2 = enc["logits"].topk(2, -1).values
     safe = int(((top2[:, 0] - top2[:, 1]) > 0.12 * sigma).long().cumprod(0).sum())
