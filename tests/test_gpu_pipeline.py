@@ -288,7 +288,9 @@ def test_generate_with_sampling(golden_dir):
         toks = out[0].tolist()
         for k, t in enumerate(toks):
             by_step[k].add(t)
-            assert t in lg[0][k].topk(top_k).indices.tolist(), f"step {k}: token {t} outside the top-{top_k} of its own logits"
+            # HF's TopKLogitsWarper keeps every score >= the k-th largest one, so ties at the threshold (frequent: the logits are
+            # bf16-rounded) stay in the support
+            assert float(lg[0][k][t]) >= float(lg[0][k].topk(top_k).values[-1]), f"step {k}: token {t} below the top-{top_k} threshold of its own logits"
     assert sum(len(b) > 1 for b in by_step[1:]) >= (n_new - 1) // 2, f"later steps are not being sampled: {[len(b) for b in by_step]}"
     stop_at = s1[2]
     cut = model.generate(ids, do_sample=True, temperature=1.5, top_p=0.95, seed=11, eos_token_id=stop_at, **args)[0].tolist()
