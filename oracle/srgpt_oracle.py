@@ -64,6 +64,7 @@ class OracleConfig:
     inter: int = 14336
     vocab: int = 128259
     rope_theta: float = 500000.0
+    rope_scaling_factor: float = 1.0  # "linear" scaling (LlamaLinearScalingRotaryEmbedding, modeling_llama.py:133-141)
     rms_eps: float = 1e-5
     # multimodal
     enable_region: bool = True
@@ -488,7 +489,10 @@ def rope_cos_sin(cfg: OracleConfig, positions: torch.Tensor, dtype: torch.dtype)
     """``LlamaRotaryEmbedding.forward`` (modeling_llama.py:117-130): fp32 freqs, cast to dtype."""
     hd = cfg.head_dim
     inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
-    freqs = positions.float()[:, None] * inv_freq[None, :]
+    pos = positions.float()
+    if cfg.rope_scaling_factor != 1.0:
+        pos = pos / cfg.rope_scaling_factor  # modeling_llama.py:138
+    freqs = pos[:, None] * inv_freq[None, :]
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
 

@@ -82,11 +82,29 @@ def _llama_dims(d: Dict[str, Any]) -> LlamaDims:
     rope = d.get("rope_theta")
     if rope is None and isinstance(d.get("rope_parameters"), dict):
         rope = d["rope_parameters"].get("rope_theta")
-    if d.get("rope_scaling") not in (None, {}):
-        raise NotImplementedError("rope_scaling checkpoints (language_model/builder.py:31-38) are a next-round item")
+    # rope_scaling as the reference's modeling file reads it (modeling_llama.py:267-292): {"type": "linear" | "dynamic", "factor": f};
+    # plus the context extension the loader applies itself (language_model/builder.py:31-38: model_max_length > max_position_embeddings)
+    factor = 1.0
+    rs = d.get("rope_scaling")
+    orig_ctx, model_max = d.get("max_position_embeddings"), d.get("model_max_length")
+    if orig_ctx and model_max and model_max > orig_ctx:
+        import math
+        rs = {"type": "linear", "factor": float(math.ceil(model_max / orig_ctx))}
+    if rs not in (None, {}):
+        kind = rs.get("type", rs.get("rope_type"))
+        if kind == "linear":
+            factor = float(rs["factor"])
+        elif kind == "dynamic":
+            # NTK scaling only changes the base once a sequence exceeds max_position_embeddings (modeling_llama.py:148-156); this
+            # decoder never runs past it (max_seq_len <= max_position_embeddings is enforced by load_pretrained_model)
+            factor = 1.0
+        elif kind in (None, "default"):
+            factor = 1.0
+        else:
+            raise ValueError(f"Unknown RoPE scaling type {kind}")  # modeling_llama.py:291
     return LlamaDims(hidden_size=d["hidden_size"], num_hidden_layers=d["num_hidden_layers"], num_attention_heads=nh,
                      num_key_value_heads=d.get("num_key_value_heads", nh), head_dim=d.get("head_dim") or d["hidden_size"] // nh,
-                     intermediate_size=d["intermediate_size"], vocab_size=d["vocab_size"], rope_theta=float(rope or 10000.0),
+                     intermediate_size=d["intermediate_size"], vocab_size=d["vocab_size"], rope_theta=float(rope or 10000.0), rope_scaling_factor=factor,
                      rms_norm_eps=d.get("rms_norm_eps", 1e-6), max_position_embeddings=d.get("max_position_embeddings", 4096),
                      bos_token_id=d.get("bos_token_id"), eos_token_id=d.get("eos_token_id"), pad_token_id=d.get("pad_token_id"),
                      tokenizer_model_max_length=d.get("tokenizer_model_max_length"),

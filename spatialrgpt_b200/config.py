@@ -53,6 +53,7 @@ class LlamaDims:
     intermediate_size: int = 14336
     vocab_size: int = 128259
     rope_theta: float = 500000.0
+    rope_scaling_factor: float = 1.0  # "linear" RoPE scaling (positions / factor; language_model/builder.py:31-38, modeling_llama.py:133-141)
     rms_norm_eps: float = 1e-5
     max_position_embeddings: int = 8192
     bos_token_id: Optional[int] = None

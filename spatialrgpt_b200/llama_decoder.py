@@ -28,6 +28,8 @@ def build_rope_tables(dims: LlamaDims, max_pos: int, device, dtype: torch.dtype 
     hd = dims.head_dim
     inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
     t = torch.arange(max_pos, dtype=torch.int64).float()
+    if getattr(dims, "rope_scaling_factor", 1.0) != 1.0:  # LlamaLinearScalingRotaryEmbedding.forward (modeling_llama.py:136-140)
+        t = t / float(dims.rope_scaling_factor)
     freqs = t[:, None] * inv_freq[None, :]
     return freqs.cos().to(dtype).to(device).contiguous(), freqs.sin().to(dtype).to(device).contiguous()
 

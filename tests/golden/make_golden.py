@@ -296,9 +296,39 @@ def run_clip_kat():
     print(f"clip_tower -> {path}: features {tuple(feats.shape)}, rms {float(feats.pow(2).mean().sqrt()):.4f}")
 
 
+@torch.no_grad()
+def run_rope_kat():
+    """cos / sin of the reference's rotary classes (modeling_llama.py:81-141), plain and with linear scaling, fp32."""
+    # the file is written to REPLACE transformers/models/llama/modeling_llama.py (relative imports): load it inside that package
+    import importlib.util
+
+    import transformers.models.llama  # noqa: F401
+    spec = importlib.util.spec_from_file_location("transformers.models.llama._srgpt_ref_modeling",
+                                                  "/root/reference/llava/train/transformers_replace/models/llama/modeling_llama.py")
+    m = importlib.util.module_from_spec(spec)
+    m.__package__ = "transformers.models.llama"
+    sys.modules[spec.name] = m
+    spec.loader.exec_module(m)
+    LlamaLinearScalingRotaryEmbedding, LlamaRotaryEmbedding = m.LlamaLinearScalingRotaryEmbedding, m.LlamaRotaryEmbedding
+
+    pos = torch.tensor([[0, 1, 2, 3, 17, 258, 259, 1000, 4095]])
+    x = torch.zeros(1, 1, pos.shape[1], 128)
+    arrays = {"positions": pos[0].numpy()}
+    for name, emb in (("plain", LlamaRotaryEmbedding(128, max_position_embeddings=8192, base=500000.0)),
+                      ("linear4", LlamaLinearScalingRotaryEmbedding(128, max_position_embeddings=8192, base=500000.0, scaling_factor=4.0))):
+        cos, sin = emb(x, pos)
+        arrays[name + "_cos"], arrays[name + "_sin"] = cos[0].numpy(), sin[0].numpy()
+    path = os.path.join(HERE, "rope_kats.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"rope_kats -> {path}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["rope"]:
+        run_rope_kat()
+        sys.exit(0)
     if sys.argv[1:] == ["clip"]:
         run_clip_kat()
         sys.exit(0)
@@ -310,3 +340,4 @@ if __name__ == "__main__":
     run_maskpool_kats()
     run_projector_kats()
     run_clip_kat()
+    run_rope_kat()

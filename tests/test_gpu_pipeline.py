@@ -368,3 +368,28 @@ def test_clip_pipeline_generate_matches_oracle():
     assert safe >= 4 and ids[0, :safe].tolist() == ref_ids[:safe].tolist()
     assert model.generate(input_ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=[m.to(DEV) for m in masks],
                           do_sample=False, max_new_tokens=n_new)[0].tolist() == ids[0].tolist()  # CUDA-graph decode
+
+
+def test_linear_rope_scaling_generate_matches_oracle(golden_dir):
+    """rope_scaling {"type": "linear", "factor": 4} (language_model/builder.py:31-38 -> LlamaLinearScalingRotaryEmbedding)."""
+    name = "tiny_masks_gqa"
+    kw, n_regions, t_text, kind, n_new, depth_on = CASES[name]
+    oc, sd, model = build_model(kw, 21)
+    oc.rope_scaling_factor = 4.0
+    from spatialrgpt_b200.llava_llama import LlavaLlamaModel
+    model.config.llama.rope_scaling_factor = 4.0
+    model = LlavaLlamaModel(model.config, model.weights, max_seq_len=512)  # tables are built at construction
+    input_ids, images, depths, masks = O.synth_request(oc, n_regions, t_text, seed=1234, kind=kind)
+    ref_ids, enc = O.generate(oc, sd, input_ids, images, depths, masks, n_new, return_all=True)
+    plain_ids, _ = O.generate(O.OracleConfig(**kw), sd, input_ids, images, depths, masks, n_new, return_all=True)
+    ids, logits = model.generate(input_ids.to(DEV), images=images.to(DEV), depths=depths.to(DEV), masks=[m.to(DEV) for m in masks],
+                                 do_sample=False, max_new_tokens=n_new, output_logits=True)
+    sigma = float(enc["logits"].std())
+    top2 = enc["logits"].topk(2, -1).values
+    safe = int(((top2[:, 0] - top2[:, 1]) > 0.12 * sigma).long().cumprod(0).sum())
+    assert safe >= 1 and ids[0, :safe].tolist() == ref_ids[:safe].tolist()
+    err = (logits[0][:safe].cpu() - enc["logits"][:safe]).abs().max().item()
+    assert err <= 0.06 * sigma
+    # the scaling really changes the computation: without it the logits of the first step differ by far more than the tolerance
+    _, enc0 = O.generate(O.OracleConfig(**kw), sd, input_ids, images, depths, masks, 1, return_all=True)
+    assert (enc0["logits"][0] - enc["logits"][0]).abs().max().item() > 0.2 * sigma

@@ -182,6 +182,21 @@ def test_read_checkpoint_with_tokenizer_registers_special_tokens(tmp_path):
     assert not cfg.mm_use_im_patch_token and tok.convert_tokens_to_ids("<im_patch>") in (None, tok.unk_token_id)
 
 
+def test_rope_scaling_config_is_read_like_the_reference():
+    """modeling_llama.py:267-292 (rope_scaling type linear / dynamic / unknown) and the loader's own context extension
+    (language_model/builder.py:31-38: model_max_length > max_position_embeddings -> linear, factor = ceil(ratio))."""
+    from spatialrgpt_b200.builder import _llama_dims
+    base = {"hidden_size": 64, "num_hidden_layers": 1, "num_attention_heads": 2, "intermediate_size": 128, "vocab_size": 100,
+            "max_position_embeddings": 4096}
+    assert _llama_dims(base).rope_scaling_factor == 1.0
+    assert _llama_dims({**base, "rope_scaling": {"type": "linear", "factor": 2.0}}).rope_scaling_factor == 2.0
+    assert _llama_dims({**base, "rope_scaling": {"type": "dynamic", "factor": 2.0}}).rope_scaling_factor == 1.0
+    assert _llama_dims({**base, "model_max_length": 10000}).rope_scaling_factor == 3.0
+    assert _llama_dims({**base, "model_max_length": 4096}).rope_scaling_factor == 1.0
+    with pytest.raises(ValueError):
+        _llama_dims({**base, "rope_scaling": {"type": "yarn", "factor": 2.0}})
+
+
 def test_clip_checkpoint_reads_back_as_a_clip_tower(tmp_path):
     """multimodal_encoder/builder.py:38-47 picks the tower class from the vision config's architecture name; a checkpoint whose
     vision_tower/ holds a CLIPVisionModel parses as a CLIP tower ("patch" select, quick_gelu, class token + pre_layrnorm weights)."""

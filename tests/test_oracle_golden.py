@@ -92,6 +92,22 @@ def test_depth_to_u8x3():
     assert torch.equal(out[..., 0], out[..., 2])
 
 
+def test_rope_tables_match_reference_rotary_classes(golden_dir):
+    """cos / sin of LlamaRotaryEmbedding and LlamaLinearScalingRotaryEmbedding (modeling_llama.py:81-141; fixture by
+    ``make_golden.py rope``): the oracle's restatement and the host-side table builder of the product path, fp32 and bf16."""
+    from spatialrgpt_b200.config import LlamaDims
+    from spatialrgpt_b200.llama_decoder import build_rope_tables
+    g = load_npz(os.path.join(golden_dir, "rope_kats.npz"))
+    pos = g["positions"].long()
+    for name, factor in (("plain", 1.0), ("linear4", 4.0)):
+        oc = O.OracleConfig(head_dim=128, rope_theta=500000.0, rope_scaling_factor=factor)
+        cos, sin = O.rope_cos_sin(oc, pos, torch.float32)
+        assert torch.equal(cos, g[name + "_cos"]) and torch.equal(sin, g[name + "_sin"])
+        tc, ts = build_rope_tables(LlamaDims(head_dim=128, rope_theta=500000.0, rope_scaling_factor=factor), 4096, "cpu", torch.bfloat16)
+        assert torch.equal(tc[pos].float(), g[name + "_cos"][:, :64].to(torch.bfloat16).float())
+        assert torch.equal(ts[pos].float(), g[name + "_sin"][:, :64].to(torch.bfloat16).float())
+
+
 def test_clip_tower_matches_reference_module(golden_dir):
     """The oracle's CLIP branch (clip_encoder.py:8-13 over HF CLIPVisionModel) against the reference's VisionTower.forward +
     feature_select("patch") run on the same seeded weights (fixture by ``make_golden.py clip``): the class token is dropped,
