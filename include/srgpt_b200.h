@@ -190,6 +190,13 @@ int srgpt_lm_head_argmax_bf16(const void* x, const void* W, int ldw, int V, int 
 int srgpt_argmax_f32(const float* x, int rows, int cols, long long* out, void* stream);
 /* Same over bf16 rows [rows, ldx] (the bf16-rounded logits of a batched lm_head GEMM, modeling_llama.py:1044). */
 int srgpt_argmax_bf16(const void* x, int ldx, int rows, int cols, long long* out, void* stream);
+/* Beam-search candidates (rowops.cu): replaces log_softmax + the [num_beams x vocab] torch.topk of HF GenerationMixin.beam_search
+ * (transformers 4.37.2; reached from llava_llama.py:212 when the eval scripts pass --num_beams > 1).  logits: [n_beams, ldx] in the
+ * element type (the rounded lm_head output, modeling_llama.py:1044-1045).  Per row the n_cand best
+ * (log_softmax(logits.float())[token] + beam_scores[row], token) in (score desc, token asc) order -> cand_scores / cand_tokens
+ * [n_beams, n_cand] (token -1 / score -inf when a row has fewer finite logits). */
+int srgpt_beam_candidates_bf16(const void* logits, int ldx, int n_beams, int V, const float* beam_scores, int n_cand,
+                               float* cand_scores, int* cand_tokens, void* stream);
 /* Temperature + nucleus (top-p) sampling of one token from fp32 logits [V] (sampling.cu): replaces HF's TemperatureLogitsWarper /
  * TopKLogitsWarper / TopPLogitsWarper / multinomial behind do_sample=True (llava/eval/eval_spatial.py:231-236, llava/eval/model_vqa.py:72-78).
  * params = device float[3] {temperature, top_p, top_k (0 = off)}; seed = device u64; the draw is a counter-based generator of

@@ -580,6 +580,94 @@ def greedy_generate(cfg: OracleConfig, w_llm: Dict[str, torch.Tensor], inputs_em
     return ids
 
 
+def beam_search_generate(cfg: OracleConfig, w_llm: Dict[str, torch.Tensor], inputs_embeds: torch.Tensor, num_beams: int,
+                         max_new_tokens: int, eos_token_id=None, length_penalty: float = 1.0, early_stopping: bool = False,
+                         dtype: torch.dtype = torch.float32, return_trace: bool = False):
+    """HF ``GenerationMixin.beam_search`` + ``BeamSearchScorer`` (third party, transformers 4.37.2 generation/utils.py and
+    generation/beam_search.py; call sites llava_llama.py:212 with ``num_beams`` from eval_spatial.py:234 / eval_region_cls.py:320) for one
+    prompt given as ``inputs_embeds`` (so the decoder prompt length is 0 and only NEW ids are returned).  Restated:
+      * beam_scores start at [0, -1e9, ...]; every step: log_softmax of the fp32 logits of each beam + its beam score, the 2 x num_beams
+        best (score, beam, token) of the flattened [num_beams x vocab] table, walked in rank order;
+      * an EOS candidate of rank < num_beams closes a hypothesis: score = sum_logprobs / (generated_len ** length_penalty) with
+        generated_len counting the EOS; a hypothesis list keeps the num_beams best; other candidates fill the next beams until
+        num_beams are taken;
+      * the prompt is done when the list is full and (early_stopping or worst kept score >= best running sum_logprobs /
+        cur_len ** length_penalty), cur_len counting the token just chosen; otherwise at max_new_tokens the running beams are
+        added as hypotheses (no EOS) and the best hypothesis is returned, with the EOS re-appended when it is shorter than the longest
+        allowed output (finalize).
+    Ties in the top-k are broken towards the lower flat index (beam-major); torch.topk leaves them unspecified."""
+    eos = []
+    if eos_token_id is not None:
+        eos = list(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else [int(eos_token_id)]
+    k, V = num_beams, cfg.vocab
+    emb = w_llm["model.embed_tokens.weight"]
+    logits, cache = llama_forward(cfg, w_llm, inputs_embeds, None, dtype)
+    last = [logits[-1]] * k
+    caches = [cache] * k  # llama_forward never mutates a cache it is given (it returns a new list of concatenated tensors)
+    seqs: List[List[int]] = [[] for _ in range(k)]
+    beam_scores = torch.full((k,), -1e9)
+    beam_scores[0] = 0.0
+    hyps: List = []  # (score, tokens)
+    worst = 1e9
+    done = False
+    trace = []
+    for step in range(max_new_tokens):
+        table = torch.stack([F.log_softmax(x.float(), dim=-1) for x in last]) + beam_scores[:, None]
+        flat = table.view(-1)
+        # top 2k, ties towards the lower flat index (stable sort of the negated scores)
+        order = torch.sort(-flat, stable=True).indices[: max(2, 1 + len(eos)) * k]
+        cur_len = step + 1  # tokens generated once this step's choice is appended (decoder prompt length is 0)
+        nxt = []
+        for rank, fi in enumerate(order.tolist()):
+            b, t, sc = fi // V, fi % V, float(flat[fi])
+            if t in eos:
+                if rank >= k:
+                    continue
+                score = sc / (cur_len ** length_penalty)
+                if len(hyps) < k or score > worst:
+                    hyps.append((score, list(seqs[b])))
+                    if len(hyps) > k:
+                        hyps.remove(min(hyps, key=lambda h: h[0]))
+                    worst = min(h[0] for h in hyps)
+            else:
+                nxt.append((sc, b, t))
+            if len(nxt) == k:
+                break
+        assert len(nxt) == k
+        if return_trace:
+            trace.append([(round(sc, 6), b, t) for sc, b, t in nxt])
+        best_running = float(flat[order[0]])
+        if len(hyps) >= k and (early_stopping or worst >= best_running / (cur_len ** length_penalty)):
+            done = True
+        seqs = [seqs[b] + [t] for _, b, t in nxt]
+        beam_scores = torch.tensor([sc for sc, _, _ in nxt])
+        if done or step == max_new_tokens - 1:
+            break
+        parents = [b for _, b, _ in nxt]
+        new_last, new_caches = [], []
+        for i, (_, b, t) in enumerate(nxt):
+            lg, c = llama_forward(cfg, w_llm, emb[t][None].to(dtype), caches[b], dtype)
+            new_last.append(lg[-1])
+            new_caches.append(c)
+        last, caches = new_last, new_caches
+    if not done:  # finalize: the running beams become hypotheses, scored over their generated length
+        for i in range(k):
+            score = float(beam_scores[i]) / (len(seqs[i]) ** length_penalty)
+            if len(hyps) < k or score > worst:
+                hyps.append((score, list(seqs[i])))
+                if len(hyps) > k:
+                    hyps.remove(min(hyps, key=lambda h: h[0]))
+                worst = min(h[0] for h in hyps)
+    best = max(hyps, key=lambda h: h[0])
+    out = list(best[1])
+    if len(out) < max_new_tokens and eos:  # beam_search.py finalize: the EOS is written back when the hypothesis is shorter than the output
+        out.append(eos[0])
+    ids = torch.tensor(out, dtype=torch.long)
+    if return_trace:
+        return ids, trace, best[0]
+    return ids
+
+
 # ----------------------------------------------------------------------------------------------
 # whole request
 # ----------------------------------------------------------------------------------------------

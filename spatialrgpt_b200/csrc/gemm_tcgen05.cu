@@ -903,20 +903,23 @@ constexpr int TSK_MAX_CTAS = 256;
 constexpr int TSK_FLAG_BYTES = TSK_MAX_CTAS * 4;
 constexpr long long TSK_SLOT_FLOATS = 3LL * BM * TSK_BN;  // MT = 3 accumulators of 128 x 128
 
-template <int MT>
+// BN < 128 (MT = 1 only): narrow weight tiles for the skinny GEMMs of a batched decode step (M <= 128 rows), see launch_tall_sk
+template <int MT, int BN = TSK_BN>
 struct TskCfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
-  static constexpr int B_BYTES = TSK_BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // 32 / 48 / 64 KB
-  static constexpr int STAGES = MT == 3 ? 3 : (MT == 2 ? 4 : 6);  // 192 KB in flight in every case
-  static constexpr int TMEM_COLS = MT == 1 ? 128 : (MT == 2 ? 256 : 512);
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // 32 / 48 / 64 KB (BN = 128); 24 / 20 KB (BN = 64 / 32)
+  static constexpr int STAGES = MT == 3 ? 3 : (MT == 2 ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 9)));  // ~192 KB in flight in every case
+  static constexpr int TMEM_COLS = MT == 1 ? (BN < 32 ? 32 : BN) : (MT == 2 ? 256 : 512);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
 };
 
 struct TskWs {
-  float* partial;        // [gridDim.x][MT][128][128] fp32
+  float* partial;        // [gridDim.x][MT][128][BN] fp32
   unsigned int* flags;   // [gridDim.x], == epoch once CTA c's partial is complete
   unsigned int epoch;
+  int whole_tiles;       // 1: CTAs own whole n-tiles (contiguous ranges balanced over the grid): no k-split, no partials, no flags
+  int a_stage_tx;        // bytes one A box delivers per m-tile and k-block (the A map's box may hold fewer than 128 rows)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -928,11 +931,11 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int EPI, int MT>
+template <int EPI, int MT, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p, const TskWs ws) {
-  using C = TskCfg<MT>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, BN = TSK_BN;
+  using C = TskCfg<MT, BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -947,7 +950,7 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_kb = (p.K + BK - 1) / BK;
   const long long total = (long long)tiles_n * num_kb;
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-  auto range_begin = [&](int c) { return (int)(total * c / G); };
+  auto range_begin = [&](int c) { return ws.whole_tiles ? (int)((long long)tiles_n * c / G) * num_kb : (int)(total * c / G); };
   const int u_begin = range_begin(cta), u_end = range_begin(cta + 1);
 
   if (warp == 0 && lane == 0) {
@@ -975,10 +978,11 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int tile = u / num_kb, kb = u - tile * num_kb;
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, STAGE_BYTES);
+        mbar_expect_tx(fb, MT * ws.a_stage_tx + C::B_BYTES);
         uint8_t* sa = smem + stage * STAGE_BYTES;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) tma_load_2d(smem_u32(sa + mt * A_STAGE_BYTES), &tmap_a, fb, kb * BK, mt * BM);  // rows >= M zero-filled
+        // (a box of fewer than 128 rows leaves the rest of the A stage stale: those accumulator rows are never read)
         tma_load_2d(smem_u32(sa + C::A_BYTES), &tmap_b, fb, kb * BK, tile * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -1058,7 +1062,7 @@ gemm_tall_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int ci = 0; ci < 2; ++ci) {
           const int c = cpart * 2 + ci;
           const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
+          if (c * 32 >= BN || col0 >= p.N) break;  // warp-uniform
           uint32_t r[32];
           __syncwarp();  // the row guard below diverges; tcgen05.ld is warp-collective
           tmem_ld_32x32b_x32(tmem_base + mt * BN + c * 32 + ((uint32_t)(lg * 32) << 16), r);
@@ -1301,25 +1305,33 @@ static TskState g_tsk;
 
 static long long tsk_workspace_bytes(int ctas) { return TSK_FLAG_BYTES + (long long)ctas * TSK_SLOT_FLOATS * 4; }
 
-template <int EPI, int MT>
-static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
-  using C = TskCfg<MT>;
+template <int EPI, int MT, int BN>
+static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream, int whole_grid) {
+  using C = TskCfg<MT, BN>;
   static bool configured = false;
   if (!configured) {
-    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tall_sk_kernel<EPI, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SRGPT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tall_sk_kernel<EPI, MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
+  // A box: 128 rows, or 32 / 64 when that covers all M rows of a one-tile problem (fewer bytes written to shared memory per k-block)
+  const int a_box = (MT == 1 && p.M <= 32) ? 32 : ((MT == 1 && p.M <= 64) ? 64 : BM);
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, A, p.M, p.K, lda, BM);
+  int rc = make_tmap(&ta, A, p.M, p.K, lda, a_box);
   if (rc != SRGPT_OK) return rc;
-  rc = make_tmap(&tb, W, p.N, p.K, ldw, TSK_BN);
+  rc = make_tmap(&tb, W, p.N, p.K, ldw, BN);
   if (rc != SRGPT_OK) return rc;
-  const long long total = (long long)ceil_div(p.N, TSK_BN) * ceil_div(p.K, BK);
+  const long long total = (long long)ceil_div(p.N, BN) * ceil_div(p.K, BK);
   int grid = sm_count();
   if (grid > TSK_MAX_CTAS) grid = TSK_MAX_CTAS;
   if ((long long)grid > total) grid = (int)total;
-  while (tsk_workspace_bytes(grid) > g_tsk.bytes && grid > 1) --grid;  // a small workspace only narrows the grid
   TskWs ws;
+  ws.whole_tiles = whole_grid > 0 ? 1 : 0;
+  ws.a_stage_tx = a_box * BK * 2;
+  if (whole_grid > 0) {
+    grid = whole_grid;
+  } else {
+    while (tsk_workspace_bytes(grid) > g_tsk.bytes && grid > 1) --grid;  // a small workspace only narrows the grid
+  }
   ws.flags = reinterpret_cast<unsigned int*>(g_tsk.base);
   ws.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g_tsk.base) + TSK_FLAG_BYTES);
   if (++g_tsk.epoch == 0) g_tsk.epoch = 1;  // flags start at 0 (zeroed workspace) and never equal a future epoch
@@ -1329,16 +1341,53 @@ static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, con
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tall_sk_kernel<EPI, MT>, ta, tb, p, ws));
+  SRGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tall_sk_kernel<EPI, MT, BN>, ta, tb, p, ws));
   return SRGPT_OK;
+}
+
+// One-tile-high problems (M <= 128: the projections and the lm_head of a batched decode step) - WHOLE n-tiles per CTA.
+// ncu at M = 32 (profiles/r02_ncu_full_tsk_m32_summary.txt): the stream-K split costs a fixed ~18 us per launch whatever the matrix
+// (partial stores + fence + flag, owner polls, dependent partial loads: o_proj 27 us against a 5 us HBM floor, down 40 / 18, gate-up
+// 52 / 36).  Without a k-split nothing is exchanged; what fills the chip instead is a NARROWER weight tile: BN is chosen per problem from
+// {128, 64, 32} by a two-term cost model - HBM time of the weights vs waves x per-SM TMA ingest (~88 GB/s, DESIGN.md "GEMM: what bounds
+// it") of one tile's weight + activation bytes - and the grid is the balanced whole-tile count ceil(tiles / waves).
+// SRGPT_GEMM_TSK_WHOLE=-1 restores the stream-K split (A/B knob).
+template <int EPI>
+static int launch_skinny(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream, bool* handled) {
+  static const int whole_env = env_int("SRGPT_GEMM_TSK_WHOLE");
+  *handled = false;
+  if (whole_env < 0 || p.M > BM) return SRGPT_OK;
+  const int sms = sm_count();
+  const double hbm_s = (double)p.N * p.K * 2 / 6.4e12;
+  int best_bn = 0, best_grid = 0;
+  double best_t = 1e30;
+  const int cands[3] = {128, 64, 32};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (EPI == SRGPT_EPI_SWIGLU && bn < 64) continue;  // keep (gate, up) pairs and 16-byte output vectors inside a chunk
+    const int tiles = ceil_div(p.N, bn);
+    const int waves = ceil_div(tiles, sms);
+    const double per_sm = (double)waves * ((double)bn + (double)(p.M < 32 ? 32 : p.M)) * p.K * 2 / 88e9;
+    const double t = (hbm_s > per_sm ? hbm_s : per_sm) * (1.0 + 0.02 * i);  // ties -> the wider tile
+    if (t < best_t) { best_t = t; best_bn = bn; best_grid = ceil_div(tiles, waves); }
+  }
+  *handled = true;
+  if (best_bn == 128) return launch_tall_sk_mt<EPI, 1, 128>(A, lda, W, ldw, p, stream, best_grid);
+  if (best_bn == 64) return launch_tall_sk_mt<EPI, 1, 64>(A, lda, W, ldw, p, stream, best_grid);
+  return launch_tall_sk_mt<EPI, 1, 32>(A, lda, W, ldw, p, stream, best_grid);
 }
 
 template <int EPI>
 static int launch_tall_sk(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream) {
   const int mt = ceil_div(p.M, BM);
-  if (mt == 1) return launch_tall_sk_mt<EPI, 1>(A, lda, W, ldw, p, stream);
-  if (mt == 2) return launch_tall_sk_mt<EPI, 2>(A, lda, W, ldw, p, stream);
-  return launch_tall_sk_mt<EPI, 3>(A, lda, W, ldw, p, stream);
+  if (mt == 1) {
+    bool handled = false;
+    const int rc = launch_skinny<EPI>(A, lda, W, ldw, p, stream, &handled);
+    if (handled) return rc;
+    return launch_tall_sk_mt<EPI, 1, TSK_BN>(A, lda, W, ldw, p, stream, 0);
+  }
+  if (mt == 2) return launch_tall_sk_mt<EPI, 2, TSK_BN>(A, lda, W, ldw, p, stream, 0);
+  return launch_tall_sk_mt<EPI, 3, TSK_BN>(A, lda, W, ldw, p, stream, 0);
 }
 
 template <int EPI>

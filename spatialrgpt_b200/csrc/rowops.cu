@@ -308,6 +308,81 @@ __global__ void argmax_unpack_kernel(long long* __restrict__ out, int rows) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// beam search candidates: per beam row, log_softmax of the (element-type rounded) logits + the beam's running score, and the
+// n_cand best (score, token) of the row in (score desc, token asc) order.  One 1024-thread CTA per row; the row (<= 256 KB) is
+// re-read from L2 once per candidate: pass j finds the successor of candidate j-1 in that order, so no selection state is kept.
+// ---------------------------------------------------------------------------------------------
+constexpr int BEAM_THREADS = 1024;
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* sk) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+    v = ov > v ? ov : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long t = sk[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ov = __shfl_xor_sync(0xffffffffu, t, o);
+    t = ov > t ? ov : t;
+  }
+  return t;
+}
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_candidates_kernel(const bf16* __restrict__ logits, int ldx, int V, const float* __restrict__ beam_scores, int n_cand, float* __restrict__ cand_scores,
+                       int* __restrict__ cand_tokens) {
+  __shared__ unsigned long long sk[32];
+  __shared__ float sred[32];
+  const bf16* row = logits + (size_t)blockIdx.x * ldx;
+  const int tid = threadIdx.x;
+  // log-sum-exp in fp32 over the rounded logits (torch: log_softmax(logits.float(), -1))
+  float m = -INFINITY;
+  for (int c = tid; c < V; c += BEAM_THREADS) {
+    const float v = e2f(row[c]);
+    if (v == v) m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  if ((tid & 31) == 0) sred[tid >> 5] = m;
+  __syncthreads();
+  m = warp_max(sred[tid & 31]);
+  float z = 0.f;
+  for (int c = tid; c < V; c += BEAM_THREADS) {
+    const float v = e2f(row[c]);
+    if (v == v) z += expf(v - m);
+  }
+  z = block_sum(z, sred);
+  const float lse = logf(z);
+  const float bs = beam_scores[blockIdx.x];
+  // key = (order-preserving bits of the logit, ~token): the maximum key below the previous one is the next candidate
+  unsigned long long prev = ~0ull;
+  for (int j = 0; j < n_cand; ++j) {
+    unsigned long long best = 0ull;
+    for (int c = tid; c < V; c += BEAM_THREADS) {
+      const float v = e2f(row[c]);
+      if (v == v) {
+        const unsigned long long k = ((unsigned long long)float_order_bits(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)c);
+        if (k < prev && k > best) best = k;
+      }
+    }
+    best = block_max_u64(best, sk);
+    if (tid == 0) {
+      if (best == 0ull) {  // fewer than n_cand finite logits
+        cand_scores[(size_t)blockIdx.x * n_cand + j] = -INFINITY;
+        cand_tokens[(size_t)blockIdx.x * n_cand + j] = -1;
+      } else {
+        const int tok = (int)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
+        const float v = e2f(row[tok]);
+        cand_scores[(size_t)blockIdx.x * n_cand + j] = ((v - m) - lse) + bs;
+        cand_tokens[(size_t)blockIdx.x * n_cand + j] = tok;
+      }
+    }
+    prev = best == 0ull ? 0ull : best;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // batched decode bookkeeping: one CTA per sequence b: out_ids[*step * B + b] = ids[b]; h[b,:] = embed[ids[b],:]; ++pos[b];
 // the last CTA to finish (atomic ticket) advances *step, so one launch serves the whole batch inside a CUDA graph
 // ---------------------------------------------------------------------------------------------
@@ -445,6 +520,19 @@ extern "C" __attribute__((visibility("default"))) int srgpt_argmax_bf16(const vo
     return SRGPT_OK;
   }
   argmax_kernel<bf16><<<rows, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), ldx, cols, out);
+  SRGPT_CHECK_LAUNCH();
+  return SRGPT_OK;
+}
+
+// Beam-search candidates (HF GenerationMixin.beam_search, transformers 4.37.2 generation/utils.py: log_softmax of the next-token logits +
+// beam_scores, then torch.topk over the flattened [num_beams x vocab] table; call site llava_llama.py:212 with num_beams > 1): per beam row
+// the n_cand best (log_softmax(logits)[token] + beam_scores[row], token), ties towards the lower token id.  The host merges the
+// num_beams x n_cand pairs (the global top-2k is a subset of the per-row top-2k).
+extern "C" __attribute__((visibility("default"))) int srgpt_beam_candidates_bf16(const void* logits, int ldx, int n_beams, int V, const float* beam_scores, int n_cand,
+                                                                                  float* cand_scores, int* cand_tokens, void* stream) {
+  SRGPT_CHECK_ARG(logits && beam_scores && cand_scores && cand_tokens && n_beams > 0 && V > 0 && ldx >= V && n_cand > 0 && n_cand <= V);
+  beam_candidates_kernel<<<n_beams, BEAM_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(logits), ldx, V, beam_scores, n_cand,
+                                                                                             cand_scores, cand_tokens);
   SRGPT_CHECK_LAUNCH();
   return SRGPT_OK;
 }

@@ -386,7 +386,7 @@ class LlamaDecoder:
         self._bstate = st
         return st
 
-    def _batch_step_launch(self, st) -> None:
+    def _batch_step_launch(self, st, logits_only: bool = False) -> None:
         """One decode step of all B sequences (llava_arch.py:549-611 + modeling_llama.py:540-562 semantics without padding): the
         projections are tcgen05 GEMMs over the B rows (tall stream-K configuration), RoPE / KV append and attention per sequence."""
         d, w, B = self.dims, self.w, st["B"]
@@ -407,6 +407,8 @@ class LlamaDecoder:
         ops.rmsnorm(h, w.norm, d.rms_norm_eps, out=xn)
         lg = st["logits"][:, :V]
         ops.gemm(xn, w.lm_head, out=lg)  # bf16 logits (modeling_llama.py:1044), arg max with the lowest index on ties
+        if logits_only:  # beam search: the host picks the next tokens from the candidates of these logits
+            return
         ops.argmax_bf16(lg, out=st["ids"])
         ops.decode_batch_advance(st["ids"], w.embed, h, st["out"], st["step"], st["pos"], st["ticket"])
 
@@ -476,6 +478,125 @@ class LlamaDecoder:
         n = min(n, max_new_tokens)
         res = out2d[:n].t().contiguous()
         return [res[b, : (stopped[b] if stopped[b] is not None else n)].clone() for b in range(B)]
+
+    @torch.no_grad()
+    @ops.in_own_dtype
+    def generate_beam(self, inputs_embeds: torch.Tensor, num_beams: int, max_new_tokens: int, eos_token_ids=None, stopping_fn=None,
+                      length_penalty: float = 1.0, early_stopping: bool = False, use_graph: bool = True) -> torch.Tensor:
+        """Beam search from prompt embeddings [S, H] (HF GenerationMixin.beam_search + BeamSearchScorer behind llava_llama.py:212 when
+        the eval scripts pass --num_beams > 1; restated by the CPU checker of the test suite (beam_search_generate), which is pinned to HF's own
+        generate()).  Device side: the prompt is prefilled once per beam as one packed batch (HF expands the inputs the same way), every
+        step runs the batched decode layers over the num_beams rows, a kernel reduces each row's logits to its 2 x num_beams best
+        (log-prob + beam score, token) pairs, and the surviving beams' KV rows are re-ordered page-wise.  Host side: the hypothesis
+        bookkeeping on the num_beams x 2 num_beams candidates - the same control logic HF runs in Python.  Returns the NEW ids."""
+        d, w, k = self.dims, self.w, int(num_beams)
+        S, V = inputs_embeds.shape[0], d.vocab_size
+        if k < 2:
+            raise ValueError("generate_beam needs num_beams >= 2")
+        if max_new_tokens < 1:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        if S + max_new_tokens > self.max_seq_len:
+            raise RuntimeError(f"{S} prompt + {max_new_tokens} new tokens exceed max_seq_len {self.max_seq_len}")
+        eos = []
+        if eos_token_ids is not None:
+            eos = [int(e) for e in (eos_token_ids if isinstance(eos_token_ids, (list, tuple, set)) else [eos_token_ids])]
+        n_cand = max(2, 1 + len(eos)) * k
+        for b in range(len(self.cache.owned)):
+            self.cache.release(b)
+        self.ensure_capacity(k, S + max_new_tokens)
+        self.cache.reserve_many([S + max_new_tokens] * k)
+        hidden = self.prefill_packed(inputs_embeds.to(self.dtype).repeat(k, 1), [S] * k)
+        _, lg = self.first_tokens(hidden, [S] * k, return_logits=True)
+        st = self._batch_state(k)
+        st["logits"][:, :V].copy_(lg)
+        dev = self.device
+        beam_scores = torch.full((k,), -1e9, dtype=torch.float32)
+        beam_scores[0] = 0.0
+        d_scores = beam_scores.to(dev)
+        cand_s = torch.empty((k, n_cand), dtype=torch.float32, device=dev)
+        cand_t = torch.empty((k, n_cand), dtype=torch.int32, device=dev)
+        h_s = torch.empty((k, n_cand), dtype=torch.float32, pin_memory=True)
+        h_t = torch.empty((k, n_cand), dtype=torch.int32, pin_memory=True)
+        seqs: List[List[int]] = [[] for _ in range(k)]
+        hyps: List = []  # (score, tokens) of finished hypotheses, at most k kept
+        worst, done = 1e9, False
+        zero = torch.zeros(k, dtype=torch.int32, device=dev)
+        tables = [list(self.cache.owned[b]) for b in range(k)]  # page ids by position // PAGE_SIZE
+        pages_all = self.cache.pages
+        graph = st.get("beam_graph") if use_graph else None
+
+        def keep(score: float, toks: List[int]) -> None:
+            nonlocal worst
+            if len(hyps) < k or score > worst:
+                hyps.append((score, toks))
+                if len(hyps) > k:
+                    hyps.remove(min(hyps, key=lambda x: x[0]))
+                worst = min(x[0] for x in hyps)
+
+        for step in range(max_new_tokens):
+            ops.beam_candidates(st["logits"][:, :V], d_scores, cand_s, cand_t)
+            h_s.copy_(cand_s, non_blocking=True)
+            h_t.copy_(cand_t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            # merge the per-beam candidates: (score desc, beam asc, token asc) = the flat-index order of HF's topk on ties
+            flat = sorted(((-float(h_s[b, j]), b, int(h_t[b, j])) for b in range(k) for j in range(n_cand) if int(h_t[b, j]) >= 0))[:n_cand]
+            cur_len = step + 1
+            nxt = []
+            for rank, (neg, b, t) in enumerate(flat):
+                sc = -neg
+                if t in eos:
+                    if rank >= k:
+                        continue
+                    keep(sc / (cur_len ** length_penalty), list(seqs[b]))
+                else:
+                    nxt.append((sc, b, t))
+                if len(nxt) == k:
+                    break
+            if len(nxt) < k:
+                raise RuntimeError("beam search ran out of non-EOS candidates")  # HF asserts the same
+            if len(hyps) >= k and (early_stopping or worst >= (-flat[0][0]) / (cur_len ** length_penalty)):
+                done = True
+            seqs = [seqs[b] + [t] for _, b, t in nxt]
+            beam_scores = torch.tensor([sc for sc, _, _ in nxt], dtype=torch.float32)
+            if done or step == max_new_tokens - 1:
+                break
+            if stopping_fn is not None and all(stopping_fn(torch.tensor(q, dtype=torch.int64)) for q in seqs):
+                break  # KeywordsStoppingCriteria.__call__ requires every row (beam) to have hit (mm_utils.py:616-617)
+            # ---- device state of the next step: KV rows of the generated region follow their parents (HF _reorder_cache,
+            #      modeling_llama.py:1151-1158, copies the WHOLE cache; here only the pages that hold generated tokens)
+            parents = [b for _, b, _ in nxt]
+            if step > 0 and any(p != i for i, p in enumerate(parents)):
+                j0, j1 = S // PAGE_SIZE, (S + step - 1) // PAGE_SIZE
+                src = [tables[p][j] for i, p in enumerate(parents) if p != i for j in range(j0, j1 + 1)]
+                dst = [tables[i][j] for i, p in enumerate(parents) if p != i for j in range(j0, j1 + 1)]
+                src_t = torch.tensor(src, dtype=torch.int64).to(dev)
+                dst_t = torch.tensor(dst, dtype=torch.int64).to(dev)
+                pages_all[:, dst_t] = pages_all[:, src_t]  # gather into a temporary, then scatter: permutations are safe
+            ids = torch.tensor([t for _, _, t in nxt], dtype=torch.int32).to(dev)
+            st["h"].copy_(ops.splice_rows(w.embed, None, None, None, zero, ids))
+            st["pos"].fill_(S + step)
+            d_scores.copy_(beam_scores, non_blocking=True)
+            if use_graph and graph is None:
+                saved = st["h"].clone()
+                self._batch_step_launch(st, logits_only=True)  # warm-up outside capture; rewrites only this step's own KV rows
+                torch.cuda.synchronize()
+                st["h"].copy_(saved)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._batch_step_launch(st, logits_only=True)
+                st["beam_graph"] = graph
+            if graph is not None:
+                graph.replay()
+                ops.LAUNCHES += 8 * d.num_hidden_layers + 2
+            else:
+                self._batch_step_launch(st, logits_only=True)
+        if not done:  # finalize (beam_search.py): the running beams become hypotheses over their generated length
+            for i in range(k):
+                keep(float(beam_scores[i]) / (len(seqs[i]) ** length_penalty), list(seqs[i]))
+        best = list(max(hyps, key=lambda x: x[0])[1])
+        if len(best) < max_new_tokens and eos:
+            best.append(eos[0])
+        return torch.tensor(best, dtype=torch.int64, device=dev)
 
     @torch.no_grad()
     @ops.in_own_dtype

@@ -339,8 +339,10 @@ class LlavaLlamaModel:
         sampling = None
         if do_sample and temperature not in (0, 0.0):
             sampling = dict(temperature=1.0 if temperature is None else float(temperature), top_p=top_p, top_k=top_k, seed=seed)
-        if num_beams != 1:
-            raise NotImplementedError("beam search is a next-round item (SURVEY.md §8f.4)")
+        length_penalty = float(generation_kwargs.pop("length_penalty", 1.0))
+        early_stopping = bool(generation_kwargs.pop("early_stopping", False))
+        if num_beams != 1 and (sampling is not None or return_logits):
+            raise NotImplementedError("beam search is implemented for do_sample=False without output_logits (the eval scripts' mode)")
         if generation_kwargs:
             raise TypeError(f"unsupported generation kwargs: {sorted(generation_kwargs)}")
 
@@ -364,7 +366,16 @@ class LlavaLlamaModel:
                 return any(bool(c(ids[None], None)) for c in _sc)
         lens = [int(n) for n in lens]
         left = getattr(self.config.llama, "tokenizer_padding_side", "right") == "left"
-        if B == 1:
+        if num_beams != 1 and B != 1:
+            raise NotImplementedError("beam search over a batch of prompts (the reference's eval scripts run batch 1)")
+        if B == 1 and num_beams != 1:
+            n = lens[0]
+            emb = packed if packed is not None else (inputs_embeds[0, inputs_embeds.shape[1] - n:] if left else inputs_embeds[0, :n])
+            if not hasattr(self.llm, "generate_beam") or type(self.llm).__name__ == "TPLlamaDecoder":
+                raise NotImplementedError("beam search on the tensor-parallel decoder")
+            outs.append(self.llm.generate_beam(emb, num_beams, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,
+                                               length_penalty=length_penalty, early_stopping=early_stopping, use_graph=use_graph))
+        elif B == 1:
             n = lens[0]
             emb = packed if packed is not None else (inputs_embeds[0, inputs_embeds.shape[1] - n:] if left else inputs_embeds[0, :n])
             r = self.llm.generate_from_embeds(emb, int(max_new_tokens), eos_token_ids=eos_token_id, stopping_fn=stop_fn,

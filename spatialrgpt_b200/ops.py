@@ -506,6 +506,17 @@ def sample_top_p(logits: torch.Tensor, params: torch.Tensor, seed, step: torch.T
                                              _p(out_ids), _p(embed_table), _p(next_x), K, _stream()), "srgpt_sample_top_p_f32")
 
 
+def beam_candidates(logits: torch.Tensor, beam_scores: torch.Tensor, cand_scores: torch.Tensor, cand_tokens: torch.Tensor) -> None:
+    """Per beam row: the n_cand best (log_softmax(logits)[token] + beam_scores[row], token) -> cand_scores / cand_tokens [k, n_cand]."""
+    _need(logits, ELEM(), "beam_candidates.logits"); _need(beam_scores, torch.float32, "beam_candidates.beam_scores")
+    _need(cand_scores, torch.float32, "beam_candidates.cand_scores"); _need(cand_tokens, torch.int32, "beam_candidates.cand_tokens")
+    k, V = logits.shape
+    if cand_scores.shape != cand_tokens.shape or cand_scores.shape[0] != k or not cand_scores.is_contiguous() or not cand_tokens.is_contiguous():
+        raise SrgptError("beam_candidates: cand_scores / cand_tokens must be contiguous [n_beams, n_cand]")
+    check(_lib.load().srgpt_beam_candidates_bf16(_p(logits), _rowmajor2d(logits, "beam_candidates.logits"), k, V, _p(beam_scores), cand_scores.shape[1],
+                                                 _p(cand_scores), _p(cand_tokens), _stream()), "srgpt_beam_candidates_bf16")
+
+
 def argmax_f32(x: torch.Tensor) -> torch.Tensor:
     _need(x, torch.float32, "argmax_f32.x")
     rows, cols = x.shape

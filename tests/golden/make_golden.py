@@ -323,9 +323,48 @@ def run_rope_kat():
     print(f"rope_kats -> {path}")
 
 
+BEAM_CASES = [  # (num_beams, eos_token_id, max_new_tokens, length_penalty, early_stopping)
+    (1, None, 10, 1.0, False), (3, None, 10, 1.0, False), (3, [460], 10, 1.0, False), (4, [38, 97], 12, 1.0, False),
+    (2, [886], 10, 1.0, False), (4, [134, 562], 16, 1.0, False), (3, [764], 16, 2.0, False), (3, [764], 16, 0.5, True), (5, [303], 14, 1.0, True),
+]
+BEAM_WEIGHT_SEED = 7
+
+
+@torch.no_grad()
+def run_beam_kats():
+    """HF ``generate(inputs_embeds=..., num_beams=k)`` (the call llava_llama.py:212 makes when the eval scripts pass --num_beams) on a stock
+    LlamaForCausalLM holding the oracle's seeded weights.  Run with the transformers of this image (5.5; the reference pins 4.37.2,
+    whose beam search is the same algorithm for these settings) - the generated ids pin the oracle's restatement."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = O.OracleConfig(**CASES["tiny_masks_gqa"][0])
+    sd = O.make_weights(cfg, seed=BEAM_WEIGHT_SEED)
+    lcfg = LlamaConfig(hidden_size=cfg.hidden, intermediate_size=cfg.inter, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+                       num_key_value_heads=cfg.kv_heads, vocab_size=cfg.vocab, rms_norm_eps=cfg.rms_eps, rope_theta=cfg.rope_theta,
+                       max_position_embeddings=4096, tie_word_embeddings=False, head_dim=cfg.head_dim, attention_bias=False, mlp_bias=False,
+                       bos_token_id=1, eos_token_id=None, pad_token_id=None)
+    lcfg._attn_implementation = "eager"
+    llm = LlamaForCausalLM(lcfg).float().eval()
+    llm.load_state_dict({k: v.float() for k, v in sd["llm"].items()}, strict=True)
+    g = torch.Generator().manual_seed(0)
+    emb = (torch.randn(20, cfg.hidden, generator=g) * 0.3).to(torch.bfloat16).float()
+    arrays = {"inputs_embeds": emb.numpy(), "weight_seed": np.int64(BEAM_WEIGHT_SEED)}
+    for i, (nb, eos, n_new, lp, es) in enumerate(BEAM_CASES):
+        out = llm.generate(inputs_embeds=emb[None], num_beams=nb, do_sample=False, max_new_tokens=n_new, eos_token_id=eos, pad_token_id=0,
+                           early_stopping=es, length_penalty=lp, num_return_sequences=1)[0]
+        arrays[f"case{i}"] = out.numpy()
+        print(i, nb, eos, n_new, lp, es, out.tolist())
+    path = os.path.join(HERE, "beam_kats.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"beam_kats -> {path}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["beam"]:
+        run_beam_kats()
+        sys.exit(0)
     if sys.argv[1:] == ["rope"]:
         run_rope_kat()
         sys.exit(0)
@@ -341,3 +380,4 @@ if __name__ == "__main__":
     run_projector_kats()
     run_clip_kat()
     run_rope_kat()
+    run_beam_kats()

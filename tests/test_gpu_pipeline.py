@@ -127,8 +127,6 @@ def test_eos_and_stopping_criteria(golden_dir):
             return output_ids.shape[1] >= 2
     ids = model.generate(input_ids.to(DEV), stopping_criteria=[StopAfter()], **kwargs)
     assert ids[0].tolist() == ref[:2]
-    with pytest.raises(NotImplementedError):
-        model.generate(input_ids.to(DEV), num_beams=4, **kwargs)
 
 
 def test_text_only_and_no_mask_image():
@@ -390,6 +388,12 @@ def test_linear_rope_scaling_generate_matches_oracle(golden_dir):
     assert safe >= 1 and ids[0, :safe].tolist() == ref_ids[:safe].tolist()
     err = (logits[0][:safe].cpu() - enc["logits"][:safe]).abs().max().item()
     assert err <= 0.06 * sigma
-    # the scaling really changes the computation: without it the logits of the first step differ by far more than the tolerance
-    _, enc0 = O.generate(O.OracleConfig(**kw), sd, input_ids, images, depths, masks, 1, return_all=True)
-    assert (enc0["logits"][0] - enc["logits"][0]).abs().max().item() > 0.2 * sigma
+    # the tables the kernels read are the scaled ones (bit-exact against the reference's rotary class on the CPU side:
+    # tests/test_oracle_golden.py::test_rope_tables_match_reference_rotary_classes); at these sizes the logits move by less than the
+    # tolerance when the scaling is dropped, so the discriminating check is on the tables themselves
+    from spatialrgpt_b200.config import LlamaDims
+    from spatialrgpt_b200.llama_decoder import build_rope_tables
+    d = model.config.llama
+    want = build_rope_tables(LlamaDims(head_dim=d.head_dim, rope_theta=d.rope_theta, rope_scaling_factor=4.0), 512, "cpu", torch.bfloat16)
+    plain = build_rope_tables(LlamaDims(head_dim=d.head_dim, rope_theta=d.rope_theta), 512, "cpu", torch.bfloat16)
+    assert torch.equal(model.llm.cos.cpu(), want[0]) and torch.equal(model.llm.sin.cpu(), want[1]) and not torch.equal(want[0], plain[0])

@@ -92,6 +92,21 @@ def test_depth_to_u8x3():
     assert torch.equal(out[..., 0], out[..., 2])
 
 
+def test_beam_search_matches_hf_generate(golden_dir):
+    """The oracle's restatement of HF beam search against ``LlamaForCausalLM.generate(inputs_embeds=..., num_beams=k)`` on the same
+    seeded weights (fixture by ``make_golden.py beam``): plain beams, EOS-closed hypotheses, length penalties, early stopping."""
+    from tests.golden.make_golden import BEAM_CASES, CASES as C2
+    g = load_npz(os.path.join(golden_dir, "beam_kats.npz"))
+    oc = O.OracleConfig(**C2["tiny_masks_gqa"][0])
+    sd = O.make_weights(oc, seed=int(g["weight_seed"]))
+    for i, (nb, eos, n_new, lp, es) in enumerate(BEAM_CASES):
+        ids = O.beam_search_generate(oc, sd["llm"], g["inputs_embeds"], nb, n_new, eos_token_id=eos, length_penalty=lp, early_stopping=es)
+        ref = g[f"case{i}"].tolist()
+        assert ids.tolist() == ref[: len(ids)], (i, ids.tolist(), ref)
+        assert all(t == 0 for t in ref[len(ids):])  # HF pads a shorter best hypothesis with pad_token_id (0 in the fixture)
+    assert O.beam_search_generate(oc, sd["llm"], g["inputs_embeds"], 1, 10).tolist() == O.greedy_generate(oc, sd["llm"], g["inputs_embeds"], 10).tolist()
+
+
 def test_rope_tables_match_reference_rotary_classes(golden_dir):
     """cos / sin of LlamaRotaryEmbedding and LlamaLinearScalingRotaryEmbedding (modeling_llama.py:81-141; fixture by
     ``make_golden.py rope``): the oracle's restatement and the host-side table builder of the product path, fp32 and bf16."""
