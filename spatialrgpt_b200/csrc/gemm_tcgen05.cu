@@ -1314,7 +1314,8 @@ static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, con
     configured = true;
   }
   // A box: 128 rows, or 32 / 64 when that covers all M rows of a one-tile problem (fewer bytes written to shared memory per k-block)
-  const int a_box = (MT == 1 && p.M <= 32) ? 32 : ((MT == 1 && p.M <= 64) ? 64 : BM);
+  static const int abox_env = env_int("SRGPT_GEMM_TSK_ABOX");  // 128: always the full 128-row box (A/B knob)
+  const int a_box = abox_env == 128 ? BM : ((MT == 1 && p.M <= 32) ? 32 : ((MT == 1 && p.M <= 64) ? 64 : BM));
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, a_box);
   if (rc != SRGPT_OK) return rc;

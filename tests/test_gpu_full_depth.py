@@ -26,4 +26,6 @@ def test_c2_full_depth_matches_oracle_fixture(golden_dir):
     assert not fails, fails
     # `fails` already holds the id rule (ids must agree wherever the oracle's margin exceeds 4 x the rms noise).  Near-ties are free to
     # flip with any change of summation order: step 2 of the fixture has a margin of 0.11 logits under an rms noise of 0.2.
-    assert report["steps_compared_vs_fp32"] >= 3 and report["steps_equal_to_bf16_oracle"] >= report["steps_id_must_agree_bf16"]
+    # (the fixture's steps 1 and 2 have margins of 0.27 and 0.11 logits: any change of an fp32 summation order - e.g. the region projector
+    # GEMMs moving from split-k partials to whole tiles - may move the sequence off the oracle's there; step 0, margin 1.76, is robust)
+    assert report["steps_compared_vs_fp32"] >= 2 and report["steps_equal_to_bf16_oracle"] >= report["steps_id_must_agree_bf16"]
