@@ -1314,8 +1314,8 @@ static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, con
     configured = true;
   }
   // A box: 128 rows, or 32 / 64 when that covers all M rows of a one-tile problem (fewer bytes written to shared memory per k-block)
-  static const int abox_env = env_int("SRGPT_GEMM_TSK_ABOX");  // 128: always the full 128-row box (A/B knob)
-  const int a_box = abox_env == 128 ? BM : ((MT == 1 && p.M <= 32) ? 32 : ((MT == 1 && p.M <= 64) ? 64 : BM));
+  // the small boxes only in the (opt-in) whole-tile mode; with the stream-K split they measured the same as the full box
+  const int a_box = whole_grid <= 0 ? BM : ((MT == 1 && p.M <= 32) ? 32 : ((MT == 1 && p.M <= 64) ? 64 : BM));
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, p.M, p.K, lda, a_box);
   if (rc != SRGPT_OK) return rc;
@@ -1352,12 +1352,15 @@ static int launch_tall_sk_mt(const void* A, int lda, const void* W, int ldw, con
 // 52 / 36).  Without a k-split nothing is exchanged; what fills the chip instead is a NARROWER weight tile: BN is chosen per problem from
 // {128, 64, 32} by a two-term cost model - HBM time of the weights vs waves x per-SM TMA ingest (~88 GB/s, DESIGN.md "GEMM: what bounds
 // it") of one tile's weight + activation bytes - and the grid is the balanced whole-tile count ceil(tiles / waves).
-// SRGPT_GEMM_TSK_WHOLE=-1 restores the stream-K split (A/B knob).
+// MEASURED SLOWER (profiles/r02_ab_batched_decode_skinny.txt, 32 sequences: 7.18 ms per step against 6.24 ms with the stream-K split;
+// launch list: the BN = 32 o_proj / down GEMMs average 47 us against 34 us): a 32-row weight box is 4 KB, so the nine stages hold 72 KB of
+// real data per SM instead of 192 KB and the TMA request rate, not the byte rate, bounds the stream - the cost model above is wrong about
+// small boxes.  The stream-K split therefore stays the default; SRGPT_GEMM_TSK_WHOLE=1 keeps this configuration reproducible.
 template <int EPI>
 static int launch_skinny(const void* A, int lda, const void* W, int ldw, const Params& p, cudaStream_t stream, bool* handled) {
   static const int whole_env = env_int("SRGPT_GEMM_TSK_WHOLE");
   *handled = false;
-  if (whole_env < 0 || p.M > BM) return SRGPT_OK;
+  if (whole_env <= 0 || p.M > BM) return SRGPT_OK;  // opt-in (SRGPT_GEMM_TSK_WHOLE=1): measured slower, see above
   const int sms = sm_count();
   const double hbm_s = (double)p.N * p.K * 2 / 6.4e12;
   int best_bn = 0, best_grid = 0;

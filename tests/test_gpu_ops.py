@@ -91,7 +91,7 @@ def test_gemm_cluster_multicast_path():
         "import torch\n"
         "from spatialrgpt_b200 import ops\n"
         "g = torch.Generator().manual_seed(0)\n"
-        "for (M, N, K) in [(259, 640, 512), (1024, 1152, 1152), (4096, 4608, 320), (300, 4304, 1152), (32, 4096, 4096), (100, 1536, 4096)]:\n"
+        "for (M, N, K) in [(259, 640, 512), (1024, 1152, 1152), (4096, 4608, 320), (300, 4304, 1152), (32, 4096, 4096), (100, 1536, 4096), (32, 6144, 4096), (32, 28672, 4096)]:\n"
         "    a = torch.randn(M, K, generator=g).bfloat16(); w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()\n"
         "    out = ops.gemm(a.cuda(), w.cuda(), out_fp32=True).cpu()\n"
         "    ref = a.float() @ w.float().t()\n"
@@ -104,7 +104,7 @@ def test_gemm_cluster_multicast_path():
     # (non-TMA-store) epilogue
     for knob, val in (("SRGPT_GEMM_CL", "2"), ("SRGPT_GEMM_TALL", "1"), ("SRGPT_GEMM_GM", "3"), ("SRGPT_GEMM_PAIR", "1"),
                       ("SRGPT_GEMM_EW", "16"), ("SRGPT_GEMM_TSK", "1"), ("SRGPT_GEMM_TSK", "-1"), ("SRGPT_GEMM_DIRECT_EPI", "1"),
-                      ("SRGPT_GEMM_TSK_WHOLE", "-1")):  # the stream-K split at M <= 128 instead of whole narrow tiles
+                      ("SRGPT_GEMM_TSK_WHOLE", "1")):  # whole narrow weight tiles at M <= 128 instead of the stream-K split
         env = dict(os.environ, **{knob: val})
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -114,7 +114,7 @@ def test_gemm_cluster_multicast_path():
 @pytest.mark.parametrize("M,N,K,epi", [(259, 6144, 4096, "none"), (259, 4096, 14336, "residual"), (259, 28672, 4096, "swiglu"),
                                        (300, 4608, 1152, "gelu_erf"), (100, 20008, 1024, "bias"), (384, 1000, 4096, "none"),
                                        (130, 520, 8200, "residual"), (3, 128259, 4096, "none"),
-                                       # one-tile-high problems of a batched decode step: whole narrow tiles (BN 32 / 64 / 128 by the cost model)
+                                       # one-tile-high problems of a batched decode step (stream-K split; whole narrow tiles under SRGPT_GEMM_TSK_WHOLE=1)
                                        (32, 4096, 4096, "residual"), (32, 6144, 4096, "none"), (32, 28672, 4096, "swiglu"),
                                        (32, 4096, 14336, "residual"), (17, 1000, 4096, "bias"), (64, 4096, 4096, "gelu_erf"),
                                        (128, 4104, 2048, "residual"), (5, 1003, 512, "none")])
