@@ -400,8 +400,8 @@ def cpu_reference_sample(decode_tokens: int = 6):
         one = O.OracleConfig(v_layers=1, layers=1)
         tab = w["llm"]["model.embed_tokens.weight"]
         best = (None, 1e30)
-        # score = the request's own mix (127 decode rows + one 259-row prompt through a layer), best of 3 repetitions per
-        # candidate: a single noisy probe picked 8 threads in one run and 16 in the next on the same box (2.9 vs 4.6 tokens/s)
+        # score = the request's own mix: 127 x one FULL-DEPTH decode token (all 32 layers, best of 3) + the 259-row prompt (one layer,
+        # best of 2, x 32).  One-layer probes of a few ms picked 8, 16 or 32 threads at random on the same box (2.9 .. 4.7 tokens/s)
         for t in sorted({cores, 64, 32, 16, 8}):
             if t > cores:
                 continue
@@ -411,11 +411,12 @@ def cpu_reference_sample(decode_tokens: int = 6):
                 O.llama_forward(one, w["llm"], tab[5][None], None)
                 for _ in range(3):
                     t0 = time.perf_counter()
-                    O.llama_forward(one, w["llm"], tab[5][None], None)
-                    t1 = time.perf_counter()
+                    O.llama_forward(oc, w["llm"], tab[5][None], None)
+                    t_dec = min(t_dec, time.perf_counter() - t0)
+                for _ in range(2):
+                    t0 = time.perf_counter()
                     O.llama_forward(one, w["llm"], tab[:259], None)
-                    t2 = time.perf_counter()
-                    t_dec, t_pre = min(t_dec, t1 - t0), min(t_pre, t2 - t1)
+                    t_pre = min(t_pre, (time.perf_counter() - t0) * oc.layers)
             dt = (NEW_TOKENS - 1) * t_dec + t_pre
             if dt < best[1]:
                 best = (t, dt)
