@@ -151,10 +151,27 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    # NCCL's log (incl. the "nranks N" init lines the driver reads) goes to stderr, never stdout: rank 0 prints ONE JSON line
+    # NCCL's log (incl. the "nranks N" init lines the driver reads) must reach stderr, never stdout: rank 0 prints ONE JSON line.
+    # NCCL_DEBUG_FILE=/dev/stderr does NOT do that when stderr is a file (NCCL fopen()s it with "w": every rank truncates the
+    # shared file and the log is lost - seen on the 2-GPU pre-flight), so each rank logs to its own temporary file and copies it to
+    # stderr when it is done.  A caller who sets NCCL_DEBUG_FILE keeps their own destination.
     os.environ.setdefault("NCCL_DEBUG", "INFO")
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    nccl_log = None
+    if world > 1 and "NCCL_DEBUG_FILE" not in os.environ:
+        import tempfile
+        nccl_log = os.path.join(tempfile.gettempdir(), f"srgpt_nccl_rank{rank}_{os.getpid()}.log")
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
+
+    def forward_nccl_log():
+        if nccl_log is not None and os.path.exists(nccl_log):
+            try:
+                with open(nccl_log, errors="replace") as f:
+                    sys.stderr.write(f.read())
+                sys.stderr.flush()
+                os.remove(nccl_log)
+            except OSError:
+                pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -325,6 +342,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        forward_nccl_log()
         return
     cpu = cpu_reference_sample()
     line = {
@@ -355,6 +373,7 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    forward_nccl_log()
 
 
 # --------------------------------------------------------------------------------------------------
