@@ -155,8 +155,11 @@ def run_ours(args):
     # NCCL_DEBUG_FILE=/dev/stderr does NOT do that when stderr is a file (NCCL fopen()s it with "w": every rank truncates the
     # shared file and the log is lost - seen on the 2-GPU pre-flight), so each rank logs to its own temporary file and copies it to
     # stderr when it is done.  A caller who sets NCCL_DEBUG_FILE keeps their own destination.
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    # The GPU boxes export NCCL_DEBUG=VERSION, which prints only a version banner (to stdout): levels below INFO are raised to
+    # INFO / INIT so that the communicator's "rank r nranks N" lines exist; a caller's INFO / TRACE setting is kept.
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     nccl_log = None
     if world > 1 and "NCCL_DEBUG_FILE" not in os.environ:
         import tempfile
