@@ -66,6 +66,9 @@ def _vision_config(d: Dict[str, Any]) -> VisionConfig:
     d = d.get("vision_config", d)  # a full SiglipConfig / CLIPConfig nests the vision part
     mt = d.get("model_type") or ""
     is_clip = ("clip" in arch or "clip" in mt) and "siglip" not in (arch + mt)  # multimodal_encoder/builder.py:38-47 keys on the architecture name
+    for other in ("intern", "radio"):  # multimodal_encoder/builder.py:27-35: towers of other model families (out of scope)
+        if other in arch or other in mt:
+            raise NotImplementedError(f"vision tower family {other!r} is outside the SpatialRGPT generate() path (SigLIP and CLIP towers are built)")
     if is_clip:
         return VisionConfig(image_size=d.get("image_size", 224), patch_size=d.get("patch_size", 32), hidden_size=d.get("hidden_size", 768),
                             num_hidden_layers=d.get("num_hidden_layers", 12), num_attention_heads=d.get("num_attention_heads", 12),
@@ -131,6 +134,8 @@ def read_checkpoint(model_path: str, load_tokenizer: bool = True):
     enable_region = bool(top.get("enable_region", False))
     re_cfg = _read_json(os.path.join(paths["region_extractor"], "config.json")) if enable_region else {}
 
+    if top.get("s2"):
+        raise NotImplementedError("S2 multi-scale tower wrappers (CLIPVisionTowerS2 / SiglipVisionTowerS2, multimodal_encoder/builder.py:36-47)")
     cfg = LlavaConfig(
         model_type=top.get("model_type", "llava_llama"), architectures=tuple(top.get("architectures", ("LlavaLlamaModel",))),
         resume_path=model_path, image_aspect_ratio=top.get("image_aspect_ratio", "resize"),

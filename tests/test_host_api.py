@@ -197,6 +197,16 @@ def test_rope_scaling_config_is_read_like_the_reference():
         _llama_dims({**base, "rope_scaling": {"type": "yarn", "factor": 2.0}})
 
 
+def test_unsupported_tower_families_raise_at_the_loader():
+    from spatialrgpt_b200.builder import _vision_config
+    base = {"image_size": 448, "patch_size": 14, "hidden_size": 64, "num_hidden_layers": 2, "num_attention_heads": 2, "intermediate_size": 128}
+    assert not _vision_config({**base, "architectures": ["SiglipVisionModel"]}).is_clip
+    assert _vision_config({**base, "architectures": ["CLIPVisionModel"]}).is_clip
+    for arch in ("InternVisionModel", "RADIOModel"):
+        with pytest.raises(NotImplementedError):
+            _vision_config({**base, "architectures": [arch]})
+
+
 def test_clip_checkpoint_reads_back_as_a_clip_tower(tmp_path):
     """multimodal_encoder/builder.py:38-47 picks the tower class from the vision config's architecture name; a checkpoint whose
     vision_tower/ holds a CLIPVisionModel parses as a CLIP tower ("patch" select, quick_gelu, class token + pre_layrnorm weights)."""
