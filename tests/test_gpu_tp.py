@@ -35,7 +35,8 @@ def test_tp_world1_equals_plain_decoder():
         model.generate(ids.to(DEV), images=a["images"], depths=a["depths"], masks=a["masks"], do_sample=True, temperature=0.8, max_new_tokens=4)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run by hand with gpurun --gpus 2)")
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("SRGPT_RUN_TP2_TEST") != "1",
+                    reason="needs 2 GPUs and SRGPT_RUN_TP2_TEST=1 (a torchrun child of 2 ranks; run by hand: gpurun --gpus 2, tools/gpu_job_tp.sh 2)")
 def test_tp2_ids_equal_tp1_under_torchrun():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
