@@ -120,6 +120,70 @@ def process_regions(masks: Sequence[np.ndarray], image_processor, data_args, dev
     return torch.vstack(rows).float()
 
 
+def process_masks(sources, data_args, image_info=None) -> torch.Tensor:
+    """mm_utils.py:279-375 (the dataset-side twin of process_regions, data/dataset.py:1760): regions given as COCO run-length masks
+    ("rle"), polygons ("segmentation") or boxes ("bbox") in ``sources[0]`` -> float tensor [M, R, R].  Like the reference, ONE of
+    the modalities present is drawn with ``random.choice`` (the global generator), the uint8 masks are resized with
+    cv2.INTER_NEAREST ("resize") or zero-padded to a square ("pad") and then go through the mask processor (no normalisation, no
+    rescale).  Run-length masks are decoded by this package's own COCO RLE decoder (eval_spatial.rle_decode); polygons need
+    pycocotools' rasteriser and raise without it."""
+    import random
+
+    import cv2
+
+    mp = _mask_processor(data_args.image_processor)
+    modality = random.choice([m for m in ("rle", "segmentation", "bbox") if m in sources[0].keys()])
+    mode = getattr(data_args, "image_aspect_ratio", None)
+    size = _target_size(data_args.image_processor) if mode == "resize" else None
+
+    def fit(m: np.ndarray) -> np.ndarray:
+        if mode == "resize":
+            m = cv2.resize(m, (size["width"], size["height"]), interpolation=cv2.INTER_NEAREST)
+        if mode == "pad":
+            m = _pad_to_square(m)
+        return m
+
+    masks = []
+    if modality == "rle":
+        from .eval_spatial import rle_decode
+        masks = [fit(rle_decode(r).astype(np.uint8)) for r in sources[0]["rle"]]
+    elif modality == "segmentation":
+        try:
+            from pycocotools import mask as cocomask
+        except ImportError as e:
+            raise NotImplementedError("polygon regions are rasterised by pycocotools (mm_utils.py:335-346), which is not installed") from e
+        info = sources[0]["image_info"]
+        for poly in sources[0]["segmentation"]:
+            m = np.sum(cocomask.decode(cocomask.frPyObjects(poly, info["height"], info["width"])), axis=2)
+            masks.append(fit(m.astype(np.uint8)))
+    else:
+        info = image_info if image_info is not None else sources[0]["image_info"]
+        masks = [fit(m) for m in boxes_to_masks(sources[0]["bbox"], info["height"], info["width"])]
+    rows = [mp.preprocess(m[None, ...], return_tensors="pt")["pixel_values"][0] for m in masks]
+    return torch.vstack(rows).float()
+
+
+def process_depth(depth_file, data_args, depth_folder=None) -> torch.Tensor:
+    """mm_utils.py:377-418: a (pre-normalised) depth image through the image path - plain ``Image.resize`` to the tower size for
+    "resize" (PIL's default filter, like process_image), mean-colour square padding for "pad", then the HF processor."""
+    import os
+
+    from PIL import Image
+
+    processor = data_args.image_processor
+    if isinstance(depth_file, str):
+        depth = Image.open(os.path.join(depth_folder, depth_file) if depth_folder is not None else depth_file)
+    else:
+        depth = depth_file
+    mode = getattr(data_args, "image_aspect_ratio", None)
+    if mode == "resize":
+        size = _target_size(processor)
+        depth = depth.resize((size["height"], size["width"]))
+    if mode == "pad":
+        depth = _expand2square(depth, tuple(int(x * 255) for x in processor.image_mean))
+    return processor.preprocess(depth, return_tensors="pt")["pixel_values"][0]
+
+
 def boxes_to_masks(bboxes, image_h: int, image_w: int) -> List[np.ndarray]:
     """Box regions as the reference builds them (mm_utils.py:349-364, eval_spatial.py:158-161): clamp,
     then fill [y1:y2, x1:x2] with ones."""

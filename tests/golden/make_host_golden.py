@@ -84,6 +84,62 @@ def make_preproc_golden(RM):
     print("wrote host_preproc.npz:", {k: v.shape for k, v in out.items()})
 
 
+def masks_depth_inputs():
+    """Region sources in the dataset's three forms (one per call so that random.choice has a single option) and a depth image."""
+    import numpy as np
+    from PIL import Image
+
+    from spatialrgpt_b200.eval_spatial import rle_encode_counts
+    rng = np.random.RandomState(11)
+    H, W = 45, 80
+    info = {"height": H, "width": W}
+    boxes = [[3, 4, 40, 30], [-5, 10, 90, 44], [60, 0, 70, 45]]
+    rles = []
+    for _ in range(2):
+        m = np.zeros((H, W), dtype=np.uint8)
+        y0, x0 = rng.randint(0, H // 2), rng.randint(0, W // 2)
+        m[y0:y0 + 17, x0:x0 + 23] = 1
+        flat = m.flatten(order="F")  # COCO RLE is column-major
+        counts, cur, run = [], 0, 0
+        for v in flat:
+            if v == cur:
+                run += 1
+            else:
+                counts.append(run); cur, run = v, 1
+        counts.append(run)
+        rles.append({"size": [H, W], "counts": rle_encode_counts(counts)})
+    low = rng.randint(0, 255, (H // 5 + 1, W // 5 + 1), dtype=np.uint8)
+    depth = Image.fromarray(np.repeat(np.asarray(Image.fromarray(low).resize((W, H), Image.BILINEAR))[:, :, None], 3, axis=2))
+    return info, boxes, rles, depth
+
+
+def make_masks_depth_golden(RM):
+    """process_masks (bbox and rle modalities) and process_depth of the REFERENCE (llava/mm_utils.py:279-418), both aspect modes.
+    pycocotools is not installed here: for the rle modality the reference's ``cocomask.decode`` is served by this repo's COCO RLE
+    decoder, so that case pins everything AFTER the decode (nearest resize / padding / mask processor), not the decoder itself
+    (tests/test_eval_driver_cpu.py checks the decoder against hand-built masks)."""
+    import numpy as np
+    from types import SimpleNamespace
+    from transformers import SiglipImageProcessor
+
+    from spatialrgpt_b200.eval_spatial import rle_decode
+    sys.modules["pycocotools"].mask.decode = rle_decode
+    RM.cocomask.decode = rle_decode
+    info, boxes, rles, depth = masks_depth_inputs()
+    out = {}
+    for mode in ("resize", "pad"):
+        proc = SiglipImageProcessor(size={"height": 56, "width": 56})
+        if getattr(proc, "crop_size", None) is None and "crop_size" in vars(proc):
+            delattr(proc, "crop_size")
+        cfg = SimpleNamespace(image_aspect_ratio=mode, image_processor=proc)
+        out[f"masks_bbox_{mode}"] = RM.process_masks([{"bbox": boxes, "image_info": info}], cfg).numpy()
+        out[f"masks_bbox_info_{mode}"] = RM.process_masks([{"bbox": boxes}], cfg, image_info=info).numpy()
+        out[f"masks_rle_{mode}"] = RM.process_masks([{"rle": rles}], cfg).numpy()
+        out[f"depth_{mode}"] = RM.process_depth(depth, cfg, None).numpy()
+    np.savez_compressed(os.path.join(HERE, "host_masks_depth.npz"), **out)
+    print("wrote host_masks_depth.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main():
     ref_shim.install()
     from llava import conversation as RC
@@ -113,6 +169,7 @@ def main():
     out["stopping_ids"] = base
     out["model_names"] = {p: RM.get_model_name_from_path(p) for p in ["a/b/SpatialRGPT-VILA1.5-8B", "x/run1/checkpoint-500/", "solo"]}
     make_preproc_golden(RM)
+    make_masks_depth_golden(RM)
     with open(os.path.join(HERE, "host_api.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote host_api.json:", {k: len(v) for k, v in out.items()})

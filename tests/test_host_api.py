@@ -182,6 +182,36 @@ def test_read_checkpoint_with_tokenizer_registers_special_tokens(tmp_path):
     assert not cfg.mm_use_im_patch_token and tok.convert_tokens_to_ids("<im_patch>") in (None, tok.unk_token_id)
 
 
+def test_process_masks_and_process_depth_match_reference():
+    """mm_utils.py:279-418 (the dataset-side region / depth preparation) against outputs of the reference's own functions
+    (tests/golden/host_masks_depth.npz by make_host_golden.py): box, box + external image_info and run-length regions, a depth image,
+    both aspect modes; the modality draw uses the global ``random`` generator like the reference."""
+    import random
+    from types import SimpleNamespace
+
+    from transformers import SiglipImageProcessor
+
+    from spatialrgpt_b200 import mm_utils as M
+    from tests.golden.make_host_golden import masks_depth_inputs
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "host_masks_depth.npz"))
+    info, boxes, rles, depth = masks_depth_inputs()
+    for mode in ("resize", "pad"):
+        proc = SiglipImageProcessor(size={"height": 56, "width": 56})
+        if getattr(proc, "crop_size", None) is None and "crop_size" in vars(proc):
+            delattr(proc, "crop_size")
+        cfg = SimpleNamespace(image_aspect_ratio=mode, image_processor=proc)
+        assert np.array_equal(M.process_masks([{"bbox": boxes, "image_info": info}], cfg).numpy(), g[f"masks_bbox_{mode}"])
+        assert np.array_equal(M.process_masks([{"bbox": boxes}], cfg, image_info=info).numpy(), g[f"masks_bbox_info_{mode}"])
+        assert np.array_equal(M.process_masks([{"rle": rles}], cfg).numpy(), g[f"masks_rle_{mode}"])
+        assert np.array_equal(M.process_depth(depth, cfg, None).numpy(), g[f"depth_{mode}"])  # same PIL / HF processor underneath -> exact
+        # both modalities present: one is drawn with random.choice (seeded here); either way the result is one of the two fixtures
+        random.seed(3)
+        both = M.process_masks([{"bbox": boxes[:2], "rle": rles, "image_info": info}], cfg).numpy()
+        assert np.array_equal(both, g[f"masks_rle_{mode}"]) or np.array_equal(both, g[f"masks_bbox_{mode}"][:2])
+    with pytest.raises(NotImplementedError):
+        M.process_masks([{"segmentation": [[[1, 1, 5, 1, 5, 5]]], "image_info": info}], cfg)
+
+
 def test_rope_scaling_config_is_read_like_the_reference():
     """modeling_llama.py:267-292 (rope_scaling type linear / dynamic / unknown) and the loader's own context extension
     (language_model/builder.py:31-38: model_max_length > max_position_embeddings -> linear, factor = ceil(ratio))."""
