@@ -27,16 +27,36 @@ def _target_size(image_processor) -> dict:
     return image_processor.size
 
 
-def _expand2square(pil_img, background_color):
+def expand2square(pil_img, background_color):
+    """mm_utils.py:249-276: pad to a square with ``background_color`` (its first component for mode "L"), image centred."""
     from PIL import Image
 
     w, h = pil_img.size
+    if pil_img.mode == "L":
+        background_color = background_color[0]
     if w == h:
         return pil_img
     side = max(w, h)
     result = Image.new(pil_img.mode, (side, side), background_color)
     result.paste(pil_img, ((side - w) // 2, (side - h) // 2))
     return result
+
+
+_expand2square = expand2square
+
+
+def load_image_from_base64(image):
+    """mm_utils.py:245-246."""
+    import base64
+    from io import BytesIO
+
+    from PIL import Image
+    return Image.open(BytesIO(base64.b64decode(image)))
+
+
+def is_gemma_tokenizer(tokenizer) -> bool:
+    """mm_utils.py:573-574."""
+    return "gemma" in tokenizer.__class__.__name__.lower()
 
 
 def process_image(image_file, data_args, image_folder=None, return_info: bool = False):

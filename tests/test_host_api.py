@@ -212,6 +212,28 @@ def test_process_masks_and_process_depth_match_reference():
         M.process_masks([{"segmentation": [[[1, 1, 5, 1, 5, 5]]], "image_info": info}], cfg)
 
 
+def test_small_image_helpers():
+    """expand2square (mm_utils.py:249-276, incl. mode "L"), load_image_from_base64 (245-246), is_gemma_tokenizer (573-574)."""
+    import base64
+    from io import BytesIO
+
+    from PIL import Image
+
+    from llava.mm_utils import expand2square, is_gemma_tokenizer, load_image_from_base64
+    im = Image.fromarray(np.full((4, 10, 3), 200, dtype=np.uint8))
+    sq = expand2square(im, (10, 20, 30))
+    a = np.asarray(sq)
+    assert sq.size == (10, 10) and (a[:3] == (10, 20, 30)).all() and (a[3:7] == 200).all() and (a[7:] == (10, 20, 30)).all()
+    tall = np.asarray(expand2square(Image.fromarray(np.full((9, 4), 7, dtype=np.uint8), mode="L"), (99, 1, 1)))
+    assert tall.shape == (9, 9) and (tall[:, :2] == 99).all() and (tall[:, 2:6] == 7).all() and (tall[:, 6:] == 99).all()
+    assert expand2square(sq, (0, 0, 0)) is sq
+    buf = BytesIO()
+    im.save(buf, format="PNG")
+    back = load_image_from_base64(base64.b64encode(buf.getvalue()))
+    assert np.array_equal(np.asarray(back), np.asarray(im))
+    assert is_gemma_tokenizer(type("GemmaTokenizerFast", (), {})()) and not is_gemma_tokenizer(ToyTokenizer())
+
+
 def test_rope_scaling_config_is_read_like_the_reference():
     """modeling_llama.py:267-292 (rope_scaling type linear / dynamic / unknown) and the loader's own context extension
     (language_model/builder.py:31-38: model_max_length > max_position_embeddings -> linear, factor = ceil(ratio))."""
